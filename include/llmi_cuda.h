@@ -1,0 +1,158 @@
+/* llmi_cuda.h — C ABI of libllmi_cuda.so, the B200 (sm_100a) implementation of
+ * llm_inference's quantized mat-vec hot path.
+ *
+ * The reference (corywalker/llm_inference) has no FFI: its operator boundary is
+ * the set of free functions in ops.h, called from model.cpp.  This header is
+ * the C boundary underneath a drop-in for those functions
+ * (llm_inference_b200/host/ops_cuda.cpp defines the very same C++ symbols and
+ * forwards here).  Every entry point cites the reference interface it replaces.
+ *
+ * Conventions: plain pointers and sizes only; every function returns an int
+ * status (LLMI_OK == 0) and never throws; llmi_last_error() gives the message
+ * of the last failure on the calling thread.  One host thread drives a device
+ * (the reference's ops are not re-entrant either: ops.cpp:18-19).  "dev"
+ * pointers are CUDA device pointers; streams are cudaStream_t passed as void*.
+ * All device-tier calls are stream-ordered and CUDA-graph capturable.
+ *
+ * There is NO CPU fallback: without a CUDA device every compute entry point
+ * fails with LLMI_ERR_CUDA.
+ */
+#ifndef LLMI_CUDA_H
+#define LLMI_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LLMI_ABI_VERSION 1
+
+enum llmi_status {
+  LLMI_OK = 0,
+  LLMI_ERR_ARG = 1,         /* null pointer, bad range, K not a block multiple */
+  LLMI_ERR_TYPE = 2,        /* "mat_vec_mul: unsupported tensor type N" (ops.cpp:953) */
+  LLMI_ERR_SIZE = 3,        /* "...: input vector size mismatch" (ops.cpp:197 etc.) */
+  LLMI_ERR_CUDA = 4,        /* CUDA runtime/driver failure, or no device */
+  LLMI_ERR_STATE = 5        /* llmi_init not called, activation not prepared ... */
+};
+
+/* ggml tensor type ids as stored in GGUF (gguf.h:30-46) */
+enum llmi_type {
+  LLMI_F32 = 0, LLMI_F16 = 1, LLMI_Q4_0 = 2, LLMI_Q5_0 = 6, LLMI_Q8_0 = 8,
+  LLMI_Q4_K = 12, LLMI_Q6_K = 14, LLMI_BF16 = 30
+};
+
+typedef struct llmi_weight_s* llmi_weight_t; /* one uploaded, repacked matrix */
+typedef struct llmi_act_s* llmi_act_t;       /* one quantized activation vector */
+typedef void* llmi_stream_t;                 /* cudaStream_t */
+
+/* ---- lifecycle -------------------------------------------------------- */
+
+/* Replaces init_ops(int n_threads) (ops.h:38, ops.cpp:21-24): instead of a
+ * thread pool, selects the CUDA device and creates the library context.  Must
+ * be called before anything else; idempotent for the same device. */
+int llmi_init(int device);
+int llmi_shutdown(void);
+const char* llmi_last_error(void);
+int llmi_abi_version(void);
+/* number of SMs of the active device (grid sizing is exposed for benches) */
+int llmi_sm_count(void);
+
+/* ---- weights ---------------------------------------------------------- */
+
+/* Replaces GGUFFile::get_tensor_data + per-call row pointer math
+ * (gguf.cpp:354-356, ops.cpp:206,221): uploads rows [row_begin,row_end) of a
+ * K=n_cols x N=n_rows matrix stored in the reference/GGUF block layout
+ * (row r at host_blocks + r*row_bytes, dense) ONCE and repacks it on the device
+ * into 16-byte-aligned quant / scale planes ("slab layout").
+ * host_blocks may be unaligned (GGUF tensor offsets are not, model_test.cpp:377).
+ * The full range [0,n_rows) is the single-GPU case; a sub-range is one rank's
+ * shard of an output-row-sharded matrix (the multi-GPU image of the thread
+ * partition at ops.cpp:439-448). */
+int llmi_weight_upload(const void* host_blocks, uint32_t ggml_type,
+                       uint64_t n_cols, uint64_t n_rows, uint64_t row_begin,
+                       uint64_t row_end, llmi_weight_t* out);
+int llmi_weight_free(llmi_weight_t w);
+int llmi_weight_dims(llmi_weight_t w, uint32_t* ggml_type, uint64_t* n_cols,
+                     uint64_t* n_rows, uint64_t* row_begin, uint64_t* row_end);
+uint64_t llmi_weight_device_bytes(llmi_weight_t w);
+/* bytes of one weight row in the reference layout (0 = unsupported / bad K) */
+uint64_t llmi_row_bytes(uint32_t ggml_type, uint64_t n_cols);
+
+/* Registry keyed by the host pointer of the blocks, for callers that only hold
+ * (TensorInfo, GGUFFile) like ops.h's mat_vec_mul: first use uploads, later
+ * uses hit the cache.  Lifetime = until llmi_registry_clear()/llmi_shutdown(). */
+int llmi_registry_get(const void* host_blocks, uint32_t ggml_type,
+                      uint64_t n_cols, uint64_t n_rows, llmi_weight_t* out);
+int llmi_registry_clear(void);
+
+/* ---- activations ------------------------------------------------------ */
+
+int llmi_act_create(uint64_t max_cols, llmi_act_t* out);
+int llmi_act_free(llmi_act_t a);
+
+/* quantize_row_q8_0 (ops.h:94, ops.cpp:116-139) on the device: x_dev[n] fp32
+ * -> int8 quants + f16 scales (bit-exact with the reference). */
+int llmi_quantize_q8_0(const float* x_dev, uint64_t n, llmi_act_t a, llmi_stream_t s);
+/* quantize_row_q8_k (ops.h:104, ops.cpp:142-178): int8 quants, fp32 scale per
+ * 256, int16 sums per 16 (bit-exact with the reference). */
+int llmi_quantize_q8_k(const float* x_dev, uint64_t n, llmi_act_t a, llmi_stream_t s);
+/* x -> f16 rounding used by mat_vec_mul_fp16 (ops.cpp:542-551). */
+int llmi_round_f16(const float* x_dev, uint64_t n, llmi_act_t a, llmi_stream_t s);
+/* fp32 pass-through for the formats that do not quantize x (Q5_0 ops.cpp:856-878,
+ * BF16 ops.cpp:908-916). */
+int llmi_stage_f32(const float* x_dev, uint64_t n, llmi_act_t a, llmi_stream_t s);
+/* Picks whichever of the four the weight format consumes. */
+int llmi_act_prepare(llmi_weight_t w, const float* x_dev, llmi_act_t a, llmi_stream_t s);
+
+/* Copy the quantized activation back in the reference's record layout, for
+ * bit-exact checks: n/32 x BlockQ8_0 (34 B, ops.h:89-92) or n/256 x block_q8_K
+ * (292 B, ops.h:98-102).  Synchronises the stream the act was produced on. */
+int llmi_act_export_q8_0(llmi_act_t a, void* host_blocks);
+int llmi_act_export_q8_k(llmi_act_t a, void* host_blocks);
+
+/* ---- mat-vec, device tier (the timed path) ---------------------------- */
+
+/* o[row_begin..row_end) = W[rows] . act   for any supported format; replaces
+ * the compute_range bodies + pool fan-out of mat_vec_mul_q4_0/_q8_0/_q4_k/_q6_k/
+ * _q5_0/_bf16/_fp16 (ops.cpp:188-931).  out_dev is the FULL n_rows-long fp32
+ * vector; only this handle's row range is written. */
+int llmi_gemv(llmi_weight_t w, llmi_act_t a, float* out_dev, llmi_stream_t s);
+/* llmi_act_prepare + llmi_gemv: exactly one reference mat_vec_mul call. */
+int llmi_mat_vec_mul_dev(llmi_weight_t w, const float* x_dev, llmi_act_t a,
+                         float* out_dev, llmi_stream_t s);
+
+/* Tuning knob for benches: K-split (warps cooperating on one 8-row slab) for a
+ * format; 0 restores the heuristic. */
+int llmi_set_ksplit(uint32_t ggml_type, int ksplit);
+
+/* Per-block integer dot products (must be bit-exact with the reference):
+ * Q4_0/Q8_0: rows*(K/32) int32; Q4_K: rows*(K/32); Q6_K: rows*(K/128).
+ * dots_host is indexed [local_row][block]. */
+int llmi_debug_block_dots(llmi_weight_t w, llmi_act_t a, int32_t* dots_host);
+
+/* ---- mat-vec, host-vector tier (what the ops.h drop-in calls) ---------- */
+
+/* mat_vec_mul(o, w_tensor, gguf_file, x) (ops.h:53): H2D x, quantize, GEMV,
+ * D2H o, synchronous like the reference (returns after the join, ops.cpp:450).
+ * n_x must equal K (else LLMI_ERR_SIZE); n_o must equal N. */
+int llmi_host_mat_vec_mul(llmi_weight_t w, const float* x, uint64_t n_x,
+                          float* o, uint64_t n_o);
+/* quantize_row_q8_0 / quantize_row_q8_k with host vectors (ops.h:94,104);
+ * y receives reference-layout records. */
+int llmi_host_quantize_row_q8_0(const float* x, uint64_t n, void* y);
+int llmi_host_quantize_row_q8_k(const float* x, uint64_t n, void* y);
+
+/* ---- device memory helpers (benches / tests; plain cudaMalloc wrappers) - */
+int llmi_dev_alloc(uint64_t bytes, void** out_dev);
+int llmi_dev_free(void* dev);
+int llmi_h2d(void* dst_dev, const void* src_host, uint64_t bytes);
+int llmi_d2h(void* dst_host, const void* src_dev, uint64_t bytes);
+int llmi_device_sync(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LLMI_CUDA_H */

@@ -1,0 +1,439 @@
+// C ABI of libllmi_cuda.so (include/llmi_cuda.h): context, weights, activations,
+// the host-vector tier used by the ops.h drop-in, and small device helpers.
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "llmi_internal.h"
+
+namespace {
+
+thread_local std::string t_err;
+
+struct Context {
+  bool ready = false;
+  int device = -1;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;  // stream of the host-vector tier
+  // host-tier scratch, grown on demand
+  float* x_dev = nullptr;
+  size_t x_cap = 0;
+  float* o_dev = nullptr;
+  size_t o_cap = 0;
+  llmi_act_t act = nullptr;
+  uint8_t* scratch = nullptr;
+  size_t scratch_cap = 0;
+  std::map<std::tuple<const void*, uint32_t, uint64_t, uint64_t>, llmi_weight_t> registry;
+  int ksplit[32] = {0};
+};
+Context g;
+std::mutex g_mu;
+
+int type_slot(uint32_t t) { return t < 32 ? int(t) : 31; }
+
+bool supported(uint32_t t) {
+  switch (t) {
+    case LLMI_Q4_0: case LLMI_Q8_0: case LLMI_Q5_0: case LLMI_Q4_K: case LLMI_Q6_K: case LLMI_F16: case LLMI_BF16:
+      return true;
+    default: return false;
+  }
+}
+
+int ensure_cap(void** p, size_t* cap, size_t need) {
+  if (*cap >= need) return LLMI_OK;
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  *cap = 0;
+  const size_t want = round_up(need, 1 << 16);
+  LLMI_CUDA_TRY(cudaMalloc(p, want));
+  *cap = want;
+  return LLMI_OK;
+}
+
+#define LLMI_NEED_INIT() \
+  if (!g.ready) return llmi_fail(LLMI_ERR_STATE, "llmi_init() has not been called")
+
+}  // namespace
+
+void llmi_set_error(const std::string& msg) { t_err = msg; }
+int llmi_fail(int code, const std::string& msg) {
+  t_err = msg;
+  return code;
+}
+int llmi_cuda_fail(cudaError_t e, const char* what) {
+  t_err = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
+  return LLMI_ERR_CUDA;
+}
+
+extern "C" {
+
+const char* llmi_last_error(void) { return t_err.c_str(); }
+int llmi_abi_version(void) { return LLMI_ABI_VERSION; }
+int llmi_sm_count(void) { return g.sm_count; }
+
+uint64_t llmi_row_bytes(uint32_t t, uint64_t k) {
+  switch (t) {
+    case LLMI_Q4_0: return k % 32 ? 0 : k / 32 * 18;
+    case LLMI_Q8_0: return k % 32 ? 0 : k / 32 * 34;
+    case LLMI_Q5_0: return k % 32 ? 0 : k / 32 * 22;
+    case LLMI_Q4_K: return k % 256 ? 0 : k / 256 * 144;
+    case LLMI_Q6_K: return k % 256 ? 0 : k / 256 * 210;
+    case LLMI_F16:
+    case LLMI_BF16: return k * 2;
+    default: return 0;
+  }
+}
+
+int llmi_init(int device) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g.ready && g.device == device) return LLMI_OK;
+  if (g.ready) return llmi_fail(LLMI_ERR_STATE, "llmi_init: already initialised on another device");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    (void)cudaGetLastError();
+    return llmi_fail(LLMI_ERR_CUDA,
+                     "llmi_init: no CUDA device available (this library has no CPU fallback)");
+  }
+  if (device < 0 || device >= n) return llmi_fail(LLMI_ERR_ARG, "llmi_init: bad device index");
+  LLMI_CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  LLMI_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    return llmi_fail(LLMI_ERR_CUDA, std::string("llmi_init: device '") + prop.name +
+                                        "' is not sm_100 (this library is built for B200 only)");
+  }
+  g.sm_count = prop.multiProcessorCount;
+  LLMI_CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+  LLMI_CUDA_TRY(llmi_gemv_init());
+  g.device = device;
+  g.ready = true;
+  return LLMI_OK;
+}
+
+int llmi_shutdown(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!g.ready) return LLMI_OK;
+  cudaDeviceSynchronize();
+  for (auto& kv : g.registry) llmi_weight_free(kv.second);
+  g.registry.clear();
+  if (g.act) llmi_act_free(g.act);
+  if (g.x_dev) cudaFree(g.x_dev);
+  if (g.o_dev) cudaFree(g.o_dev);
+  if (g.scratch) cudaFree(g.scratch);
+  if (g.stream) cudaStreamDestroy(g.stream);
+  g = Context();
+  return LLMI_OK;
+}
+
+// ------------------------------------------------------------------ weights
+
+int llmi_weight_upload(const void* host_blocks, uint32_t ggml_type, uint64_t n_cols, uint64_t n_rows,
+                       uint64_t row_begin, uint64_t row_end, llmi_weight_t* out) {
+  LLMI_NEED_INIT();
+  if (!host_blocks || !out) return llmi_fail(LLMI_ERR_ARG, "llmi_weight_upload: null pointer");
+  if (!supported(ggml_type))
+    return llmi_fail(LLMI_ERR_TYPE, "mat_vec_mul: unsupported tensor type " + std::to_string(ggml_type));
+  const uint64_t rb = llmi_row_bytes(ggml_type, n_cols);
+  if (rb == 0 || n_cols == 0)
+    return llmi_fail(LLMI_ERR_ARG, "llmi_weight_upload: n_cols is not a multiple of the block size");
+  if (row_begin > row_end || row_end > n_rows) return llmi_fail(LLMI_ERR_ARG, "llmi_weight_upload: bad row range");
+  llmi_weight_s* w = new llmi_weight_s();
+  w->type = ggml_type;
+  w->n_cols = n_cols;
+  w->n_rows = n_rows;
+  w->row_begin = row_begin;
+  w->row_end = row_end;
+  const size_t total = llmi_plan_planes(*w);
+  w->bytes = total;
+  if (w->n_local == 0) {
+    *out = w;
+    return LLMI_OK;
+  }
+  cudaError_t e = cudaMalloc(&w->base, total);
+  if (e != cudaSuccess) {
+    delete w;
+    return llmi_cuda_fail(e, "cudaMalloc(weight planes)");
+  }
+  w->p_q = w->base + reinterpret_cast<size_t>(w->p_q);
+  w->p_d = w->base + reinterpret_cast<size_t>(w->p_d);
+  w->p_x = w->base + reinterpret_cast<size_t>(w->p_x);
+  // stage the raw rows of this shard, repack on the device, drop the staging copy
+  const size_t raw_bytes = size_t(w->n_local) * rb;
+  uint8_t* raw = nullptr;
+  e = cudaMalloc(&raw, raw_bytes);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(raw, static_cast<const uint8_t*>(host_blocks) + size_t(row_begin) * rb, raw_bytes,
+                        cudaMemcpyHostToDevice, g.stream);
+  if (e == cudaSuccess) e = llmi_launch_repack(*w, raw, g.stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+  if (raw) cudaFree(raw);
+  if (e != cudaSuccess) {
+    cudaFree(w->base);
+    delete w;
+    return llmi_cuda_fail(e, "weight upload/repack");
+  }
+  *out = w;
+  return LLMI_OK;
+}
+
+int llmi_weight_free(llmi_weight_t w) {
+  if (!w) return LLMI_OK;
+  if (w->base) cudaFree(w->base);
+  delete w;
+  return LLMI_OK;
+}
+
+int llmi_weight_dims(llmi_weight_t w, uint32_t* t, uint64_t* k, uint64_t* n, uint64_t* rb, uint64_t* re) {
+  if (!w) return llmi_fail(LLMI_ERR_ARG, "llmi_weight_dims: null handle");
+  if (t) *t = w->type;
+  if (k) *k = w->n_cols;
+  if (n) *n = w->n_rows;
+  if (rb) *rb = w->row_begin;
+  if (re) *re = w->row_end;
+  return LLMI_OK;
+}
+
+uint64_t llmi_weight_device_bytes(llmi_weight_t w) { return w ? w->bytes : 0; }
+
+int llmi_registry_get(const void* host_blocks, uint32_t t, uint64_t k, uint64_t n, llmi_weight_t* out) {
+  LLMI_NEED_INIT();
+  if (!out) return llmi_fail(LLMI_ERR_ARG, "llmi_registry_get: null out");
+  auto key = std::make_tuple(host_blocks, t, k, n);
+  auto it = g.registry.find(key);
+  if (it != g.registry.end()) {
+    *out = it->second;
+    return LLMI_OK;
+  }
+  llmi_weight_t w = nullptr;
+  const int rc = llmi_weight_upload(host_blocks, t, k, n, 0, n, &w);
+  if (rc != LLMI_OK) return rc;
+  g.registry[key] = w;
+  *out = w;
+  return LLMI_OK;
+}
+
+int llmi_registry_clear(void) {
+  for (auto& kv : g.registry) llmi_weight_free(kv.second);
+  g.registry.clear();
+  return LLMI_OK;
+}
+
+// -------------------------------------------------------------- activations
+
+int llmi_act_create(uint64_t max_cols, llmi_act_t* out) {
+  LLMI_NEED_INIT();
+  if (!out || max_cols == 0) return llmi_fail(LLMI_ERR_ARG, "llmi_act_create: bad argument");
+  llmi_act_s* a = new llmi_act_s();
+  a->max_cols = max_cols;
+  a->buf_bytes = round_up(4 * max_cols + 64, 256);  // fp32 staging is the largest kind
+  cudaError_t e = cudaMalloc(&a->buf, a->buf_bytes);
+  if (e != cudaSuccess) {
+    delete a;
+    return llmi_cuda_fail(e, "cudaMalloc(activation)");
+  }
+  *out = a;
+  return LLMI_OK;
+}
+
+int llmi_act_free(llmi_act_t a) {
+  if (!a) return LLMI_OK;
+  if (a->buf) cudaFree(a->buf);
+  delete a;
+  return LLMI_OK;
+}
+
+static int act_check(llmi_act_t a, const float* x, uint64_t n, uint64_t multiple, const char* who) {
+  if (!a || !x) return llmi_fail(LLMI_ERR_ARG, std::string(who) + ": null pointer");
+  if (n == 0 || n > a->max_cols) return llmi_fail(LLMI_ERR_SIZE, std::string(who) + ": n exceeds activation capacity");
+  if (n % multiple) return llmi_fail(LLMI_ERR_ARG, std::string(who) + ": n is not a multiple of the block size");
+  return LLMI_OK;
+}
+
+int llmi_quantize_q8_0(const float* x, uint64_t n, llmi_act_t a, llmi_stream_t s) {
+  LLMI_NEED_INIT();
+  if (int rc = act_check(a, x, n, 32, "llmi_quantize_q8_0")) return rc;
+  LLMI_CUDA_TRY(llmi_launch_quantize_q8_0(x, n, a->buf, (cudaStream_t)s));
+  a->kind = ACT_Q8_0;
+  a->n = n;
+  a->last_stream = (cudaStream_t)s;
+  return LLMI_OK;
+}
+
+int llmi_quantize_q8_k(const float* x, uint64_t n, llmi_act_t a, llmi_stream_t s) {
+  LLMI_NEED_INIT();
+  if (int rc = act_check(a, x, n, 256, "llmi_quantize_q8_k")) return rc;
+  LLMI_CUDA_TRY(llmi_launch_quantize_q8_k(x, n, a->buf, (cudaStream_t)s));
+  a->kind = ACT_Q8_K;
+  a->n = n;
+  a->last_stream = (cudaStream_t)s;
+  return LLMI_OK;
+}
+
+int llmi_round_f16(const float* x, uint64_t n, llmi_act_t a, llmi_stream_t s) {
+  LLMI_NEED_INIT();
+  if (int rc = act_check(a, x, n, 1, "llmi_round_f16")) return rc;
+  LLMI_CUDA_TRY(llmi_launch_round_f16(x, n, a->buf, (cudaStream_t)s));
+  a->kind = ACT_F16;
+  a->n = n;
+  a->last_stream = (cudaStream_t)s;
+  return LLMI_OK;
+}
+
+int llmi_stage_f32(const float* x, uint64_t n, llmi_act_t a, llmi_stream_t s) {
+  LLMI_NEED_INIT();
+  if (int rc = act_check(a, x, n, 1, "llmi_stage_f32")) return rc;
+  const size_t padded = act_bytes(ACT_F32, n);
+  if (padded > 4 * n) LLMI_CUDA_TRY(cudaMemsetAsync(a->buf + 4 * n, 0, padded - 4 * n, (cudaStream_t)s));
+  LLMI_CUDA_TRY(cudaMemcpyAsync(a->buf, x, 4 * n, cudaMemcpyDeviceToDevice, (cudaStream_t)s));
+  a->kind = ACT_F32;
+  a->n = n;
+  a->last_stream = (cudaStream_t)s;
+  return LLMI_OK;
+}
+
+int llmi_act_prepare(llmi_weight_t w, const float* x, llmi_act_t a, llmi_stream_t s) {
+  if (!w) return llmi_fail(LLMI_ERR_ARG, "llmi_act_prepare: null weight");
+  switch (llmi_act_kind_for(w->type)) {
+    case ACT_Q8_0: return llmi_quantize_q8_0(x, w->n_cols, a, s);
+    case ACT_Q8_K: return llmi_quantize_q8_k(x, w->n_cols, a, s);
+    case ACT_F16: return llmi_round_f16(x, w->n_cols, a, s);
+    case ACT_F32: return llmi_stage_f32(x, w->n_cols, a, s);
+    default: return llmi_fail(LLMI_ERR_TYPE, "mat_vec_mul: unsupported tensor type " + std::to_string(w->type));
+  }
+}
+
+static int act_export(llmi_act_t a, void* host, int kind, size_t rec, size_t per, const char* who) {
+  LLMI_NEED_INIT();
+  if (!a || !host) return llmi_fail(LLMI_ERR_ARG, std::string(who) + ": null pointer");
+  if (a->kind != kind) return llmi_fail(LLMI_ERR_STATE, std::string(who) + ": activation holds another format");
+  const size_t bytes = a->n / per * rec;
+  if (int rc = ensure_cap((void**)&g.scratch, &g.scratch_cap, bytes)) return rc;
+  cudaStream_t s = a->last_stream;
+  if (kind == ACT_Q8_0) LLMI_CUDA_TRY(llmi_launch_export_q8_0(a->buf, a->n, g.scratch, s));
+  else LLMI_CUDA_TRY(llmi_launch_export_q8_k(a->buf, a->n, g.scratch, s));
+  LLMI_CUDA_TRY(cudaMemcpyAsync(host, g.scratch, bytes, cudaMemcpyDeviceToHost, s));
+  LLMI_CUDA_TRY(cudaStreamSynchronize(s));
+  return LLMI_OK;
+}
+
+int llmi_act_export_q8_0(llmi_act_t a, void* host) { return act_export(a, host, ACT_Q8_0, 34, 32, "llmi_act_export_q8_0"); }
+int llmi_act_export_q8_k(llmi_act_t a, void* host) { return act_export(a, host, ACT_Q8_K, 292, 256, "llmi_act_export_q8_k"); }
+
+// ------------------------------------------------------------------- mat-vec
+
+int llmi_set_ksplit(uint32_t t, int ks) {
+  if (ks != 0 && ks != 1 && ks != 2 && ks != 4 && ks != 8 && ks != 16)
+    return llmi_fail(LLMI_ERR_ARG, "llmi_set_ksplit: ksplit must be 0,1,2,4,8 or 16");
+  g.ksplit[type_slot(t)] = ks;
+  return LLMI_OK;
+}
+
+int llmi_gemv(llmi_weight_t w, llmi_act_t a, float* out, llmi_stream_t s) {
+  LLMI_NEED_INIT();
+  if (!w || !a || !out) return llmi_fail(LLMI_ERR_ARG, "llmi_gemv: null pointer");
+  if (a->kind != llmi_act_kind_for(w->type))
+    return llmi_fail(LLMI_ERR_STATE, "llmi_gemv: activation was not prepared for this weight format");
+  if (a->n != w->n_cols) return llmi_fail(LLMI_ERR_SIZE, "mat_vec_mul: input vector size mismatch");
+  LLMI_CUDA_TRY(llmi_launch_gemv(*w, *a, out, g.ksplit[type_slot(w->type)], (cudaStream_t)s));
+  return LLMI_OK;
+}
+
+int llmi_mat_vec_mul_dev(llmi_weight_t w, const float* x, llmi_act_t a, float* out, llmi_stream_t s) {
+  if (int rc = llmi_act_prepare(w, x, a, s)) return rc;
+  return llmi_gemv(w, a, out, s);
+}
+
+int llmi_debug_block_dots(llmi_weight_t w, llmi_act_t a, int32_t* dots_host) {
+  LLMI_NEED_INIT();
+  if (!w || !a || !dots_host) return llmi_fail(LLMI_ERR_ARG, "llmi_debug_block_dots: null pointer");
+  if (w->type != LLMI_Q4_0 && w->type != LLMI_Q8_0 && w->type != LLMI_Q4_K && w->type != LLMI_Q6_K)
+    return llmi_fail(LLMI_ERR_TYPE, "llmi_debug_block_dots: format has no integer block dots");
+  if (a->kind != llmi_act_kind_for(w->type) || a->n != w->n_cols)
+    return llmi_fail(LLMI_ERR_STATE, "llmi_debug_block_dots: activation not prepared for this weight");
+  const uint64_t per_row = w->type == LLMI_Q6_K ? w->nb * 2 : (w->type == LLMI_Q4_K ? w->nb * 8 : w->nb);
+  const size_t bytes = size_t(w->n_local) * per_row * 4;
+  if (int rc = ensure_cap((void**)&g.scratch, &g.scratch_cap, bytes)) return rc;
+  cudaStream_t s = a->last_stream;
+  LLMI_CUDA_TRY(llmi_launch_block_dots(*w, *a, reinterpret_cast<int32_t*>(g.scratch), s));
+  LLMI_CUDA_TRY(cudaMemcpyAsync(dots_host, g.scratch, bytes, cudaMemcpyDeviceToHost, s));
+  LLMI_CUDA_TRY(cudaStreamSynchronize(s));
+  return LLMI_OK;
+}
+
+// ---------------------------------------------------------- host-vector tier
+
+int llmi_host_mat_vec_mul(llmi_weight_t w, const float* x, uint64_t n_x, float* o, uint64_t n_o) {
+  LLMI_NEED_INIT();
+  if (!w || !x || !o) return llmi_fail(LLMI_ERR_ARG, "llmi_host_mat_vec_mul: null pointer");
+  if (n_x != w->n_cols) return llmi_fail(LLMI_ERR_SIZE, "mat_vec_mul: input vector size mismatch");
+  if (n_o != w->n_rows) return llmi_fail(LLMI_ERR_SIZE, "mat_vec_mul: output vector size mismatch");
+  if (int rc = ensure_cap((void**)&g.x_dev, &g.x_cap, 4 * n_x)) return rc;
+  if (int rc = ensure_cap((void**)&g.o_dev, &g.o_cap, 4 * n_o)) return rc;
+  if (!g.act || g.act->max_cols < n_x) {
+    if (g.act) llmi_act_free(g.act);
+    g.act = nullptr;
+    if (int rc = llmi_act_create(n_x, &g.act)) return rc;
+  }
+  LLMI_CUDA_TRY(cudaMemcpyAsync(g.x_dev, x, 4 * n_x, cudaMemcpyHostToDevice, g.stream));
+  if (int rc = llmi_mat_vec_mul_dev(w, g.x_dev, g.act, g.o_dev, g.stream)) return rc;
+  LLMI_CUDA_TRY(cudaMemcpyAsync(o + w->row_begin, g.o_dev + w->row_begin, 4 * w->n_local, cudaMemcpyDeviceToHost,
+                                g.stream));
+  LLMI_CUDA_TRY(cudaStreamSynchronize(g.stream));
+  return LLMI_OK;
+}
+
+static int host_quantize(const float* x, uint64_t n, void* y, bool k_quant) {
+  LLMI_NEED_INIT();
+  if (!x || !y) return llmi_fail(LLMI_ERR_ARG, "quantize_row: null pointer");
+  if (n == 0) return LLMI_OK;
+  if (int rc = ensure_cap((void**)&g.x_dev, &g.x_cap, 4 * n)) return rc;
+  if (!g.act || g.act->max_cols < n) {
+    if (g.act) llmi_act_free(g.act);
+    g.act = nullptr;
+    if (int rc = llmi_act_create(n, &g.act)) return rc;
+  }
+  LLMI_CUDA_TRY(cudaMemcpyAsync(g.x_dev, x, 4 * n, cudaMemcpyHostToDevice, g.stream));
+  if (k_quant) {
+    if (int rc = llmi_quantize_q8_k(g.x_dev, n, g.act, g.stream)) return rc;
+    return llmi_act_export_q8_k(g.act, y);
+  }
+  if (int rc = llmi_quantize_q8_0(g.x_dev, n, g.act, g.stream)) return rc;
+  return llmi_act_export_q8_0(g.act, y);
+}
+
+int llmi_host_quantize_row_q8_0(const float* x, uint64_t n, void* y) { return host_quantize(x, n, y, false); }
+int llmi_host_quantize_row_q8_k(const float* x, uint64_t n, void* y) { return host_quantize(x, n, y, true); }
+
+// ------------------------------------------------------------ device helpers
+
+int llmi_dev_alloc(uint64_t bytes, void** out) {
+  LLMI_NEED_INIT();
+  if (!out) return llmi_fail(LLMI_ERR_ARG, "llmi_dev_alloc: null out");
+  LLMI_CUDA_TRY(cudaMalloc(out, bytes ? bytes : 16));
+  return LLMI_OK;
+}
+int llmi_dev_free(void* p) {
+  if (p) LLMI_CUDA_TRY(cudaFree(p));
+  return LLMI_OK;
+}
+int llmi_h2d(void* dst, const void* src, uint64_t bytes) {
+  LLMI_NEED_INIT();
+  LLMI_CUDA_TRY(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+  return LLMI_OK;
+}
+int llmi_d2h(void* dst, const void* src, uint64_t bytes) {
+  LLMI_NEED_INIT();
+  LLMI_CUDA_TRY(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+  return LLMI_OK;
+}
+int llmi_device_sync(void) {
+  LLMI_NEED_INIT();
+  LLMI_CUDA_TRY(cudaDeviceSynchronize());
+  return LLMI_OK;
+}
+
+}  // extern "C"

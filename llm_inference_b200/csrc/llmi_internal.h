@@ -1,0 +1,92 @@
+// Internal declarations shared by the translation units of libllmi_cuda.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "llmi_cuda.h"
+
+// ---------------------------------------------------------------------------
+// Slab layout.  Output rows are grouped into slabs of 8.  Inside
+// a slab every plane is stored "unit-major, row-minor" in 16-byte items, so that
+// the 32 lanes of a warp (lane = 8*sub + row) read 512 contiguous bytes per
+// 128-bit load, for any K.  Rows past the end of the matrix are padded with
+// zero-weight blocks.
+// ---------------------------------------------------------------------------
+constexpr int LLMI_SLAB = 8;
+
+struct llmi_weight_s {
+  uint32_t type = 0;
+  uint64_t n_cols = 0, n_rows = 0;       // K, N of the full matrix
+  uint64_t row_begin = 0, row_end = 0;   // rows held by this handle
+  uint64_t n_local = 0, n_slabs = 0;
+  uint64_t nb = 0;        // K-units per row: 32-blocks, 256-super-blocks or 8-halves chunks
+  uint8_t* base = nullptr;  // one allocation, planes below point into it
+  size_t bytes = 0;
+  // format-specific planes (see repack.cu for the exact item order)
+  uint8_t* p_q = nullptr;    // quants (16-byte items)
+  uint8_t* p_d = nullptr;    // f16 block scales
+  uint8_t* p_x = nullptr;    // Q5_0: qh words; Q4_K: header items; Q6_K: int8 scales
+};
+
+// kinds of prepared activation
+enum : int { ACT_NONE = 0, ACT_Q8_0 = 1, ACT_Q8_K = 2, ACT_F16 = 3, ACT_F32 = 4 };
+
+// Device layout of a prepared activation (one contiguous, 16-byte-multiple
+// buffer so a single bulk async copy stages it into shared memory):
+//   ACT_Q8_0: [K int8 quants][K/32 x {f16 d, int16 sum-of-quants}]
+//   ACT_Q8_K: [K int8 quants][K/16 int16 bsums][K/256 fp32 d]
+//   ACT_F16 : [K f16]            (x rounded to f16)
+//   ACT_F32 : [K fp32]
+struct llmi_act_s {
+  uint64_t max_cols = 0;
+  uint64_t n = 0;
+  int kind = ACT_NONE;
+  uint8_t* buf = nullptr;
+  size_t buf_bytes = 0;
+  cudaStream_t last_stream = nullptr;
+};
+
+inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+inline size_t act_bytes(int kind, uint64_t n) {
+  switch (kind) {
+    case ACT_Q8_0: return round_up(n + 4 * (n / 32), 16);
+    case ACT_Q8_K: return round_up(n + 2 * (n / 16) + 4 * (n / 256), 16);
+    case ACT_F16: return round_up(2 * n, 16);
+    case ACT_F32: return round_up(4 * n, 16);
+    default: return 0;
+  }
+}
+
+// error plumbing (capi.cu)
+void llmi_set_error(const std::string& msg);
+int llmi_fail(int code, const std::string& msg);
+int llmi_cuda_fail(cudaError_t e, const char* what);
+
+#define LLMI_CUDA_TRY(expr)                                  \
+  do {                                                       \
+    cudaError_t _e = (expr);                                 \
+    if (_e != cudaSuccess) return llmi_cuda_fail(_e, #expr); \
+  } while (0)
+
+// launchers implemented in the .cu files -------------------------------------
+// repack.cu: raw (reference layout, rows [0,n_local)) -> planes of w
+cudaError_t llmi_launch_repack(const llmi_weight_s& w, const uint8_t* raw_dev, cudaStream_t s);
+size_t llmi_plan_planes(llmi_weight_s& w);  // fills nb/n_slabs, returns total bytes, sets plane offsets relative to 0
+
+// quantize.cu
+cudaError_t llmi_launch_quantize_q8_0(const float* x, uint64_t n, uint8_t* buf, cudaStream_t s);
+cudaError_t llmi_launch_quantize_q8_k(const float* x, uint64_t n, uint8_t* buf, cudaStream_t s);
+cudaError_t llmi_launch_round_f16(const float* x, uint64_t n, uint8_t* buf, cudaStream_t s);
+cudaError_t llmi_launch_export_q8_0(const uint8_t* buf, uint64_t n, uint8_t* out34, cudaStream_t s);
+cudaError_t llmi_launch_export_q8_k(const uint8_t* buf, uint64_t n, uint8_t* out292, cudaStream_t s);
+
+// gemv.cu
+cudaError_t llmi_gemv_init();  // opt-in dynamic shared memory for every instantiation
+cudaError_t llmi_launch_gemv(const llmi_weight_s& w, const llmi_act_s& a, float* out, int ksplit_override,
+                             cudaStream_t s);
+cudaError_t llmi_launch_block_dots(const llmi_weight_s& w, const llmi_act_s& a, int32_t* dots_dev, cudaStream_t s);
+int llmi_act_kind_for(uint32_t ggml_type);
