@@ -124,9 +124,10 @@ int llmi_gemv(llmi_weight_t w, llmi_act_t a, float* out_dev, llmi_stream_t s);
 int llmi_mat_vec_mul_dev(llmi_weight_t w, const float* x_dev, llmi_act_t a,
                          float* out_dev, llmi_stream_t s);
 
-/* Tuning knob for benches: K-split (warps cooperating on one 8-row slab) for a
- * format; 0 restores the heuristic. */
-int llmi_set_ksplit(uint32_t ggml_type, int ksplit);
+/* Tuning knob for benches: pins the CTA shape of the mat-vec kernel — warps per
+ * CTA (4, 8 or 16) and consecutive 8-row slabs per CTA; 0 = heuristic.  Results
+ * never depend on it (canonical summation order). */
+int llmi_set_gemv_shape(int warps, int slabs_per_cta);
 
 /* Per-block integer dot products (must be bit-exact with the reference):
  * Q4_0/Q8_0: rows*(K/32) int32; Q4_K: rows*(K/32); Q6_K: rows*(K/128).

@@ -41,7 +41,7 @@ SIGNATURES = {
     "llmi_act_export_q8_k": (_int, [_vp, _vp]),
     "llmi_gemv": (_int, [_vp, _vp, _vp, _vp]),
     "llmi_mat_vec_mul_dev": (_int, [_vp, _vp, _vp, _vp, _vp]),
-    "llmi_set_ksplit": (_int, [_u32, _int]),
+    "llmi_set_gemv_shape": (_int, [_int, _int]),
     "llmi_debug_block_dots": (_int, [_vp, _vp, _vp]),
     "llmi_host_mat_vec_mul": (_int, [_vp, _vp, _u64, _vp, _u64]),
     "llmi_host_quantize_row_q8_0": (_int, [_vp, _u64, _vp]),

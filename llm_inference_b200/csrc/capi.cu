@@ -27,12 +27,9 @@ struct Context {
   uint8_t* scratch = nullptr;
   size_t scratch_cap = 0;
   std::map<std::tuple<const void*, uint32_t, uint64_t, uint64_t>, llmi_weight_t> registry;
-  int ksplit[32] = {0};
 };
 Context g;
 std::mutex g_mu;
-
-int type_slot(uint32_t t) { return t < 32 ? int(t) : 31; }
 
 bool supported(uint32_t t) {
   switch (t) {
@@ -325,10 +322,10 @@ int llmi_act_export_q8_k(llmi_act_t a, void* host) { return act_export(a, host, 
 
 // ------------------------------------------------------------------- mat-vec
 
-int llmi_set_ksplit(uint32_t t, int ks) {
-  if (ks != 0 && ks != 1 && ks != 2 && ks != 4 && ks != 8 && ks != 16)
-    return llmi_fail(LLMI_ERR_ARG, "llmi_set_ksplit: ksplit must be 0,1,2,4,8 or 16");
-  g.ksplit[type_slot(t)] = ks;
+int llmi_set_gemv_shape(int warps, int slabs_per_cta) {
+  if ((warps != 0 && warps != 4 && warps != 8 && warps != 16) || slabs_per_cta < 0 || slabs_per_cta > 64)
+    return llmi_fail(LLMI_ERR_ARG, "llmi_set_gemv_shape: warps in {0,4,8,16}, slabs_per_cta in [0,64]");
+  llmi_gemv_set_shape(warps, slabs_per_cta);
   return LLMI_OK;
 }
 
@@ -338,7 +335,7 @@ int llmi_gemv(llmi_weight_t w, llmi_act_t a, float* out, llmi_stream_t s) {
   if (a->kind != llmi_act_kind_for(w->type))
     return llmi_fail(LLMI_ERR_STATE, "llmi_gemv: activation was not prepared for this weight format");
   if (a->n != w->n_cols) return llmi_fail(LLMI_ERR_SIZE, "mat_vec_mul: input vector size mismatch");
-  LLMI_CUDA_TRY(llmi_launch_gemv(*w, *a, out, g.ksplit[type_slot(w->type)], (cudaStream_t)s));
+  LLMI_CUDA_TRY(llmi_launch_gemv(*w, *a, out, (cudaStream_t)s));
   return LLMI_OK;
 }
 

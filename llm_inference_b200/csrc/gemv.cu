@@ -1,15 +1,21 @@
 // Decode mat-vec kernels for sm_100a — the replacement for the compute_range
 // bodies + thread-pool fan-out of ops.cpp:188-931.
 //
-// Shape of every kernel:
-//   * work unit = one SLAB of 8 output rows; lane = 8*sub + row, so one 128-bit
+// One kernel shape for every format:
+//   * data unit = one SLAB of 8 output rows; lane = 8*sub + row, so one 128-bit
 //     load per lane covers 4 K-units x 8 rows = 512 contiguous bytes of the
 //     quant plane (weights are read exactly once, straight into registers,
 //     L1 no-allocate; no shared-memory round trip for weights);
-//   * KSPLIT warps cooperate on a slab, interleaved along K (the reference's
-//     row partition, ops.cpp:439-448, becomes grid partitioning; K-split adds
-//     parallelism for the short/wide matrices and is reduced in a fixed order,
-//     so results are deterministic and independent of the grid);
+//   * work item = (slab, K-chunk): 512 elements of K for the block formats,
+//     128 for F16/BF16.  A CTA of W warps owns S consecutive slabs and deals
+//     their items round-robin to its warps — the reference's row partition
+//     over threads (ops.cpp:439-448) becomes a (row-slab, K-chunk) partition
+//     over the grid;
+//   * canonical summation: a row's result is the left-to-right sum over its
+//     K-chunks of (xor-shuffle tree over the 4 sub-lanes of (sequential sum
+//     over the chunk's units)).  The order depends only on K and the format,
+//     so results are deterministic and independent of W, S, the grid, the SM
+//     count and of row sharding across GPUs (bit-identical shards);
 //   * the quantized activation vector (K bytes + scales) is staged into shared
 //     memory once per CTA with one bulk async copy (cp.async.bulk -> UBLKCP)
 //     completing on an mbarrier, overlapped with the first weight loads;
@@ -83,6 +89,8 @@ struct GemvArgs {
   uint32_t act_bytes;
   float* out;  // already offset to this handle's first row
   uint32_t n_local, n_slabs, nb, n_cols;
+  uint32_t units;   // K-units per slab row (4 blocks of 32 / one super-block / 4 chunks of 8)
+  uint32_t chunks;  // K-chunks (work items) per slab = ceil(units / Body::C)
 };
 
 // ------------------------------------------------ integer block dot products
@@ -183,367 +191,308 @@ __device__ __forceinline__ int sbyte(const uint2 v, const int i) {  // signed by
 }
 
 // ------------------------------------------------------------ format bodies
-// Each body returns the lane's partial sum over the K-units it owns:
-//   units u = kw + ks*j, lane's sub-position = lane>>3, row in slab = lane&7.
+// A Body describes one format: Frag = the registers one lane loads for one
+// K-unit, load() issues the global loads, compute() folds the unit into the
+// lane's partial sum.  C = units per K-chunk (512 elements; 128 for F16/BF16).
+// lane = 8*sub + r: r = row in slab, sub = position inside the unit.
 
-template <int UNROLL>
 struct BodyQ4_0 {
-  __device__ static float run(const GemvArgs& a, const uint8_t* sm, uint64_t* bar, uint32_t slab, int kw, int ks,
-                              int lane) {
-    const int r = lane & 7, sub = lane >> 3;
-    const uint32_t nb = a.nb;
-    const uint4* q = reinterpret_cast<const uint4*>(a.q) + (size_t)slab * nb * 8 + r;
-    const uint16_t* d = reinterpret_cast<const uint16_t*>(a.d) + (size_t)slab * nb * 8 + r;
-    const int4* xs = reinterpret_cast<const int4*>(sm);
-    const uint32_t* meta = reinterpret_cast<const uint32_t*>(sm + a.n_cols);
-    float acc = 0.0f;
-    bool waited = false;
-    const uint32_t step = 4u * ks;
-    for (uint32_t b0 = 4u * kw + sub; b0 < nb; b0 += step * UNROLL) {
-      uint4 w[UNROLL];
-      uint16_t dw[UNROLL];
-#pragma unroll
-      for (int i = 0; i < UNROLL; ++i) {
-        const uint32_t b = b0 + i * step;
-        if (b < nb) {
-          w[i] = ldg_stream(q + (size_t)b * 8);
-          dw[i] = ldg_stream(d + (size_t)b * 8);
-        }
-      }
-      if (!waited) {
-        mbar_wait(bar, 0);
-        waited = true;
-      }
-#pragma unroll
-      for (int i = 0; i < UNROLL; ++i) {
-        const uint32_t b = b0 + i * step;
-        if (b < nb) {
-          const int4 xa = xs[2 * b], xb = xs[2 * b + 1];
-          const uint32_t m = meta[b];
-          const int dot = q4_0_block_dot(w[i], xa, xb, int(int16_t(m >> 16)));
-          acc = fmaf(h2f(dw[i]) * h2f(uint16_t(m & 0xffffu)), float(dot), acc);  // ops.cpp:380-395
-        }
-      }
+  static constexpr int C = 4;
+  struct Frag {
+    uint4 w;
+    uint16_t d;
+  };
+  __device__ static void load(Frag& f, const GemvArgs& a, uint32_t slab, uint32_t u, int r, int sub) {
+    const uint32_t b = 4 * u + sub;
+    if (b < a.nb) {
+      const size_t i = ((size_t)slab * a.nb + b) * 8 + r;
+      f.w = ldg_stream(reinterpret_cast<const uint4*>(a.q) + i);
+      f.d = ldg_stream(reinterpret_cast<const uint16_t*>(a.d) + i);
     }
-    if (!waited) mbar_wait(bar, 0);
+  }
+  __device__ static float compute(const Frag& f, const GemvArgs& a, const uint8_t* sm, uint32_t u, int sub,
+                                  float acc) {
+    const uint32_t b = 4 * u + sub;
+    if (b < a.nb) {
+      const int4* xs = reinterpret_cast<const int4*>(sm);
+      const uint32_t m = reinterpret_cast<const uint32_t*>(sm + a.n_cols)[b];
+      const int dot = q4_0_block_dot(f.w, xs[2 * b], xs[2 * b + 1], int(int16_t(m >> 16)));
+      acc = fmaf(h2f(f.d) * h2f(uint16_t(m & 0xffffu)), float(dot), acc);  // ops.cpp:380-395
+    }
     return acc;
   }
 };
 
-template <int UNROLL>
 struct BodyQ8_0 {
-  __device__ static float run(const GemvArgs& a, const uint8_t* sm, uint64_t* bar, uint32_t slab, int kw, int ks,
-                              int lane) {
-    const int r = lane & 7, sub = lane >> 3;
-    const uint32_t nb = a.nb;
-    const uint4* q = reinterpret_cast<const uint4*>(a.q) + (size_t)slab * nb * 16 + r;
-    const uint16_t* d = reinterpret_cast<const uint16_t*>(a.d) + (size_t)slab * nb * 8 + r;
-    const int4* xs = reinterpret_cast<const int4*>(sm);
-    const uint32_t* meta = reinterpret_cast<const uint32_t*>(sm + a.n_cols);
-    float acc = 0.0f;
-    bool waited = false;
-    const uint32_t step = 4u * ks;
-    for (uint32_t b0 = 4u * kw + sub; b0 < nb; b0 += step * UNROLL) {
-      uint4 w0[UNROLL], w1[UNROLL];
-      uint16_t dw[UNROLL];
-#pragma unroll
-      for (int i = 0; i < UNROLL; ++i) {
-        const uint32_t b = b0 + i * step;
-        if (b < nb) {
-          w0[i] = ldg_stream(q + (size_t)b * 16);
-          w1[i] = ldg_stream(q + (size_t)b * 16 + 8);
-          dw[i] = ldg_stream(d + (size_t)b * 8);
-        }
-      }
-      if (!waited) {
-        mbar_wait(bar, 0);
-        waited = true;
-      }
-#pragma unroll
-      for (int i = 0; i < UNROLL; ++i) {
-        const uint32_t b = b0 + i * step;
-        if (b < nb) {
-          const int dot = q8_0_block_dot(w0[i], w1[i], xs[2 * b], xs[2 * b + 1]);
-          const float dx = h2f(uint16_t(meta[b] & 0xffffu));
-          acc = fmaf(float(dot) * h2f(dw[i]), dx, acc);  // (int*dw)*dx, ops.cpp:820
-        }
-      }
+  static constexpr int C = 4;
+  struct Frag {
+    uint4 w0, w1;
+    uint16_t d;
+  };
+  __device__ static void load(Frag& f, const GemvArgs& a, uint32_t slab, uint32_t u, int r, int sub) {
+    const uint32_t b = 4 * u + sub;
+    if (b < a.nb) {
+      const size_t i = ((size_t)slab * a.nb + b) * 8 + r;
+      const uint4* q = reinterpret_cast<const uint4*>(a.q) + ((size_t)slab * a.nb + b) * 16 + r;
+      f.w0 = ldg_stream(q);
+      f.w1 = ldg_stream(q + 8);
+      f.d = ldg_stream(reinterpret_cast<const uint16_t*>(a.d) + i);
     }
-    if (!waited) mbar_wait(bar, 0);
+  }
+  __device__ static float compute(const Frag& f, const GemvArgs& a, const uint8_t* sm, uint32_t u, int sub,
+                                  float acc) {
+    const uint32_t b = 4 * u + sub;
+    if (b < a.nb) {
+      const int4* xs = reinterpret_cast<const int4*>(sm);
+      const int dot = q8_0_block_dot(f.w0, f.w1, xs[2 * b], xs[2 * b + 1]);
+      const float dx = h2f(uint16_t(reinterpret_cast<const uint32_t*>(sm + a.n_cols)[b] & 0xffffu));
+      acc = fmaf(float(dot) * h2f(f.d), dx, acc);  // (int*dw)*dx, ops.cpp:820
+    }
     return acc;
   }
 };
 
 // Q5_0 keeps fp32 activations (ops.cpp:856-878): no integer dot.
-template <int UNROLL>
 struct BodyQ5_0 {
-  __device__ static float run(const GemvArgs& a, const uint8_t* sm, uint64_t* bar, uint32_t slab, int kw, int ks,
-                              int lane) {
-    const int r = lane & 7, sub = lane >> 3;
-    const uint32_t nb = a.nb;
-    const uint4* q = reinterpret_cast<const uint4*>(a.q) + (size_t)slab * nb * 8 + r;
-    const uint32_t* qhp = reinterpret_cast<const uint32_t*>(a.x) + (size_t)slab * nb * 8 + r;
-    const uint16_t* d = reinterpret_cast<const uint16_t*>(a.d) + (size_t)slab * nb * 8 + r;
-    const float4* xs = reinterpret_cast<const float4*>(sm);
-    float acc0 = 0.0f, acc1 = 0.0f;
-    bool waited = false;
-    const uint32_t step = 4u * ks;
-    for (uint32_t b0 = 4u * kw + sub; b0 < nb; b0 += step * UNROLL) {
-      uint4 w[UNROLL];
-      uint32_t qh[UNROLL];
-      uint16_t dw[UNROLL];
-#pragma unroll
-      for (int i = 0; i < UNROLL; ++i) {
-        const uint32_t b = b0 + i * step;
-        if (b < nb) {
-          w[i] = ldg_stream(q + (size_t)b * 8);
-          qh[i] = ldg_stream(qhp + (size_t)b * 8);
-          dw[i] = ldg_stream(d + (size_t)b * 8);
-        }
-      }
-      if (!waited) {
-        mbar_wait(bar, 0);
-        waited = true;
-      }
-#pragma unroll
-      for (int i = 0; i < UNROLL; ++i) {
-        const uint32_t b = b0 + i * step;
-        if (b < nb) {
-          const float dv = h2f(dw[i]);
-          const uint32_t ws[4] = {w[i].x, w[i].y, w[i].z, w[i].w};
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const float4 xl = xs[b * 8 + g], xh = xs[b * 8 + 4 + g];
-            const float xlv[4] = {xl.x, xl.y, xl.z, xl.w}, xhv[4] = {xh.x, xh.y, xh.z, xh.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int idx = 4 * g + e;
-              const uint32_t byte = (ws[g] >> (8 * e)) & 0xffu;
-              const int q0 = int((byte & 0x0fu) | (((qh[i] >> idx) & 1u) << 4));
-              const int q1 = int((byte >> 4) | (((qh[i] >> (idx + 16)) & 1u) << 4));
-              acc0 = fmaf(dv * float(q0 - 16), xlv[e], acc0);  // ops.cpp:873
-              acc1 = fmaf(dv * float(q1 - 16), xhv[e], acc1);  // ops.cpp:874
-            }
-          }
-        }
-      }
+  static constexpr int C = 4;
+  struct Frag {
+    uint4 w;
+    uint32_t qh;
+    uint16_t d;
+  };
+  __device__ static void load(Frag& f, const GemvArgs& a, uint32_t slab, uint32_t u, int r, int sub) {
+    const uint32_t b = 4 * u + sub;
+    if (b < a.nb) {
+      const size_t i = ((size_t)slab * a.nb + b) * 8 + r;
+      f.w = ldg_stream(reinterpret_cast<const uint4*>(a.q) + i);
+      f.qh = ldg_stream(reinterpret_cast<const uint32_t*>(a.x) + i);
+      f.d = ldg_stream(reinterpret_cast<const uint16_t*>(a.d) + i);
     }
-    if (!waited) mbar_wait(bar, 0);
-    return acc0 + acc1;
   }
-};
-
-// K-quants: one super-block of 256 per warp iteration; sub = 64-element chunk.
-template <int UNROLL>
-struct BodyQ4_K {
-  __device__ static float run(const GemvArgs& a, const uint8_t* sm, uint64_t* bar, uint32_t slab, int kw, int ks,
-                              int lane) {
-    const int r = lane & 7, c = lane >> 3;
-    const uint32_t nb = a.nb;
-    const uint4* hdr = reinterpret_cast<const uint4*>(a.x) + (size_t)slab * nb * 8 + r;
-    const uint4* q = reinterpret_cast<const uint4*>(a.q) + ((size_t)slab * nb * 4 + c) * 16 + r;
-    const int4* xs = reinterpret_cast<const int4*>(sm);
-    const uint2* bs = reinterpret_cast<const uint2*>(sm + a.n_cols);
-    const float* xd = reinterpret_cast<const float*>(sm + a.n_cols + a.n_cols / 8);
-    float acc = 0.0f;
-    bool waited = false;
-    for (uint32_t s0 = kw; s0 < nb; s0 += ks * UNROLL) {
-      uint4 h[UNROLL], qa[UNROLL], qb[UNROLL];
+  __device__ static float compute(const Frag& f, const GemvArgs& a, const uint8_t* sm, uint32_t u, int sub,
+                                  float acc) {
+    const uint32_t b = 4 * u + sub;
+    if (b < a.nb) {
+      const float4* xs = reinterpret_cast<const float4*>(sm) + (size_t)b * 8;
+      const float dv = h2f(f.d);
+      const uint32_t ws[4] = {f.w.x, f.w.y, f.w.z, f.w.w};
+      float acc1 = 0.0f;
 #pragma unroll
-      for (int i = 0; i < UNROLL; ++i) {
-        const uint32_t sb = s0 + i * ks;
-        if (sb < nb) {
-          h[i] = ldg_stream(hdr + (size_t)sb * 8);
-          qa[i] = ldg_stream(q + (size_t)sb * 64);
-          qb[i] = ldg_stream(q + (size_t)sb * 64 + 8);
+      for (int g = 0; g < 4; ++g) {
+        const float4 xl = xs[g], xh = xs[4 + g];
+        const float xlv[4] = {xl.x, xl.y, xl.z, xl.w}, xhv[4] = {xh.x, xh.y, xh.z, xh.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int idx = 4 * g + e;
+          const uint32_t byte = (ws[g] >> (8 * e)) & 0xffu;
+          const int q0 = int((byte & 0x0fu) | (((f.qh >> idx) & 1u) << 4));
+          const int q1 = int((byte >> 4) | (((f.qh >> (idx + 16)) & 1u) << 4));
+          acc = fmaf(dv * float(q0 - 16), xlv[e], acc);    // ops.cpp:873
+          acc1 = fmaf(dv * float(q1 - 16), xhv[e], acc1);  // ops.cpp:874
         }
       }
-      if (!waited) {
-        mbar_wait(bar, 0);
-        waited = true;
-      }
-#pragma unroll
-      for (int i = 0; i < UNROLL; ++i) {
-        const uint32_t sb = s0 + i * ks;
-        if (sb < nb) {
-          const int4* xp = xs + sb * 16 + c * 4;
-          int sum_lo, sum_hi;
-          q4_k_pair_dots(qa[i], qb[i], xp[0], xp[1], xp[2], xp[3], sum_lo, sum_hi);
-          const uint2 b4 = bs[sb * 4 + c];  // bsums 4c..4c+3 of this super-block
-          const int bs_lo = int(int16_t(b4.x & 0xffffu)) + int(int16_t(b4.x >> 16));
-          const int bs_hi = int(int16_t(b4.y & 0xffffu)) + int(int16_t(b4.y >> 16));
-          int sc1, m1, sc2, m2;
-          q4_k_scale_min(h[i], 2 * c, sc1, m1);
-          q4_k_scale_min(h[i], 2 * c + 1, sc2, m2);
-          const float dx = xd[sb];
-          const float dd = h2f(uint16_t(h[i].x & 0xffffu)) * dx;  // ops.cpp:654
-          const float mm = h2f(uint16_t(h[i].x >> 16)) * dx;      // ops.cpp:655
-          acc += fmaf(dd * float(sc1), float(sum_lo), -((mm * float(m1)) * float(bs_lo)));  // ops.cpp:671
-          acc += fmaf(dd * float(sc2), float(sum_hi), -((mm * float(m2)) * float(bs_hi)));  // ops.cpp:682
-        }
-      }
+      acc += acc1;
     }
-    if (!waited) mbar_wait(bar, 0);
     return acc;
   }
 };
 
-template <int UNROLL>
+// K-quants: unit = one super-block of 256; sub = its 64-element quarter.
+struct BodyQ4_K {
+  static constexpr int C = 2;
+  struct Frag {
+    uint4 h, qa, qb;
+  };
+  __device__ static void load(Frag& f, const GemvArgs& a, uint32_t slab, uint32_t u, int r, int c) {
+    const size_t su = (size_t)slab * a.nb + u;
+    f.h = ldg_stream(reinterpret_cast<const uint4*>(a.x) + su * 8 + r);
+    const uint4* q = reinterpret_cast<const uint4*>(a.q) + (su * 4 + c) * 16 + r;
+    f.qa = ldg_stream(q);
+    f.qb = ldg_stream(q + 8);
+  }
+  __device__ static float compute(const Frag& f, const GemvArgs& a, const uint8_t* sm, uint32_t sb, int c,
+                                  float acc) {
+    const int4* xp = reinterpret_cast<const int4*>(sm) + sb * 16 + c * 4;
+    int sum_lo, sum_hi;
+    q4_k_pair_dots(f.qa, f.qb, xp[0], xp[1], xp[2], xp[3], sum_lo, sum_hi);
+    const uint2 b4 = reinterpret_cast<const uint2*>(sm + a.n_cols)[sb * 4 + c];  // bsums 4c..4c+3
+    const int bs_lo = int(int16_t(b4.x & 0xffffu)) + int(int16_t(b4.x >> 16));
+    const int bs_hi = int(int16_t(b4.y & 0xffffu)) + int(int16_t(b4.y >> 16));
+    int sc1, m1, sc2, m2;
+    q4_k_scale_min(f.h, 2 * c, sc1, m1);
+    q4_k_scale_min(f.h, 2 * c + 1, sc2, m2);
+    const float dx = reinterpret_cast<const float*>(sm + a.n_cols + a.n_cols / 8)[sb];
+    const float dd = h2f(uint16_t(f.h.x & 0xffffu)) * dx;  // ops.cpp:654
+    const float mm = h2f(uint16_t(f.h.x >> 16)) * dx;      // ops.cpp:655
+    acc += fmaf(dd * float(sc1), float(sum_lo), -((mm * float(m1)) * float(bs_lo)));  // ops.cpp:671
+    acc += fmaf(dd * float(sc2), float(sum_hi), -((mm * float(m2)) * float(bs_hi)));  // ops.cpp:682
+    return acc;
+  }
+};
+
 struct BodyQ6_K {
-  __device__ static float run(const GemvArgs& a, const uint8_t* sm, uint64_t* bar, uint32_t slab, int kw, int ks,
-                              int lane) {
-    const int r = lane & 7, sub = lane >> 3, n = sub >> 1, hh = sub & 1;
-    const uint32_t nb = a.nb;
-    const uint4* q = reinterpret_cast<const uint4*>(a.q) + ((size_t)slab * nb * 12 + sub) * 8 + r;
-    const uint2* scp = reinterpret_cast<const uint2*>(a.x) + ((size_t)slab * nb * 8 + r) * 2 + n;
-    const uint16_t* d = reinterpret_cast<const uint16_t*>(a.d) + (size_t)slab * nb * 8 + r;
+  static constexpr int C = 2;
+  struct Frag {
+    uint4 qa, qb, qh;
+    uint2 sc;
+    uint16_t d;
+  };
+  __device__ static void load(Frag& f, const GemvArgs& a, uint32_t slab, uint32_t u, int r, int sub) {
+    const size_t su = (size_t)slab * a.nb + u;
+    const uint4* q = reinterpret_cast<const uint4*>(a.q) + (su * 12 + sub) * 8 + r;
+    f.qa = ldg_stream(q);
+    f.qb = ldg_stream(q + 32);
+    f.qh = ldg_stream(q + 64);
+    f.sc = ldg_stream(reinterpret_cast<const uint2*>(a.x) + (su * 8 + r) * 2 + (sub >> 1));
+    f.d = ldg_stream(reinterpret_cast<const uint16_t*>(a.d) + su * 8 + r);
+  }
+  __device__ static float compute(const Frag& f, const GemvArgs& a, const uint8_t* sm, uint32_t sb, int sub,
+                                  float acc) {
+    const int n = sub >> 1, hh = sub & 1;
     const int4* xs = reinterpret_cast<const int4*>(sm);
     const int16_t* bs = reinterpret_cast<const int16_t*>(sm + a.n_cols);
-    const float* xd = reinterpret_cast<const float*>(sm + a.n_cols + a.n_cols / 8);
-    float acc = 0.0f;
-    bool waited = false;
-    for (uint32_t s0 = kw; s0 < nb; s0 += ks * UNROLL) {
-      uint4 qa[UNROLL], qb[UNROLL], qh[UNROLL];
-      uint2 sc[UNROLL];
-      uint16_t dw[UNROLL];
-#pragma unroll
-      for (int i = 0; i < UNROLL; ++i) {
-        const uint32_t sb = s0 + i * ks;
-        if (sb < nb) {
-          qa[i] = ldg_stream(q + (size_t)sb * 96);
-          qb[i] = ldg_stream(q + (size_t)sb * 96 + 32);
-          qh[i] = ldg_stream(q + (size_t)sb * 96 + 64);
-          sc[i] = ldg_stream(scp + (size_t)sb * 16);
-          dw[i] = ldg_stream(d + (size_t)sb * 8);
-        }
-      }
-      if (!waited) {
-        mbar_wait(bar, 0);
-        waited = true;
-      }
-#pragma unroll
-      for (int i = 0; i < UNROLL; ++i) {
-        const uint32_t sb = s0 + i * ks;
-        if (sb < nb) {
-          const uint32_t g0 = sb * 16 + n * 8 + hh;  // 16-element group of x0
-          const int part = q6_k_part(qa[i], qb[i], qh[i], xs[g0], xs[g0 + 2], xs[g0 + 4], xs[g0 + 6], sbyte(sc[i], hh),
-                                     sbyte(sc[i], hh + 2), sbyte(sc[i], hh + 4), sbyte(sc[i], hh + 6), bs[g0],
-                                     bs[g0 + 2], bs[g0 + 4], bs[g0 + 6]);
-          acc = fmaf(h2f(dw[i]) * xd[sb], float(part), acc);  // ops.cpp:738,762
-        }
-      }
-    }
-    if (!waited) mbar_wait(bar, 0);
-    return acc;
+    const uint32_t g0 = sb * 16 + n * 8 + hh;  // 16-element group of x0
+    const int part = q6_k_part(f.qa, f.qb, f.qh, xs[g0], xs[g0 + 2], xs[g0 + 4], xs[g0 + 6], sbyte(f.sc, hh),
+                               sbyte(f.sc, hh + 2), sbyte(f.sc, hh + 4), sbyte(f.sc, hh + 6), bs[g0], bs[g0 + 2],
+                               bs[g0 + 4], bs[g0 + 6]);
+    const float dx = reinterpret_cast<const float*>(sm + a.n_cols + a.n_cols / 8)[sb];
+    return fmaf(h2f(f.d) * dx, float(part), acc);  // ops.cpp:738,762
   }
 };
 
 // F16 (ops.cpp:541-586): x rounded to f16 first, products exact in fp32.
 // BF16 (ops.cpp:908-916): x stays fp32.  unit = 4 chunks of 8 elements.
-template <int UNROLL, bool IS_BF16>
+template <bool IS_BF16>
 struct BodyHalf {
-  __device__ static float run(const GemvArgs& a, const uint8_t* sm, uint64_t* bar, uint32_t slab, int kw, int ks,
-                              int lane) {
-    const int r = lane & 7, sub = lane >> 3;
-    const uint32_t nb = a.nb;  // chunks of 8
-    const uint4* q = reinterpret_cast<const uint4*>(a.q) + (size_t)slab * nb * 8 + r;
-    float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f, acc3 = 0.0f;
-    bool waited = false;
-    const uint32_t step = 4u * ks;
-    for (uint32_t c0 = 4u * kw + sub; c0 < nb; c0 += step * UNROLL) {
-      uint4 w[UNROLL];
-#pragma unroll
-      for (int i = 0; i < UNROLL; ++i) {
-        const uint32_t c = c0 + i * step;
-        if (c < nb) w[i] = ldg_stream(q + (size_t)c * 8);
+  static constexpr int C = 4;  // 4 units x 32 elements
+  struct Frag {
+    uint4 w;
+  };
+  __device__ static void load(Frag& f, const GemvArgs& a, uint32_t slab, uint32_t u, int r, int sub) {
+    const uint32_t c = 4 * u + sub;
+    if (c < a.nb) f.w = ldg_stream(reinterpret_cast<const uint4*>(a.q) + ((size_t)slab * a.nb + c) * 8 + r);
+  }
+  __device__ static float compute(const Frag& f, const GemvArgs& a, const uint8_t* sm, uint32_t u, int sub,
+                                  float acc) {
+    const uint32_t c = 4 * u + sub;
+    if (c < a.nb) {
+      float a0 = 0.0f, a1 = 0.0f;
+      if (IS_BF16) {
+        const float4 xa = reinterpret_cast<const float4*>(sm)[2 * c];
+        const float4 xb = reinterpret_cast<const float4*>(sm)[2 * c + 1];
+        a0 = fmaf(__uint_as_float(f.w.x << 16), xa.x, a0);
+        a1 = fmaf(__uint_as_float(f.w.x & 0xffff0000u), xa.y, a1);
+        a0 = fmaf(__uint_as_float(f.w.y << 16), xa.z, a0);
+        a1 = fmaf(__uint_as_float(f.w.y & 0xffff0000u), xa.w, a1);
+        a0 = fmaf(__uint_as_float(f.w.z << 16), xb.x, a0);
+        a1 = fmaf(__uint_as_float(f.w.z & 0xffff0000u), xb.y, a1);
+        a0 = fmaf(__uint_as_float(f.w.w << 16), xb.z, a0);
+        a1 = fmaf(__uint_as_float(f.w.w & 0xffff0000u), xb.w, a1);
+      } else {
+        const uint4 xv = reinterpret_cast<const uint4*>(sm)[c];
+        const float2 w0 = __half22float2(*reinterpret_cast<const __half2*>(&f.w.x));
+        const float2 w1 = __half22float2(*reinterpret_cast<const __half2*>(&f.w.y));
+        const float2 w2 = __half22float2(*reinterpret_cast<const __half2*>(&f.w.z));
+        const float2 w3 = __half22float2(*reinterpret_cast<const __half2*>(&f.w.w));
+        const float2 x0 = __half22float2(*reinterpret_cast<const __half2*>(&xv.x));
+        const float2 x1 = __half22float2(*reinterpret_cast<const __half2*>(&xv.y));
+        const float2 x2 = __half22float2(*reinterpret_cast<const __half2*>(&xv.z));
+        const float2 x3 = __half22float2(*reinterpret_cast<const __half2*>(&xv.w));
+        a0 = fmaf(w0.x, x0.x, a0);
+        a1 = fmaf(w0.y, x0.y, a1);
+        a0 = fmaf(w1.x, x1.x, a0);
+        a1 = fmaf(w1.y, x1.y, a1);
+        a0 = fmaf(w2.x, x2.x, a0);
+        a1 = fmaf(w2.y, x2.y, a1);
+        a0 = fmaf(w3.x, x3.x, a0);
+        a1 = fmaf(w3.y, x3.y, a1);
       }
-      if (!waited) {
-        mbar_wait(bar, 0);
-        waited = true;
-      }
-#pragma unroll
-      for (int i = 0; i < UNROLL; ++i) {
-        const uint32_t c = c0 + i * step;
-        if (c < nb) {
-          if (IS_BF16) {
-            const float4 xa = reinterpret_cast<const float4*>(sm)[2 * c];
-            const float4 xb = reinterpret_cast<const float4*>(sm)[2 * c + 1];
-            acc0 = fmaf(__uint_as_float(w[i].x << 16), xa.x, acc0);
-            acc1 = fmaf(__uint_as_float(w[i].x & 0xffff0000u), xa.y, acc1);
-            acc2 = fmaf(__uint_as_float(w[i].y << 16), xa.z, acc2);
-            acc3 = fmaf(__uint_as_float(w[i].y & 0xffff0000u), xa.w, acc3);
-            acc0 = fmaf(__uint_as_float(w[i].z << 16), xb.x, acc0);
-            acc1 = fmaf(__uint_as_float(w[i].z & 0xffff0000u), xb.y, acc1);
-            acc2 = fmaf(__uint_as_float(w[i].w << 16), xb.z, acc2);
-            acc3 = fmaf(__uint_as_float(w[i].w & 0xffff0000u), xb.w, acc3);
-          } else {
-            const uint4 xv = reinterpret_cast<const uint4*>(sm)[c];
-            const float2 w0 = __half22float2(*reinterpret_cast<const __half2*>(&w[i].x));
-            const float2 w1 = __half22float2(*reinterpret_cast<const __half2*>(&w[i].y));
-            const float2 w2 = __half22float2(*reinterpret_cast<const __half2*>(&w[i].z));
-            const float2 w3 = __half22float2(*reinterpret_cast<const __half2*>(&w[i].w));
-            const float2 x0 = __half22float2(*reinterpret_cast<const __half2*>(&xv.x));
-            const float2 x1 = __half22float2(*reinterpret_cast<const __half2*>(&xv.y));
-            const float2 x2 = __half22float2(*reinterpret_cast<const __half2*>(&xv.z));
-            const float2 x3 = __half22float2(*reinterpret_cast<const __half2*>(&xv.w));
-            acc0 = fmaf(w0.x, x0.x, acc0);
-            acc1 = fmaf(w0.y, x0.y, acc1);
-            acc2 = fmaf(w1.x, x1.x, acc2);
-            acc3 = fmaf(w1.y, x1.y, acc3);
-            acc0 = fmaf(w2.x, x2.x, acc0);
-            acc1 = fmaf(w2.y, x2.y, acc1);
-            acc2 = fmaf(w3.x, x3.x, acc2);
-            acc3 = fmaf(w3.y, x3.y, acc3);
-          }
-        }
-      }
+      acc += a0 + a1;
     }
-    if (!waited) mbar_wait(bar, 0);
-    return (acc0 + acc1) + (acc2 + acc3);
+    return acc;
   }
 };
 
 // ------------------------------------------------------------ kernel skeleton
-template <int KSPLIT>
-struct Cfg {
-  static constexpr int WARPS = KSPLIT >= 4 ? KSPLIT : 4;
-  static constexpr int SLABS_PER_CTA = WARPS / KSPLIT;
+template <class B, int N>
+struct FragSet {
+  typename B::Frag f[N];
 };
 
-template <class Body, int KSPLIT>
-__global__ void __launch_bounds__(Cfg<KSPLIT>::WARPS * 32) gemv_slab_kernel(const GemvArgs a) {
-  extern __shared__ __align__(128) uint8_t sm_act[];
+template <class B, int N>
+__device__ __forceinline__ void load_item(FragSet<B, N>& fs, const GemvArgs& a, uint32_t slab, uint32_t j, int r,
+                                          int sub) {
+#pragma unroll
+  for (int t = 0; t < N; ++t) {
+    const uint32_t u = j * N + t;
+    if (u < a.units) B::load(fs.f[t], a, slab, u, r, sub);
+  }
+}
+
+template <class B, int N>
+__device__ __forceinline__ float compute_item(const FragSet<B, N>& fs, const GemvArgs& a, const uint8_t* sm,
+                                              uint32_t j, int sub) {
+  float acc = 0.0f;
+#pragma unroll
+  for (int t = 0; t < N; ++t) {
+    const uint32_t u = j * N + t;
+    if (u < a.units) acc = B::compute(fs.f[t], a, sm, u, sub, acc);
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+  return acc;  // lanes 0..7: chunk partial of rows 0..7
+}
+
+// CTA = W warps over S consecutive slabs.  The S*J work items (slab, K-chunk)
+// are dealt round-robin to the warps; each warp loads one item (C units = 4
+// independent 128-bit loads per lane) per round trip, folds it, and drops the
+// chunk partial (8 floats) in shared memory.  After one barrier, thread (s, r)
+// adds the J chunk partials of its row in canonical order.  Bytes in flight
+// come from occupancy (small register footprint, many resident CTAs), not from
+// a deep per-warp pipeline: a warp has only 6 scoreboard slots, and a second
+// generation of loads in flight makes ptxas share them, which turns the
+// address setup of the next loads into waits on unrelated loads (measured 2x
+// slower, profiles/r01_notes.md).
+template <class B, int W>
+__global__ void __launch_bounds__(W * 32) gemv_slab_kernel(const GemvArgs a, const uint32_t S) {
+  extern __shared__ __align__(128) uint8_t sm_act[];  // [act_bytes][S * chunks * 8 floats]
   __shared__ __align__(8) uint64_t bar;
-  __shared__ float red[Cfg<KSPLIT>::WARPS][LLMI_SLAB];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = lane & 7, sub = lane >> 3;
   if (threadIdx.x == 0) mbar_init(&bar, 1);
   __syncthreads();
   if (threadIdx.x == 0) {
     mbar_expect_tx(&bar, a.act_bytes);
     bulk_g2s(sm_act, a.act, a.act_bytes, &bar);
   }
-  const uint32_t slab = blockIdx.x * Cfg<KSPLIT>::SLABS_PER_CTA + warp / KSPLIT;
-  const int kw = warp % KSPLIT;
-  float acc = 0.0f;
-  if (slab < a.n_slabs) {
-    acc = Body::run(a, sm_act, &bar, slab, kw, KSPLIT, lane);
-  } else {
-    mbar_wait(&bar, 0);  // never exit with the bulk copy into our smem in flight
-  }
-  acc += __shfl_xor_sync(0xffffffffu, acc, 8);
-  acc += __shfl_xor_sync(0xffffffffu, acc, 16);
-  const uint32_t row = slab * LLMI_SLAB + lane;
-  if (KSPLIT == 1) {
-    if (lane < LLMI_SLAB && slab < a.n_slabs && row < a.n_local) a.out[row] = acc;
-  } else {
-    if (lane < LLMI_SLAB) red[warp][lane] = acc;
-    __syncthreads();
-    if (kw == 0 && lane < LLMI_SLAB && slab < a.n_slabs && row < a.n_local) {
-      float s = red[warp][lane];
-#pragma unroll
-      for (int i = 1; i < KSPLIT; ++i) s += red[warp + i][lane];  // fixed order: deterministic
-      a.out[row] = s;
+  constexpr int N = B::C;
+  const uint32_t J = a.chunks;
+  const uint32_t slab0 = blockIdx.x * S;
+  const uint32_t n_sl = min(S, a.n_slabs - slab0);
+  const uint32_t n_items = n_sl * J;
+  float* part = reinterpret_cast<float*>(sm_act + a.act_bytes);
+  bool waited = false;
+#pragma unroll 1
+  for (uint32_t t = warp; t < n_items; t += W) {
+    const uint32_t sl = t / J, j = t - sl * J;
+    FragSet<B, N> f;
+    load_item<B, N>(f, a, slab0 + sl, j, r, sub);
+    if (!waited) {
+      mbar_wait(&bar, 0);
+      waited = true;
     }
+    const float v = compute_item<B, N>(f, a, sm_act, j, sub);
+    if (lane < LLMI_SLAB) part[t * LLMI_SLAB + lane] = v;
+  }
+  if (!waited) mbar_wait(&bar, 0);  // never exit with the bulk copy into our smem in flight
+  __syncthreads();
+  for (uint32_t idx = threadIdx.x; idx < n_sl * LLMI_SLAB; idx += W * 32) {
+    const uint32_t sl = idx / LLMI_SLAB, rr = idx % LLMI_SLAB;
+    const float* p = part + (size_t)sl * J * LLMI_SLAB + rr;
+    float sum = p[0];
+    for (uint32_t j = 1; j < J; ++j) sum += p[j * LLMI_SLAB];  // canonical order
+    const uint32_t row = (slab0 + sl) * LLMI_SLAB + rr;
+    if (row < a.n_local) a.out[row] = sum;
   }
 }
 
@@ -591,59 +540,67 @@ __global__ void block_dots_kernel(const GemvArgs a, uint32_t type, int32_t* dots
 // ------------------------------------------------------------------ dispatch
 constexpr int MAX_DYN_SMEM = 96 * 1024;  // fp32 activations of K=21504 need 86 KB
 
-template <class Body, int KSPLIT>
-cudaError_t launch_one(const GemvArgs& a, cudaStream_t s) {
-  using C = Cfg<KSPLIT>;
-  const uint32_t grid = (a.n_slabs + C::SLABS_PER_CTA - 1) / C::SLABS_PER_CTA;
-  gemv_slab_kernel<Body, KSPLIT><<<grid, C::WARPS * 32, a.act_bytes, s>>>(a);
+int g_sm_count = 148;
+
+using Q4_0 = BodyQ4_0;
+using Q8_0 = BodyQ8_0;
+using Q5_0 = BodyQ5_0;
+using Q4_K = BodyQ4_K;
+using Q6_K = BodyQ6_K;
+using F16 = BodyHalf<false>;
+using BF16 = BodyHalf<true>;
+
+// Benches can pin the CTA shape: g_warps in {0 (heuristic), 4, 8, 16},
+// g_slabs_per_cta in {0 (heuristic), 1..}.  Results never depend on it.
+int g_warps = 0, g_slabs_per_cta = 0;
+
+template <class B, int W>
+cudaError_t launch_w(const GemvArgs& a, uint32_t S, cudaStream_t s) {
+  const size_t smem = a.act_bytes + size_t(S) * a.chunks * LLMI_SLAB * 4;
+  const uint32_t grid = (a.n_slabs + S - 1) / S;
+  gemv_slab_kernel<B, W><<<grid, W * 32, smem, s>>>(a, S);
   return cudaGetLastError();
 }
 
-template <class Body>
-cudaError_t launch_ks(const GemvArgs& a, int ks, cudaStream_t s) {
-  switch (ks) {
-    case 1: return launch_one<Body, 1>(a, s);
-    case 2: return launch_one<Body, 2>(a, s);
-    case 4: return launch_one<Body, 4>(a, s);
-    case 8: return launch_one<Body, 8>(a, s);
-    default: return launch_one<Body, 16>(a, s);
+template <class B>
+cudaError_t launch_body(const GemvArgs& a, cudaStream_t s) {
+  const uint64_t n_items = uint64_t(a.n_slabs) * a.chunks;
+  // Heuristic from tools/gemv_sweep.py (profiles/r01_sweep_v4.jsonl): one slab
+  // per CTA and the fewest warps per CTA that still put ~24 warps on every SM
+  // (more, smaller CTAs beat fewer, larger ones); never more warps than the
+  // slab has chunks; the k-quants (bigger register footprint) stop at 8.
+  // Huge-N / short-K matrices (logits) get 4 slabs per CTA so that every warp
+  // streams several items and the activation staging is amortised.
+  const bool kq = B::C == 2;
+  int W = 4;
+  while (W < (kq ? 8 : 16) && uint64_t(a.n_slabs) * W < uint64_t(g_sm_count) * 24) W *= 2;
+  if (a.chunks <= 4) W = 4;
+  else if (a.chunks <= 8 && W > 8) W = 8;
+  uint32_t S = (a.chunks <= 10 && n_items >= uint64_t(g_sm_count) * 64 * 6) ? 4 : 1;
+  if (g_warps) W = g_warps;
+  if (g_slabs_per_cta) S = uint32_t(g_slabs_per_cta);
+  while (S > 1 && a.act_bytes + size_t(S) * a.chunks * LLMI_SLAB * 4 > size_t(MAX_DYN_SMEM)) --S;
+  switch (W) {
+    case 4: return launch_w<B, 4>(a, S, s);
+    case 8: return launch_w<B, 8>(a, S, s);
+    default: return launch_w<B, 16>(a, S, s);
   }
 }
 
-template <class Body, int KSPLIT>
-cudaError_t optin_one() {
-  return cudaFuncSetAttribute(gemv_slab_kernel<Body, KSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              MAX_DYN_SMEM);
-}
-template <class Body>
-cudaError_t optin_all() {
+template <class B>
+cudaError_t optin() {
   cudaError_t e;
-  if ((e = optin_one<Body, 1>()) != cudaSuccess) return e;
-  if ((e = optin_one<Body, 2>()) != cudaSuccess) return e;
-  if ((e = optin_one<Body, 4>()) != cudaSuccess) return e;
-  if ((e = optin_one<Body, 8>()) != cudaSuccess) return e;
-  return optin_one<Body, 16>();
+  if ((e = cudaFuncSetAttribute(gemv_slab_kernel<B, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                MAX_DYN_SMEM)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(gemv_slab_kernel<B, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                MAX_DYN_SMEM)) != cudaSuccess) return e;
+  return cudaFuncSetAttribute(gemv_slab_kernel<B, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
 }
 
-using Q4_0 = BodyQ4_0<4>;
-using Q8_0 = BodyQ8_0<2>;
-using Q5_0 = BodyQ5_0<2>;
-using Q4_K = BodyQ4_K<2>;
-using Q6_K = BodyQ6_K<2>;
-using F16 = BodyHalf<4, false>;
-using BF16 = BodyHalf<4, true>;
-
-int g_sm_count = 148;
-
-// K-split heuristic: enough warps to cover the chip (~16 per SM) while every
-// warp still owns >= 2 K-units.
-int pick_ksplit(const llmi_weight_s& w) {
-  const uint64_t units = (w.type == LLMI_Q4_K || w.type == LLMI_Q6_K) ? w.nb : (w.nb + 3) / 4;
-  const uint64_t want = uint64_t(g_sm_count) * 16;
-  int ks = 1;
-  while (ks < 16 && w.n_slabs * ks < want && units / (ks * 2) >= 2) ks *= 2;
-  return ks;
+uint32_t units_of(const llmi_weight_s& w) {
+  return (w.type == LLMI_Q4_K || w.type == LLMI_Q6_K) ? uint32_t(w.nb) : uint32_t((w.nb + 3) / 4);
 }
+uint32_t chunk_units_of(uint32_t type) { return (type == LLMI_Q4_K || type == LLMI_Q6_K) ? 2u : 4u; }
 
 }  // namespace
 
@@ -660,19 +617,30 @@ int llmi_act_kind_for(uint32_t t) {
   }
 }
 
+// K-chunks (work items) per slab of a weight; also sizes the split-slab scratch.
+uint32_t llmi_gemv_chunks(const llmi_weight_s& w) {
+  const uint32_t u = units_of(w), c = chunk_units_of(w.type);
+  return (u + c - 1) / c;
+}
+
+void llmi_gemv_set_shape(int warps, int slabs_per_cta) {
+  g_warps = warps;
+  g_slabs_per_cta = slabs_per_cta;
+}
+
 cudaError_t llmi_gemv_init() {
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   e = cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
   if (e != cudaSuccess) return e;
-  if ((e = optin_all<Q4_0>()) != cudaSuccess) return e;
-  if ((e = optin_all<Q8_0>()) != cudaSuccess) return e;
-  if ((e = optin_all<Q5_0>()) != cudaSuccess) return e;
-  if ((e = optin_all<Q4_K>()) != cudaSuccess) return e;
-  if ((e = optin_all<Q6_K>()) != cudaSuccess) return e;
-  if ((e = optin_all<F16>()) != cudaSuccess) return e;
-  return optin_all<BF16>();
+  if ((e = optin<Q4_0>()) != cudaSuccess) return e;
+  if ((e = optin<Q8_0>()) != cudaSuccess) return e;
+  if ((e = optin<Q5_0>()) != cudaSuccess) return e;
+  if ((e = optin<Q4_K>()) != cudaSuccess) return e;
+  if ((e = optin<Q6_K>()) != cudaSuccess) return e;
+  if ((e = optin<F16>()) != cudaSuccess) return e;
+  return optin<BF16>();
 }
 
 static GemvArgs make_args(const llmi_weight_s& w, const llmi_act_s& a, float* out) {
@@ -687,23 +655,23 @@ static GemvArgs make_args(const llmi_weight_s& w, const llmi_act_s& a, float* ou
   g.n_slabs = uint32_t(w.n_slabs);
   g.nb = uint32_t(w.nb);
   g.n_cols = uint32_t(w.n_cols);
+  g.units = units_of(w);
+  g.chunks = llmi_gemv_chunks(w);
   return g;
 }
 
-cudaError_t llmi_launch_gemv(const llmi_weight_s& w, const llmi_act_s& a, float* out, int ksplit_override,
-                             cudaStream_t s) {
+cudaError_t llmi_launch_gemv(const llmi_weight_s& w, const llmi_act_s& a, float* out, cudaStream_t s) {
   if (w.n_slabs == 0) return cudaSuccess;
   const GemvArgs g = make_args(w, a, out);
   if (g.act_bytes > (uint32_t)MAX_DYN_SMEM) return cudaErrorInvalidValue;
-  const int ks = ksplit_override > 0 ? ksplit_override : pick_ksplit(w);
   switch (w.type) {
-    case LLMI_Q4_0: return launch_ks<Q4_0>(g, ks, s);
-    case LLMI_Q8_0: return launch_ks<Q8_0>(g, ks, s);
-    case LLMI_Q5_0: return launch_ks<Q5_0>(g, ks, s);
-    case LLMI_Q4_K: return launch_ks<Q4_K>(g, ks, s);
-    case LLMI_Q6_K: return launch_ks<Q6_K>(g, ks, s);
-    case LLMI_F16: return launch_ks<F16>(g, ks, s);
-    case LLMI_BF16: return launch_ks<BF16>(g, ks, s);
+    case LLMI_Q4_0: return launch_body<Q4_0>(g, s);
+    case LLMI_Q8_0: return launch_body<Q8_0>(g, s);
+    case LLMI_Q5_0: return launch_body<Q5_0>(g, s);
+    case LLMI_Q4_K: return launch_body<Q4_K>(g, s);
+    case LLMI_Q6_K: return launch_body<Q6_K>(g, s);
+    case LLMI_F16: return launch_body<F16>(g, s);
+    case LLMI_BF16: return launch_body<BF16>(g, s);
     default: return cudaErrorInvalidValue;
   }
 }

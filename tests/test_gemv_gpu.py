@@ -31,8 +31,8 @@ def _weights(t, n, k, seed):
     return synth.random_blocks(t, n, k, seed=seed)
 
 
-def _run(ops, t, w, x, n, k, ksplit=0, row_range=None):
-    ops.set_ksplit(t, ksplit)
+def _run(ops, t, w, x, n, k, shape=(0, 0), row_range=None):
+    ops.set_gemv_shape(*shape)
     rb, re = row_range or (0, n)
     dw = ops.DeviceWeight(w, t, k, n, rb, re)
     dx = ops.DeviceVector(k, x)
@@ -47,7 +47,7 @@ def _run(ops, t, w, x, n, k, ksplit=0, row_range=None):
         extra["xq"] = act.export_q8_0(k) if t in (Q4_0, Q8_0) else act.export_q8_k(k)
     for h in (dw, dx, do, act):
         h.close()
-    ops.set_ksplit(t, 0)
+    ops.set_gemv_shape(0, 0)
     return o, extra
 
 
@@ -125,12 +125,15 @@ def test_matvec_parity(gpu_ops, port, t, k, n):
 @pytest.mark.parametrize("t,k,n", [(Q4_0, 1152, 1030), (Q8_0, 3840, 264), (Q4_K, 2560, 136), (Q6_K, 2560, 136),
                                    (F16, 1152, 520), (Q5_0, 1152, 72), (BF16, 1152, 72)],
                          ids=lambda v: str(v))
-@pytest.mark.parametrize("ksplit", [1, 2, 4, 8, 16])
-def test_every_ksplit_gives_the_same_rows(gpu_ops, port, t, k, n, ksplit):
+def test_result_is_independent_of_the_grid(gpu_ops, port, t, k, n):
+    # canonical chunked summation: every CTA shape gives the same bits
     w = _weights(t, n, k, seed=77 + t)
-    x = np.random.default_rng(ksplit).standard_normal(k).astype(np.float32)
-    o, _ = _run(gpu_ops, t, w, x, n, k, ksplit=ksplit)
-    _check(o, port.mat_vec_mul(t, w, x, n, k), f"ksplit={ksplit}")
+    x = np.random.default_rng(t).standard_normal(k).astype(np.float32)
+    base, _ = _run(gpu_ops, t, w, x, n, k, shape=(4, 1))
+    _check(base, port.mat_vec_mul(t, w, x, n, k), "shape=(4,1)")
+    for shape in ((4, 4), (8, 1), (8, 3), (16, 1), (16, 7), (0, 0)):
+        o, _ = _run(gpu_ops, t, w, x, n, k, shape=shape)
+        assert np.array_equal(o.view(np.uint32), base.view(np.uint32)), f"shape={shape}"
 
 
 def test_matvec_matches_golden_from_compiled_reference(gpu_ops, golden):
@@ -162,13 +165,12 @@ def test_row_sharded_handles_reproduce_the_full_result_bitwise(gpu_ops):
     t, k, n = Q4_0, 5376, 4096
     w = _weights(t, n, k, seed=9)
     x = np.random.default_rng(9).standard_normal(k).astype(np.float32)
-    gpu_ops.set_ksplit(t, 4)  # same K-split everywhere: identical per-row order
-    full, _ = _run(gpu_ops, t, w, x, n, k, ksplit=4)
+    full, _ = _run(gpu_ops, t, w, x, n, k)
     for parts in (2, 4, 8):
         got = np.zeros(n, np.float32)
         for r in range(parts):
             rb, re = r * n // parts, (r + 1) * n // parts
-            o, _ = _run(gpu_ops, t, w, x, n, k, ksplit=4, row_range=(rb, re))
+            o, _ = _run(gpu_ops, t, w, x, n, k, row_range=(rb, re))
             got[rb:re] = o[rb:re]
         assert np.array_equal(got.view(np.uint32), full.view(np.uint32)), f"{parts}-way shard"
 

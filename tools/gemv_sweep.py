@@ -4,7 +4,7 @@ Each (format, K, N) is timed inside a CUDA graph that launches the GEMV over a
 rotation of distinct weight copies totalling >= 2x L2 (so small matrices are
 read from HBM, not L2), CUDA events on the capturing stream.  Prints one JSON
 line per case: algorithmic GB/s (SURVEY §8d byte count) and fraction of the
-measured HBM peak.  Usage: python tools/gemv_sweep.py [--ksplit 0,1,2,4,8,16] [--quick]
+measured HBM peak.  Usage: python tools/gemv_sweep.py [--shapes 0x0,4x4,8x1] [--quick]
 """
 import argparse
 import json
@@ -27,7 +27,7 @@ def peak_gbs() -> float:
     return json.loads(p.read_text())["hbm_gbs"] if p.exists() else 6650.0
 
 
-def time_case(t, k, n, ksplit, iters=20, with_quant=False):
+def time_case(t, k, n, shape, iters=20, with_quant=False):
     wbytes = n * synth.row_bytes(t, k)
     copies = max(2, min(64, -(-2 * L2_BYTES // wbytes)))
     raw = synth.random_blocks(t, n, k, seed=1)
@@ -35,7 +35,7 @@ def time_case(t, k, n, ksplit, iters=20, with_quant=False):
     x = ops.DeviceVector(k, np.random.default_rng(0).standard_normal(k).astype(np.float32))
     o = ops.DeviceVector(n)
     act = ops.Activation(k)
-    ops.set_ksplit(t, ksplit)
+    ops.set_gemv_shape(*shape)
     s = torch.cuda.Stream()
     with torch.cuda.stream(s):
         act.prepare(ws[0], x, s.cuda_stream)
@@ -60,13 +60,13 @@ def time_case(t, k, n, ksplit, iters=20, with_quant=False):
     us = e0.elapsed_time(e1) * 1e3 / (iters * copies)
     for h in ws + [x, o, act]:
         h.close()
-    ops.set_ksplit(t, 0)
+    ops.set_gemv_shape(0, 0)
     return us, copies
 
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--ksplit", default="0")
+    ap.add_argument("--shapes", default="0x0", help="comma list of WxS, 0x0 = heuristic")
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--with-quant", action="store_true")
     a = ap.parse_args()
@@ -85,11 +85,12 @@ def main():
         cases = [(Q4_0, 1152, 6912), (Q4_0, 5376, 21504), (Q4_0, 21504, 5376), (F16, 1152, 262144),
                  (Q8_0, 3840, 15360), (Q4_K, 2560, 10240), (Q6_K, 10240, 2560)]
     for t, k, n in cases:
-        for ks in [int(v) for v in a.ksplit.split(",")]:
-            us, copies = time_case(t, k, n, ks, with_quant=a.with_quant)
+        for shape in a.shapes.split(","):
+            W, S = (int(v) for v in shape.split("x"))
+            us, copies = time_case(t, k, n, (W, S), with_quant=a.with_quant)
             b = synth.algorithmic_bytes(t, n, k)
             gbs = b / us * 1e-3
-            print(json.dumps({"fmt": synth.TYPE_NAMES[t], "K": k, "N": n, "ksplit": ks, "us": round(us, 3),
+            print(json.dumps({"fmt": synth.TYPE_NAMES[t], "K": k, "N": n, "shape": shape, "us": round(us, 3),
                               "alg_MB": round(b / 1e6, 3), "GBps": round(gbs, 1), "frac_of_measured_peak":
                               round(gbs / peak, 4), "copies": copies}), flush=True)
 
