@@ -146,6 +146,32 @@ int llmi_host_mat_vec_mul(llmi_weight_t w, const float* x, uint64_t n_x,
 int llmi_host_quantize_row_q8_0(const float* x, uint64_t n, void* y);
 int llmi_host_quantize_row_q8_k(const float* x, uint64_t n, void* y);
 
+/* ---- device-resident forward ------------------------------ */
+
+typedef struct llmi_model_s* llmi_model_t;
+
+/* Model(GGUFFile&) (model.h:78, model.cpp:13-56) on the device: parses the GGUF
+ * image (borrowed only during the call), uploads + repacks every matrix once,
+ * allocates activations and an fp16 KV cache of max_positions (0 = 4096).
+ * Architecture "gemma3" only; anything else returns LLMI_ERR_TYPE (use the
+ * ops.h drop-in with the reference's model.cpp for those). */
+int llmi_model_load(const void* gguf_image, uint64_t size, uint32_t max_positions, llmi_model_t* out);
+int llmi_model_free(llmi_model_t m);
+/* dims[8] = {n_layer, n_embd, n_ff, n_head, n_head_kv, head_dim, vocab, max_positions} */
+int llmi_model_info(llmi_model_t m, uint32_t* dims, uint64_t* weight_bytes);
+/* Model::forward(tokens, pos) (model.h:91, model.cpp:706-1048): host token ids
+ * in, host logits of the last token out; activations and KV stay on the device;
+ * prefill is the reference's per-token loop.  Synchronous. */
+int llmi_model_forward(llmi_model_t m, const int32_t* tokens, int n_tokens, int pos, float* logits_host);
+/* Greedy generation loop of main.cpp:172-221 entirely on the device (argmax of
+ * step i feeds step i+1; one CUDA graph launch per token): consumes first_token
+ * at position pos, returns n_steps token ids and the CUDA-event time. */
+int llmi_model_decode_greedy(llmi_model_t m, int32_t first_token, int pos, int n_steps, int32_t* out_tokens,
+                             float* ms_device);
+int llmi_model_last_logits(llmi_model_t m, float* logits_host);
+/* kernels launched per decode token (for bench.py's gpu_launches) */
+int llmi_model_launches_per_step(llmi_model_t m);
+
 /* ---- device memory helpers (benches / tests; plain cudaMalloc wrappers) - */
 int llmi_dev_alloc(uint64_t bytes, void** out_dev);
 int llmi_dev_free(void* dev);

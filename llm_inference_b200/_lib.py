@@ -46,6 +46,13 @@ SIGNATURES = {
     "llmi_host_mat_vec_mul": (_int, [_vp, _vp, _u64, _vp, _u64]),
     "llmi_host_quantize_row_q8_0": (_int, [_vp, _u64, _vp]),
     "llmi_host_quantize_row_q8_k": (_int, [_vp, _u64, _vp]),
+    "llmi_model_load": (_int, [_vp, _u64, _u32, C.POINTER(_vp)]),
+    "llmi_model_free": (_int, [_vp]),
+    "llmi_model_info": (_int, [_vp, C.POINTER(_u32), C.POINTER(_u64)]),
+    "llmi_model_forward": (_int, [_vp, _vp, _int, _int, _vp]),
+    "llmi_model_decode_greedy": (_int, [_vp, C.c_int32, _int, _int, _vp, C.POINTER(C.c_float)]),
+    "llmi_model_last_logits": (_int, [_vp, _vp]),
+    "llmi_model_launches_per_step": (_int, [_vp]),
     "llmi_dev_alloc": (_int, [_u64, C.POINTER(_vp)]),
     "llmi_dev_free": (_int, [_vp]),
     "llmi_h2d": (_int, [_vp, _vp, _u64]),

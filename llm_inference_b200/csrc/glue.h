@@ -1,0 +1,63 @@
+// Launchers of the device-resident glue kernels (glue.cu).
+#pragma once
+
+#include <cuda_fp16.h>
+
+#include "llmi_internal.h"
+
+struct EmbedArgs {
+  uint32_t type;
+  uint64_t nb;
+  uint32_t n_cols;
+  const uint8_t *q, *d, *x;
+};
+
+inline EmbedArgs make_embed_args(const llmi_weight_s& w) {
+  return EmbedArgs{w.type, w.nb, uint32_t(w.n_cols), w.p_q, w.p_d, w.p_x};
+}
+
+struct NormArgs {
+  const float* y = nullptr;       // optional: output of the previous mat-vec (post-norm + residual stage)
+  const float* w_post = nullptr;  // its norm weight
+  float* h = nullptr;             // residual stream (updated in place when y != nullptr)
+  const float* w = nullptr;       // optional: norm weight of the next stage
+  uint32_t n = 0;
+  double eps = 0.0;
+  float* xn_out = nullptr;        // optional fp32 copy of the normalized vector
+  int act_kind = ACT_NONE;
+  uint8_t* act_buf = nullptr;
+  int32_t* pos_inc = nullptr;     // optional device counter to bump (end of a token step)
+};
+
+struct QkvArgs {
+  const float *q, *k, *v;
+  const float *wq_norm, *wk_norm;
+  uint32_t H, HK, D;
+  double eps;
+  float rope_base, rope_scale, attn_scale;
+  const int32_t* pos;
+  float* q_out;
+  __half *kcache, *vcache;  // this layer's [t_max][HK][D]
+};
+
+struct AttnArgs {
+  const float* q;  // [H*D], already normed/rotated/scaled
+  const __half *kcache, *vcache;
+  uint32_t H, HK, D, t_max;
+  const int32_t* pos;
+  float softcap;
+  float* out;  // [H*D]
+};
+
+cudaError_t llmi_launch_embed(const EmbedArgs& a, const int32_t* token, float scale, float* h, cudaStream_t s);
+cudaError_t llmi_launch_norm_act(const NormArgs& a, cudaStream_t s);
+cudaError_t llmi_launch_act(const float* x, uint32_t n, int kind, uint8_t* buf, cudaStream_t s);
+cudaError_t llmi_launch_qkv_post(const QkvArgs& a, cudaStream_t s);
+size_t llmi_attention_smem(uint32_t t_max, uint32_t D);
+cudaError_t llmi_attention_init(uint32_t t_max, uint32_t D);
+cudaError_t llmi_launch_attention(const AttnArgs& a, cudaStream_t s);
+cudaError_t llmi_launch_geglu_act(const float* gate, const float* up, uint32_t n, int kind, uint8_t* buf,
+                                  float* hidden_out, cudaStream_t s);
+cudaError_t llmi_launch_argmax(float* logits, uint32_t n, float softcap, int32_t* cur_tok, int32_t* gen,
+                               int32_t* gen_count, cudaStream_t s);
+cudaError_t llmi_launch_softcap(float* logits, uint32_t n, float softcap, cudaStream_t s);

@@ -1,0 +1,459 @@
+// Device-resident Gemma-3 forward: weights uploaded once,
+// activations and the fp16 KV cache resident on the device between ops, one
+// decode token = one CUDA graph.  Follows Model::forward (model.cpp:706-1048)
+// call for call: the 7 mat-vecs per layer + the logits mat-vec are llmi_gemv
+// launches on the same repacked weights as the ops.h drop-in; everything
+// between them is glue.cu.  Prefill is the reference's per-token loop
+// (model.cpp:752-756 etc.): n tokens = n decode-shaped steps without logits.
+//
+// Only the "gemma3" architecture is handled here (gemma4's per-layer
+// embeddings / shared KV / V-norm stay on the drop-in path through the
+// reference's own model.cpp).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "glue.h"
+#include "gguf_reader.h"
+
+namespace {
+
+struct ActSet {  // one activation buffer per kind, created on demand
+  llmi_act_t a[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
+struct LayerW {
+  llmi_weight_t q = nullptr, k = nullptr, v = nullptr, o = nullptr, gate = nullptr, up = nullptr, down = nullptr;
+  float *attn_norm = nullptr, *ffn_norm = nullptr, *post_attn_norm = nullptr, *post_ffw_norm = nullptr;
+  float *q_norm = nullptr, *k_norm = nullptr;
+  bool swa = false;
+};
+
+}  // namespace
+
+struct llmi_model_s {
+  uint32_t L = 0, E = 0, F = 0, H = 0, HK = 0, D = 0, V = 0, t_max = 0;
+  double eps = 0;
+  float rope_base = 0, rope_scale = 1.0f, attn_scale = 0, attn_softcap = 0, final_softcap = 0;
+  std::vector<LayerW> layers;
+  llmi_weight_t embd = nullptr;
+  float* out_norm = nullptr;
+  std::vector<void*> owned;  // plain device allocations to free
+  float *h = nullptr, *xn = nullptr, *q = nullptr, *k = nullptr, *v = nullptr, *q_rot = nullptr, *attn = nullptr,
+        *attn_out = nullptr, *gate = nullptr, *up = nullptr, *ffn_out = nullptr, *logits = nullptr;
+  ActSet act_E, act_HD, act_F;
+  __half *kcache = nullptr, *vcache = nullptr;
+  int32_t *d_tok = nullptr, *d_pos = nullptr, *d_gen = nullptr, *d_gen_count = nullptr, *d_toks = nullptr;
+  uint32_t toks_cap = 0, gen_cap = 0;
+  cudaStream_t stream = nullptr;
+  cudaGraphExec_t decode_graph = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  float* logits_pinned = nullptr;
+  uint64_t weight_bytes = 0;
+  int launches_per_step = 0;
+};
+
+namespace {
+
+#define M_TRY(expr)                                          \
+  do {                                                       \
+    cudaError_t _e = (expr);                                 \
+    if (_e != cudaSuccess) return llmi_cuda_fail(_e, #expr); \
+  } while (0)
+#define M_RC(expr)            \
+  do {                        \
+    int _rc = (expr);         \
+    if (_rc != LLMI_OK) return _rc; \
+  } while (0)
+
+int dev_alloc(llmi_model_s* m, void** p, size_t bytes) {
+  M_TRY(cudaMalloc(p, bytes ? bytes : 16));
+  m->owned.push_back(*p);
+  return LLMI_OK;
+}
+
+int upload_f32(llmi_model_s* m, const llmi::GgufTensor* t, uint64_t n, float** out, const char* name) {
+  if (!t) return llmi_fail(LLMI_ERR_ARG, std::string("llmi_model_load: missing tensor ") + name);
+  if (t->type != LLMI_F32 || t->n_elements() < n)
+    return llmi_fail(LLMI_ERR_TYPE, std::string("llmi_model_load: ") + name + " must be F32");
+  M_RC(dev_alloc(m, (void**)out, n * 4));
+  M_TRY(cudaMemcpy(*out, t->data, n * 4, cudaMemcpyHostToDevice));
+  return LLMI_OK;
+}
+
+int upload_matrix(llmi_model_s* m, const llmi::GgufTensor* t, uint64_t k, uint64_t n, llmi_weight_t* out,
+                  const char* name) {
+  if (!t) return llmi_fail(LLMI_ERR_ARG, std::string("llmi_model_load: missing tensor ") + name);
+  if (t->shape.size() != 2 || t->shape[0] != k || t->shape[1] < n)
+    return llmi_fail(LLMI_ERR_SIZE, std::string("llmi_model_load: unexpected shape of ") + name);
+  M_RC(llmi_weight_upload(t->data, t->type, k, n, 0, n, out));
+  m->weight_bytes += llmi_row_bytes(t->type, k) * n;
+  return LLMI_OK;
+}
+
+llmi_act_t get_act(ActSet& s, int kind, uint64_t n) {
+  if (!s.a[kind]) {
+    if (llmi_act_create(n, &s.a[kind]) != LLMI_OK) return nullptr;
+  }
+  s.a[kind]->kind = kind;
+  s.a[kind]->n = n;
+  return s.a[kind];
+}
+
+// Emits every activation kind the consumers of one fp32 vector need.  `first`
+// was already produced by the fused kernel; any other kind is quantized from
+// the fp32 copy.
+int extra_acts(llmi_model_s* m, ActSet& set, const float* x, uint64_t n, int first,
+               std::initializer_list<llmi_weight_t> consumers) {
+  bool done[5] = {false, false, false, false, false};
+  done[first] = true;
+  for (llmi_weight_t w : consumers) {
+    const int kind = llmi_act_kind_for(w->type);
+    if (done[kind]) continue;
+    llmi_act_t a = get_act(set, kind, n);
+    if (!a) return LLMI_ERR_CUDA;
+    M_TRY(llmi_launch_act(x, uint32_t(n), kind, a->buf, m->stream));
+    m->launches_per_step++;
+    done[kind] = true;
+  }
+  return LLMI_OK;
+}
+
+int gemv(llmi_model_s* m, llmi_weight_t w, ActSet& set, float* out) {
+  llmi_act_t a = set.a[llmi_act_kind_for(w->type)];
+  M_TRY(llmi_launch_gemv(*w, *a, out, m->stream));
+  m->launches_per_step++;
+  return LLMI_OK;
+}
+
+// One token through all layers.  tok: device pointer to the token id.
+int run_step(llmi_model_s* m, const int32_t* tok, bool want_logits, bool want_argmax) {
+  cudaStream_t s = m->stream;
+  m->launches_per_step = 0;
+  const uint32_t E = m->E, F = m->F, HD = m->H * m->D;
+  M_TRY(llmi_launch_embed(make_embed_args(*m->embd), tok, std::sqrt(float(E)), m->h, s));  // model.cpp:710-712
+  m->launches_per_step++;
+  for (uint32_t l = 0; l < m->L; ++l) {
+    LayerW& w = m->layers[l];
+    const int kq = llmi_act_kind_for(w.q->type);
+    if (l == 0) {  // attn_norm of layer 0 (later layers: fused into the previous layer's last kernel)
+      NormArgs na;
+      na.h = m->h; na.w = w.attn_norm; na.n = E; na.eps = m->eps; na.xn_out = m->xn;
+      na.act_kind = kq; na.act_buf = get_act(m->act_E, kq, E)->buf;
+      M_TRY(llmi_launch_norm_act(na, s));
+      m->launches_per_step++;
+    }
+    M_RC(extra_acts(m, m->act_E, m->xn, E, kq, {w.k, w.v}));
+    M_RC(gemv(m, w.q, m->act_E, m->q));  // model.cpp:754
+    M_RC(gemv(m, w.k, m->act_E, m->k));  // model.cpp:784
+    M_RC(gemv(m, w.v, m->act_E, m->v));  // model.cpp:803
+    QkvArgs qa;
+    qa.q = m->q; qa.k = m->k; qa.v = m->v; qa.wq_norm = w.q_norm; qa.wk_norm = w.k_norm;
+    qa.H = m->H; qa.HK = m->HK; qa.D = m->D; qa.eps = m->eps;
+    qa.rope_base = w.swa ? 10000.0f : m->rope_base;  // model.cpp:732
+    qa.rope_scale = m->rope_scale; qa.attn_scale = m->attn_scale; qa.pos = m->d_pos; qa.q_out = m->q_rot;
+    qa.kcache = m->kcache + size_t(l) * m->t_max * m->HK * m->D;
+    qa.vcache = m->vcache + size_t(l) * m->t_max * m->HK * m->D;
+    M_TRY(llmi_launch_qkv_post(qa, s));
+    AttnArgs aa;
+    aa.q = m->q_rot; aa.kcache = qa.kcache; aa.vcache = qa.vcache; aa.H = m->H; aa.HK = m->HK; aa.D = m->D;
+    aa.t_max = m->t_max; aa.pos = m->d_pos; aa.softcap = m->attn_softcap; aa.out = m->attn;
+    M_TRY(llmi_launch_attention(aa, s));
+    const int ko = llmi_act_kind_for(w.o->type);
+    M_TRY(llmi_launch_act(m->attn, HD, ko, get_act(m->act_HD, ko, HD)->buf, s));
+    m->launches_per_step += 3;
+    M_RC(gemv(m, w.o, m->act_HD, m->attn_out));  // model.cpp:557
+    {
+      const int kg = llmi_act_kind_for(w.gate->type);
+      NormArgs na;  // post-attention norm + residual, then ffn_norm (model.cpp:843-858)
+      na.y = m->attn_out; na.w_post = w.post_attn_norm; na.h = m->h; na.w = w.ffn_norm; na.n = E; na.eps = m->eps;
+      na.xn_out = m->xn; na.act_kind = kg; na.act_buf = get_act(m->act_E, kg, E)->buf;
+      M_TRY(llmi_launch_norm_act(na, s));
+      m->launches_per_step++;
+      M_RC(extra_acts(m, m->act_E, m->xn, E, kg, {w.up}));
+    }
+    M_RC(gemv(m, w.gate, m->act_E, m->gate));  // model.cpp:875
+    M_RC(gemv(m, w.up, m->act_E, m->up));      // model.cpp:877
+    const int kd = llmi_act_kind_for(w.down->type);
+    M_TRY(llmi_launch_geglu_act(m->gate, m->up, F, kd, get_act(m->act_F, kd, F)->buf, nullptr, s));
+    m->launches_per_step++;
+    M_RC(gemv(m, w.down, m->act_F, m->ffn_out));  // model.cpp:909
+    {
+      NormArgs na;  // post-ffw norm + residual (model.cpp:915-924), then the next norm
+      na.y = m->ffn_out; na.w_post = w.post_ffw_norm; na.h = m->h; na.n = E; na.eps = m->eps; na.xn_out = m->xn;
+      if (l + 1 < m->L) {
+        const int kn = llmi_act_kind_for(m->layers[l + 1].q->type);
+        na.w = m->layers[l + 1].attn_norm; na.act_kind = kn; na.act_buf = get_act(m->act_E, kn, E)->buf;
+      } else {
+        na.pos_inc = m->d_pos;  // the token is done
+        if (want_logits) {      // final RMSNorm (model.cpp:983-986)
+          const int kl = llmi_act_kind_for(m->embd->type);
+          na.w = m->out_norm; na.act_kind = kl; na.act_buf = get_act(m->act_E, kl, E)->buf;
+        }
+      }
+      M_TRY(llmi_launch_norm_act(na, s));
+      m->launches_per_step++;
+    }
+  }
+  if (want_logits) {
+    M_RC(gemv(m, m->embd, m->act_E, m->logits));  // model.cpp:1000 / 1027
+    if (want_argmax) {
+      M_TRY(llmi_launch_argmax(m->logits, m->V, m->final_softcap, m->d_tok, m->d_gen, m->d_gen_count, s));
+      m->launches_per_step++;
+    } else if (m->final_softcap > 0.0f) {  // model.cpp:1036-1041
+      M_TRY(llmi_launch_softcap(m->logits, m->V, m->final_softcap, s));
+      m->launches_per_step++;
+    }
+  }
+  return LLMI_OK;
+}
+
+double kv_f(const llmi::GgufImage& g, const std::string& key, double dflt, bool* found = nullptr) {
+  const llmi::GgufValue* v = g.find(key);
+  if (found) *found = v != nullptr;
+  if (!v) return dflt;
+  return (v->type == 6 || v->type == 12) ? v->f : double(v->u);
+}
+
+int load_impl(llmi_model_s* m, const uint8_t* image, uint64_t size, uint32_t t_max) {
+  llmi::GgufImage g(image, size);
+  const llmi::GgufValue* arch = g.find("general.architecture");
+  if (!arch) return llmi_fail(LLMI_ERR_ARG, "Failed to find metadata key: general.architecture");
+  const std::string a = arch->s;
+  if (a != "gemma3")
+    return llmi_fail(LLMI_ERR_TYPE, "llmi_model_load: only the gemma3 architecture runs device-resident (got '" + a +
+                                        "'); use the ops.h drop-in with the reference model.cpp");
+  for (const char* k : {".block_count", ".embedding_length", ".feed_forward_length", ".attention.head_count",
+                        ".attention.head_count_kv", ".attention.layer_norm_rms_epsilon", ".rope.freq_base"})
+    if (!g.find(a + k)) return llmi_fail(LLMI_ERR_ARG, "Failed to find metadata key: " + a + k);  // model.cpp:63-67
+  m->L = uint32_t(kv_f(g, a + ".block_count", 0));
+  m->E = uint32_t(kv_f(g, a + ".embedding_length", 0));
+  m->F = uint32_t(kv_f(g, a + ".feed_forward_length", 0));
+  m->H = uint32_t(kv_f(g, a + ".attention.head_count", 0));
+  m->HK = uint32_t(kv_f(g, a + ".attention.head_count_kv", 0));
+  m->eps = double(float(kv_f(g, a + ".attention.layer_norm_rms_epsilon", 0)));  // stored f32, widened (model.cpp:84)
+  m->rope_base = float(kv_f(g, a + ".rope.freq_base", 0));
+  m->rope_scale = 1.0f;  // model.cpp:92
+  m->D = uint32_t(kv_f(g, a + ".attention.key_length", double(m->E / (m->H ? m->H : 1))));  // model.cpp:93-99
+  const uint32_t Dv = uint32_t(kv_f(g, a + ".attention.value_length", double(m->D)));
+  if (Dv != m->D || g.find(a + ".attention.key_length_swa") || g.find(a + ".attention.value_length_swa"))
+    return llmi_fail(LLMI_ERR_TYPE, "llmi_model_load: per-layer / asymmetric head sizes are not supported");
+  if (m->D % 64 || m->H == 0 || m->HK == 0 || m->H % m->HK)
+    return llmi_fail(LLMI_ERR_SIZE, "llmi_model_load: head_dim must be a multiple of 64 and n_head a multiple of n_head_kv");
+  if (kv_f(g, a + ".attention.max_alibi_bias", 0.0) > 0.0)
+    return llmi_fail(LLMI_ERR_TYPE, "llmi_model_load: ALiBi is not supported");
+  m->attn_scale = 1.0f / std::sqrt(float(m->D));  // model.cpp:117
+  m->attn_softcap = float(kv_f(g, a + ".attention.logit_softcapping", 0.0));
+  m->final_softcap = float(kv_f(g, a + ".attention.final_logit_softcapping", 0.0));  // key as in model.cpp:142
+  std::vector<bool> swa_meta;
+  if (const llmi::GgufValue* sw = g.find(a + ".attention.sliding_window_pattern"))
+    if (sw->type == 9)
+      for (const auto& e : sw->arr) swa_meta.push_back(e.u != 0);
+  m->t_max = t_max;
+  const uint32_t E = m->E, F = m->F, HD = m->H * m->D, KD = m->HK * m->D;
+
+  const llmi::GgufTensor* te = g.tensor("token_embd.weight");
+  if (!te || te->shape.size() != 2) return llmi_fail(LLMI_ERR_ARG, "llmi_model_load: missing tensor token_embd.weight");
+  if (te->type != LLMI_F16 && te->type != LLMI_Q6_K && te->type != LLMI_Q8_0 && te->type != LLMI_Q5_0)
+    return llmi_fail(LLMI_ERR_TYPE, "Error: embed_tokens: Unsupported token embedding tensor type: " +
+                                        std::to_string(te->type));  // model.cpp:324-330
+  m->V = uint32_t(te->shape[1]);
+  M_RC(upload_matrix(m, te, E, m->V, &m->embd, "token_embd.weight"));
+  M_RC(upload_f32(m, g.tensor("output_norm.weight"), E, &m->out_norm, "output_norm.weight"));
+  m->layers.resize(m->L);
+  for (uint32_t l = 0; l < m->L; ++l) {
+    LayerW& w = m->layers[l];
+    const std::string p = "blk." + std::to_string(l) + ".";
+    auto T = [&](const char* n) { return g.tensor(p + n + ".weight"); };
+    auto T2 = [&](const char* n, const char* alt) {
+      const llmi::GgufTensor* t = g.tensor(p + n + ".weight");
+      return t ? t : g.tensor(p + alt + ".weight");
+    };
+    w.swa = l < swa_meta.size() ? bool(swa_meta[l]) : (l % 6 < 5);  // model.cpp:723-729
+    M_RC(upload_f32(m, T("attn_norm"), E, &w.attn_norm, "attn_norm"));
+    M_RC(upload_f32(m, T("ffn_norm"), E, &w.ffn_norm, "ffn_norm"));
+    M_RC(upload_f32(m, T("attn_q_norm"), m->D, &w.q_norm, "attn_q_norm"));
+    M_RC(upload_f32(m, T("attn_k_norm"), m->D, &w.k_norm, "attn_k_norm"));
+    if (const llmi::GgufTensor* t = T2("post_attention_norm", "attn_post_norm"))
+      M_RC(upload_f32(m, t, E, &w.post_attn_norm, "post_attention_norm"));
+    if (const llmi::GgufTensor* t = T2("post_ffw_norm", "ffn_post_norm"))
+      M_RC(upload_f32(m, t, E, &w.post_ffw_norm, "post_ffw_norm"));
+    M_RC(upload_matrix(m, T("attn_q"), E, HD, &w.q, "attn_q"));
+    M_RC(upload_matrix(m, T("attn_k"), E, KD, &w.k, "attn_k"));
+    M_RC(upload_matrix(m, T("attn_v"), E, KD, &w.v, "attn_v"));
+    M_RC(upload_matrix(m, T("attn_output"), HD, E, &w.o, "attn_output"));
+    M_RC(upload_matrix(m, T("ffn_gate"), E, F, &w.gate, "ffn_gate"));
+    M_RC(upload_matrix(m, T("ffn_up"), E, F, &w.up, "ffn_up"));
+    M_RC(upload_matrix(m, T("ffn_down"), F, E, &w.down, "ffn_down"));
+  }
+  const size_t mx = std::max<size_t>({E, F, HD});
+  M_RC(dev_alloc(m, (void**)&m->h, E * 4));
+  M_RC(dev_alloc(m, (void**)&m->xn, mx * 4));
+  M_RC(dev_alloc(m, (void**)&m->q, HD * 4));
+  M_RC(dev_alloc(m, (void**)&m->k, KD * 4));
+  M_RC(dev_alloc(m, (void**)&m->v, KD * 4));
+  M_RC(dev_alloc(m, (void**)&m->q_rot, HD * 4));
+  M_RC(dev_alloc(m, (void**)&m->attn, HD * 4));
+  M_RC(dev_alloc(m, (void**)&m->attn_out, E * 4));
+  M_RC(dev_alloc(m, (void**)&m->gate, F * 4));
+  M_RC(dev_alloc(m, (void**)&m->up, F * 4));
+  M_RC(dev_alloc(m, (void**)&m->ffn_out, E * 4));
+  M_RC(dev_alloc(m, (void**)&m->logits, size_t(m->V) * 4));
+  const size_t kv_elems = size_t(m->L) * t_max * KD;
+  M_RC(dev_alloc(m, (void**)&m->kcache, kv_elems * 2));
+  M_RC(dev_alloc(m, (void**)&m->vcache, kv_elems * 2));
+  M_RC(dev_alloc(m, (void**)&m->d_tok, 16));
+  M_RC(dev_alloc(m, (void**)&m->d_pos, 16));
+  M_RC(dev_alloc(m, (void**)&m->d_gen_count, 16));
+  m->gen_cap = t_max + 1;
+  M_RC(dev_alloc(m, (void**)&m->d_gen, size_t(m->gen_cap) * 4));
+  m->toks_cap = t_max;
+  M_RC(dev_alloc(m, (void**)&m->d_toks, size_t(m->toks_cap) * 4));
+  M_TRY(cudaMemset(m->d_pos, 0, 16));
+  M_TRY(cudaMemset(m->d_gen_count, 0, 16));
+  M_TRY(cudaMallocHost((void**)&m->logits_pinned, size_t(m->V) * 4));
+  M_TRY(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+  M_TRY(cudaEventCreate(&m->ev0));
+  M_TRY(cudaEventCreate(&m->ev1));
+  M_TRY(llmi_attention_init(t_max, m->D));
+  return LLMI_OK;
+}
+
+int ensure_decode_graph(llmi_model_s* m) {
+  if (m->decode_graph) return LLMI_OK;
+  // warm-up run creates every lazily-allocated activation buffer outside capture
+  const int32_t zero[4] = {0, 0, 0, 0};
+  int32_t saved_pos = 0, saved_cnt = 0;
+  M_TRY(cudaMemcpy(&saved_pos, m->d_pos, 4, cudaMemcpyDeviceToHost));
+  M_TRY(cudaMemcpy(&saved_cnt, m->d_gen_count, 4, cudaMemcpyDeviceToHost));
+  M_TRY(cudaMemcpy(m->d_tok, zero, 4, cudaMemcpyHostToDevice));
+  M_RC(run_step(m, m->d_tok, true, true));
+  M_TRY(cudaStreamSynchronize(m->stream));
+  M_TRY(cudaMemcpy(m->d_pos, &saved_pos, 4, cudaMemcpyHostToDevice));
+  M_TRY(cudaMemcpy(m->d_gen_count, &saved_cnt, 4, cudaMemcpyHostToDevice));
+  cudaGraph_t graph = nullptr;
+  M_TRY(cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal));
+  const int rc = run_step(m, m->d_tok, true, true);
+  cudaError_t e = cudaStreamEndCapture(m->stream, &graph);
+  if (rc != LLMI_OK) {
+    if (graph) cudaGraphDestroy(graph);
+    return rc;
+  }
+  M_TRY(e);
+  e = cudaGraphInstantiate(&m->decode_graph, graph, 0);
+  cudaGraphDestroy(graph);
+  M_TRY(e);
+  return LLMI_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int llmi_model_load(const void* gguf_image, uint64_t size, uint32_t max_positions, llmi_model_t* out) {
+  if (!gguf_image || !out) return llmi_fail(LLMI_ERR_ARG, "llmi_model_load: null pointer");
+  if (llmi_sm_count() == 0) return llmi_fail(LLMI_ERR_STATE, "llmi_init() has not been called");
+  if (max_positions == 0) max_positions = 4096;
+  std::unique_ptr<llmi_model_s> m(new llmi_model_s());
+  int rc;
+  try {
+    rc = load_impl(m.get(), static_cast<const uint8_t*>(gguf_image), size, max_positions);
+  } catch (const std::exception& e) {
+    rc = llmi_fail(LLMI_ERR_ARG, e.what());
+  }
+  if (rc != LLMI_OK) {
+    llmi_model_free(m.release());
+    return rc;
+  }
+  *out = m.release();
+  return LLMI_OK;
+}
+
+int llmi_model_free(llmi_model_t m) {
+  if (!m) return LLMI_OK;
+  if (m->stream) cudaStreamSynchronize(m->stream);
+  if (m->decode_graph) cudaGraphExecDestroy(m->decode_graph);
+  for (auto& w : m->layers)
+    for (llmi_weight_t h : {w.q, w.k, w.v, w.o, w.gate, w.up, w.down}) llmi_weight_free(h);
+  llmi_weight_free(m->embd);
+  for (ActSet* s : {&m->act_E, &m->act_HD, &m->act_F})
+    for (llmi_act_t a : s->a) llmi_act_free(a);
+  for (void* p : m->owned) cudaFree(p);
+  if (m->logits_pinned) cudaFreeHost(m->logits_pinned);
+  if (m->ev0) cudaEventDestroy(m->ev0);
+  if (m->ev1) cudaEventDestroy(m->ev1);
+  if (m->stream) cudaStreamDestroy(m->stream);
+  delete m;
+  return LLMI_OK;
+}
+
+int llmi_model_info(llmi_model_t m, uint32_t* dims /*[8]: L,E,F,H,HK,D,V,t_max*/, uint64_t* weight_bytes) {
+  if (!m) return llmi_fail(LLMI_ERR_ARG, "llmi_model_info: null model");
+  if (dims) {
+    const uint32_t v[8] = {m->L, m->E, m->F, m->H, m->HK, m->D, m->V, m->t_max};
+    for (int i = 0; i < 8; ++i) dims[i] = v[i];
+  }
+  if (weight_bytes) *weight_bytes = m->weight_bytes;
+  return LLMI_OK;
+}
+
+// Model::forward(tokens, pos) (model.h:91, model.cpp:706-1048): host token ids
+// in, host logits of the LAST token out.  Synchronous.
+int llmi_model_forward(llmi_model_t m, const int32_t* tokens, int n_tokens, int pos, float* logits_host) {
+  if (!m || !tokens || !logits_host) return llmi_fail(LLMI_ERR_ARG, "llmi_model_forward: null pointer");
+  if (n_tokens <= 0) return llmi_fail(LLMI_ERR_ARG, "llmi_model_forward: no tokens");
+  if (pos < 0 || uint32_t(pos) + uint32_t(n_tokens) > m->t_max || uint32_t(n_tokens) > m->toks_cap)
+    return llmi_fail(LLMI_ERR_SIZE, "llmi_model_forward: position exceeds the KV cache capacity");
+  for (int i = 0; i < n_tokens; ++i)
+    if (tokens[i] < 0 || uint32_t(tokens[i]) >= m->V) return llmi_fail(LLMI_ERR_ARG, "llmi_model_forward: bad token id");
+  cudaStream_t s = m->stream;
+  M_TRY(cudaMemcpyAsync(m->d_toks, tokens, size_t(n_tokens) * 4, cudaMemcpyHostToDevice, s));
+  M_TRY(cudaMemcpyAsync(m->d_pos, &pos, 4, cudaMemcpyHostToDevice, s));
+  for (int t = 0; t < n_tokens; ++t) M_RC(run_step(m, m->d_toks + t, t == n_tokens - 1, false));
+  M_TRY(cudaMemcpyAsync(m->logits_pinned, m->logits, size_t(m->V) * 4, cudaMemcpyDeviceToHost, s));
+  M_TRY(cudaStreamSynchronize(s));
+  memcpy(logits_host, m->logits_pinned, size_t(m->V) * 4);
+  return LLMI_OK;
+}
+
+// Greedy decode entirely on the device: the argmax of step i is the token of
+// step i+1 (main.cpp:172-221 without the printing).  first_token is consumed at
+// position pos; out_tokens receives n_steps generated ids; ms_device (optional)
+// the CUDA-event time of the n_steps graph launches.
+int llmi_model_decode_greedy(llmi_model_t m, int32_t first_token, int pos, int n_steps, int32_t* out_tokens,
+                             float* ms_device) {
+  if (!m || !out_tokens) return llmi_fail(LLMI_ERR_ARG, "llmi_model_decode_greedy: null pointer");
+  if (n_steps <= 0 || pos < 0 || uint32_t(pos) + uint32_t(n_steps) > m->t_max || uint32_t(n_steps) > m->gen_cap)
+    return llmi_fail(LLMI_ERR_SIZE, "llmi_model_decode_greedy: position exceeds the KV cache capacity");
+  if (first_token < 0 || uint32_t(first_token) >= m->V)
+    return llmi_fail(LLMI_ERR_ARG, "llmi_model_decode_greedy: bad token id");
+  M_RC(ensure_decode_graph(m));
+  cudaStream_t s = m->stream;
+  const int32_t zero = 0;
+  M_TRY(cudaMemcpyAsync(m->d_tok, &first_token, 4, cudaMemcpyHostToDevice, s));
+  M_TRY(cudaMemcpyAsync(m->d_pos, &pos, 4, cudaMemcpyHostToDevice, s));
+  M_TRY(cudaMemcpyAsync(m->d_gen_count, &zero, 4, cudaMemcpyHostToDevice, s));
+  M_TRY(cudaEventRecord(m->ev0, s));
+  for (int i = 0; i < n_steps; ++i) M_TRY(cudaGraphLaunch(m->decode_graph, s));
+  M_TRY(cudaEventRecord(m->ev1, s));
+  M_TRY(cudaMemcpyAsync(out_tokens, m->d_gen, size_t(n_steps) * 4, cudaMemcpyDeviceToHost, s));
+  M_TRY(cudaStreamSynchronize(s));
+  if (ms_device) M_TRY(cudaEventElapsedTime(ms_device, m->ev0, m->ev1));
+  return LLMI_OK;
+}
+
+// Logits of the last executed step (device -> host), e.g. after decode_greedy.
+int llmi_model_last_logits(llmi_model_t m, float* logits_host) {
+  if (!m || !logits_host) return llmi_fail(LLMI_ERR_ARG, "llmi_model_last_logits: null pointer");
+  M_TRY(cudaMemcpyAsync(m->logits_pinned, m->logits, size_t(m->V) * 4, cudaMemcpyDeviceToHost, m->stream));
+  M_TRY(cudaStreamSynchronize(m->stream));
+  memcpy(logits_host, m->logits_pinned, size_t(m->V) * 4);
+  return LLMI_OK;
+}
+
+int llmi_model_launches_per_step(llmi_model_t m) { return m ? m->launches_per_step : 0; }
+
+}  // extern "C"

@@ -1,0 +1,57 @@
+"""Python mirror of the reference's Model (model.h:72-117) on the device-resident
+forward (include/llmi_cuda.h, llmi_model_*): ``Model(gguf_image)``,
+``forward(tokens, pos) -> logits`` of the last token, plus the greedy
+generation loop of main.cpp run entirely on the device."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib, ops
+
+
+class Model:
+    def __init__(self, gguf_image, max_positions: int = 4096, device: int = 0) -> None:
+        ops.init_ops(1, device)
+        L = _lib.load()
+        img = np.ascontiguousarray(np.frombuffer(gguf_image, np.uint8) if isinstance(gguf_image, (bytes, bytearray))
+                                   else gguf_image, np.uint8)
+        h = C.c_void_p()
+        _lib.check(L.llmi_model_load(img.ctypes.data, img.size, max_positions, C.byref(h)))
+        self.h = h
+        dims = (C.c_uint32 * 8)()
+        wb = C.c_uint64()
+        _lib.check(L.llmi_model_info(h, dims, C.byref(wb)))
+        (self.n_layer, self.n_embd, self.n_ff, self.n_head, self.n_head_kv, self.head_dim, self.vocab,
+         self.max_positions) = (int(v) for v in dims)
+        self.weight_bytes = int(wb.value)
+
+    def forward(self, tokens, pos: int) -> np.ndarray:
+        """Model::forward(tokens, pos): logits of the last token (model.cpp:706-1048)."""
+        tk = np.ascontiguousarray(tokens, np.int32)
+        logits = np.empty(self.vocab, np.float32)
+        _lib.check(_lib.load().llmi_model_forward(self.h, tk.ctypes.data, tk.size, pos, logits.ctypes.data))
+        return logits
+
+    def decode_greedy(self, first_token: int, pos: int, n_steps: int):
+        """(generated token ids, device milliseconds) — main.cpp:172-221 on the device."""
+        out = np.zeros(n_steps, np.int32)
+        ms = C.c_float()
+        _lib.check(_lib.load().llmi_model_decode_greedy(self.h, int(first_token), pos, n_steps, out.ctypes.data,
+                                                        C.byref(ms)))
+        return out, float(ms.value)
+
+    def last_logits(self) -> np.ndarray:
+        logits = np.empty(self.vocab, np.float32)
+        _lib.check(_lib.load().llmi_model_last_logits(self.h, logits.ctypes.data))
+        return logits
+
+    @property
+    def launches_per_step(self) -> int:
+        return int(_lib.load().llmi_model_launches_per_step(self.h))
+
+    def close(self) -> None:
+        if self.h:
+            _lib.load().llmi_model_free(self.h)
+            self.h = None

@@ -112,13 +112,15 @@ def quantize_q8_0(w: np.ndarray) -> np.ndarray:
     return out.ravel()
 
 
-def random_init_weight(ggml_type: int, n_rows: int, n_cols: int, seed: int) -> np.ndarray:
+def random_init_weight(ggml_type: int, n_rows: int, n_cols: int, seed: int, std: float | None = None) -> np.ndarray:
     """Random-init matrix N(0, 1/sqrt(K)) in the requested storage format.
     Q4_0/Q8_0/F16/BF16 are real quantizations of the float matrix; the k-quants
-    and Q5_0 use random blocks whose dequantized magnitude is of the same order."""
+    and Q5_0 use random blocks whose dequantized magnitude is of the same order.
+    ``std`` overrides the 1/sqrt(K) target."""
     rng = np.random.default_rng(seed)
+    target = np.float32(std if std is not None else 1.0 / np.sqrt(n_cols))
     if ggml_type in (Q4_0, Q8_0, F16, BF16, F32):
-        w = rng.standard_normal((n_rows, n_cols), dtype=np.float32) / np.float32(np.sqrt(n_cols))
+        w = rng.standard_normal((n_rows, n_cols), dtype=np.float32) * target
         if ggml_type == Q4_0:
             return quantize_q4_0(w)
         if ggml_type == Q8_0:
@@ -131,7 +133,7 @@ def random_init_weight(ggml_type: int, n_rows: int, n_cols: int, seed: int) -> n
         return ((bits + 0x7FFF + ((bits >> 16) & 1)) >> 16).astype(np.uint16).view(np.uint8).ravel()
     raw = random_blocks(ggml_type, n_rows, n_cols, seed).reshape(-1, _BLOCK[ggml_type][1]).copy()
     # rescale the f16 super-scales so dequantized weights are ~N(0, 1/sqrt(K))
-    s = np.float32(1.0 / np.sqrt(n_cols))
+    s = target
     nb = raw.shape[0]
     if ggml_type == Q4_K:   # w = d*sc*q - dmin*m, sc,m<=63, q<=15
         raw[:, 0:2] = _f16_bits(rng.uniform(0.5, 1.5, nb) * s / 120.0).view(np.uint8).reshape(nb, 2)
@@ -254,11 +256,13 @@ def q4_k_m_layer_types(n_layer: int) -> list[dict]:
 
 def build_gemma3_gguf(dims: GemmaDims, weight_type: int | str = Q4_0, embd_type: int = F16,
                       seed: int = 1234, n_layer: int | None = None, vocab: int | None = None,
-                      distinct_layers: bool = True) -> np.ndarray:
+                      distinct_layers: bool = True, embd_std: float = 1.0) -> np.ndarray:
     """Random-init Gemma-3 GGUF image.  ``weight_type`` is a ggml
     type id or "q4_k_m".  ``n_layer``/``vocab`` shrink the model for tests.
     With ``distinct_layers=False`` layers >= 1 reuse layer 0's quantized bytes
-    (generation time only; every layer still has its own tensor data)."""
+    (generation time only; every layer still has its own tensor data).
+    ``embd_std`` < 1 makes the (tied) embeddings small next to the layer outputs,
+    so greedy decoding depends on the whole network instead of echoing its input."""
     L = n_layer if n_layer is not None else dims.n_layer
     V = vocab if vocab is not None else dims.vocab
     E, F, H, HK, D = dims.n_embd, dims.n_ff, dims.n_head, dims.n_head_kv, dims.head_dim
@@ -281,11 +285,9 @@ def build_gemma3_gguf(dims: GemmaDims, weight_type: int | str = Q4_0, embd_type:
 
     rng = np.random.default_rng(seed)
     if embd_type == F16:
-        emb = _f16_bits(rng.standard_normal((V, E), dtype=np.float32)).view(np.uint8).ravel()
+        emb = _f16_bits(rng.standard_normal((V, E), dtype=np.float32) * np.float32(embd_std)).view(np.uint8).ravel()
     else:
-        emb = random_init_weight(embd_type, V, E, seed + 7)
-        if embd_type == Q8_0:  # embeddings ~N(0,1) rather than 1/sqrt(K)
-            emb = quantize_q8_0(rng.standard_normal((V, E), dtype=np.float32))
+        emb = random_init_weight(embd_type, V, E, seed + 7, std=embd_std)  # embeddings ~N(0, embd_std)
     g.add_tensor("token_embd.weight", embd_type, (E, V), emb)
     g.add_tensor("output_norm.weight", F32, (E,),
                  (1 + 0.1 * rng.standard_normal(E)).astype(np.float32))
