@@ -1,5 +1,6 @@
 // C ABI of libllmi_cuda.so (include/llmi_cuda.h): context, weights, activations,
 // the host-vector tier used by the ops.h drop-in, and small device helpers.
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -7,7 +8,12 @@
 #include <tuple>
 #include <vector>
 
+#include "launch.cuh"
 #include "llmi_internal.h"
+
+// Programmatic dependent launch for every kernel of the library (launch.cuh);
+// LLMI_NO_PDL=1 turns it off for A/B measurements.
+bool g_llmi_pdl = true;
 
 namespace {
 
@@ -104,6 +110,7 @@ int llmi_init(int device) {
                                         "' is not sm_100 (this library is built for B200 only)");
   }
   g.sm_count = prop.multiProcessorCount;
+  if (const char* e = getenv("LLMI_NO_PDL")) g_llmi_pdl = !(e[0] == '1');
   LLMI_CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
   LLMI_CUDA_TRY(llmi_gemv_init());
   g.device = device;

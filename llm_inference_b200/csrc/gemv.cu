@@ -24,6 +24,7 @@
 //     formulas (summation ORDER differs: that is the documented 1e-5 bound).
 #include <cuda_fp16.h>
 
+#include "launch.cuh"
 #include "llmi_internal.h"
 
 namespace {
@@ -91,6 +92,10 @@ struct GemvArgs {
   uint32_t n_local, n_slabs, nb, n_cols;
   uint32_t units;   // K-units per slab row (4 blocks of 32 / one super-block / 4 chunks of 8)
   uint32_t chunks;  // K-chunks (work items) per slab = ceil(units / Body::C)
+  // optional fused epilogue of the logits mat-vec: soft-cap + running argmax key
+  unsigned long long* argmax_key;
+  float softcap;
+  uint32_t row0;  // global index of this handle's first row
 };
 
 // ------------------------------------------------ integer block dot products
@@ -453,21 +458,47 @@ __device__ __forceinline__ float compute_item(const FragSet<B, N>& fs, const Gem
 // generation of loads in flight makes ptxas share them, which turns the
 // address setup of the next loads into waits on unrelated loads (measured 2x
 // slower, profiles/r01_notes.md).
+// Up to GEMV_MAX_BATCH matrices of the same format that consume the same
+// activation vector (q/k/v, gate/up) go out as ONE grid: the CTA index selects
+// the matrix.  The launch floor (~2.3 us) is paid once and the small matrices
+// fill the SMs together.
+constexpr int GEMV_MAX_BATCH = 3;
+struct GemvBatch {
+  GemvArgs a[GEMV_MAX_BATCH];
+  uint32_t cta_end[GEMV_MAX_BATCH];  // exclusive prefix of CTAs per matrix
+  uint32_t S[GEMV_MAX_BATCH];        // slabs per CTA
+  int n;
+};
+
+// Called by every thread after its first weight loads are in flight: wait for
+// the predecessor grid (PDL), let thread 0 start the bulk copy of the activation
+// vector it produced, wait for the bytes to land.
+__device__ __forceinline__ void stage_activation(const GemvArgs& a, uint8_t* sm_act, uint64_t* bar) {
+  pdl_wait();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, a.act_bytes);
+    bulk_g2s(sm_act, a.act, a.act_bytes, bar);
+  }
+  mbar_wait(bar, 0);
+}
+
 template <class B, int W>
-__global__ void __launch_bounds__(W * 32) gemv_slab_kernel(const GemvArgs a, const uint32_t S) {
+__global__ void __launch_bounds__(W * 32) gemv_slab_kernel(const GemvBatch batch) {
   extern __shared__ __align__(128) uint8_t sm_act[];  // [act_bytes][S * chunks * 8 floats]
   __shared__ __align__(8) uint64_t bar;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = lane & 7, sub = lane >> 3;
+  int mi = 0;
+  while (mi + 1 < batch.n && blockIdx.x >= batch.cta_end[mi]) ++mi;
+  const GemvArgs& a = batch.a[mi];
+  const uint32_t S = batch.S[mi];
+  const uint32_t cta = blockIdx.x - (mi ? batch.cta_end[mi - 1] : 0u);
+  pdl_trigger();
   if (threadIdx.x == 0) mbar_init(&bar, 1);
   __syncthreads();
-  if (threadIdx.x == 0) {
-    mbar_expect_tx(&bar, a.act_bytes);
-    bulk_g2s(sm_act, a.act, a.act_bytes, &bar);
-  }
   constexpr int N = B::C;
   const uint32_t J = a.chunks;
-  const uint32_t slab0 = blockIdx.x * S;
+  const uint32_t slab0 = cta * S;
   const uint32_t n_sl = min(S, a.n_slabs - slab0);
   const uint32_t n_items = n_sl * J;
   float* part = reinterpret_cast<float*>(sm_act + a.act_bytes);
@@ -476,23 +507,42 @@ __global__ void __launch_bounds__(W * 32) gemv_slab_kernel(const GemvArgs a, con
   for (uint32_t t = warp; t < n_items; t += W) {
     const uint32_t sl = t / J, j = t - sl * J;
     FragSet<B, N> f;
-    load_item<B, N>(f, a, slab0 + sl, j, r, sub);
+    load_item<B, N>(f, a, slab0 + sl, j, r, sub);  // weights: independent of the predecessor kernel
     if (!waited) {
-      mbar_wait(&bar, 0);
+      stage_activation(a, sm_act, &bar);
       waited = true;
     }
     const float v = compute_item<B, N>(f, a, sm_act, j, sub);
     if (lane < LLMI_SLAB) part[t * LLMI_SLAB + lane] = v;
   }
-  if (!waited) mbar_wait(&bar, 0);  // never exit with the bulk copy into our smem in flight
+  if (!waited) stage_activation(a, sm_act, &bar);  // never exit with the bulk copy into our smem in flight
   __syncthreads();
+  unsigned long long best = 0;
   for (uint32_t idx = threadIdx.x; idx < n_sl * LLMI_SLAB; idx += W * 32) {
     const uint32_t sl = idx / LLMI_SLAB, rr = idx % LLMI_SLAB;
     const float* p = part + (size_t)sl * J * LLMI_SLAB + rr;
     float sum = p[0];
     for (uint32_t j = 1; j < J; ++j) sum += p[j * LLMI_SLAB];  // canonical order
     const uint32_t row = (slab0 + sl) * LLMI_SLAB + rr;
-    if (row < a.n_local) a.out[row] = sum;
+    if (row < a.n_local) {
+      if (a.argmax_key) {  // logits: final soft-cap (model.cpp:1036-1041) + greedy argmax (main.cpp:193)
+        if (a.softcap > 0.0f) sum = __fmul_rn(a.softcap, tanhf(__fdiv_rn(sum, a.softcap)));
+        // order-preserving float -> uint; ties go to the smaller row (std::max_element)
+        uint32_t u = __float_as_uint(sum);
+        u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+        const unsigned long long k = (uint64_t(u) << 32) | uint32_t(0xffffffffu - (a.row0 + row));
+        best = k > best ? k : best;
+      }
+      a.out[row] = sum;
+    }
+  }
+  if (a.argmax_key) {  // one atomicMax per warp that saw rows (max is order-independent: deterministic)
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+      best = other > best ? other : best;
+    }
+    if (lane == 0 && best) atomicMax(a.argmax_key, best);
   }
 }
 
@@ -554,36 +604,58 @@ using BF16 = BodyHalf<true>;
 // g_slabs_per_cta in {0 (heuristic), 1..}.  Results never depend on it.
 int g_warps = 0, g_slabs_per_cta = 0;
 
-template <class B, int W>
-cudaError_t launch_w(const GemvArgs& a, uint32_t S, cudaStream_t s) {
-  const size_t smem = a.act_bytes + size_t(S) * a.chunks * LLMI_SLAB * 4;
-  const uint32_t grid = (a.n_slabs + S - 1) / S;
-  gemv_slab_kernel<B, W><<<grid, W * 32, smem, s>>>(a, S);
-  return cudaGetLastError();
-}
-
+// (W, S) for one matrix.  Heuristic from tools/gemv_sweep.py
+// (profiles/r01_sweep_v4.jsonl): one slab per CTA and the fewest warps per CTA
+// that still put ~24 warps on every SM (more, smaller CTAs beat fewer, larger
+// ones); never more warps than the slab has chunks; the k-quants (bigger
+// register footprint) stop at 8.  Huge-N / short-K matrices (logits) get 4
+// slabs per CTA so that every warp streams several items and the activation
+// staging is amortised.
 template <class B>
-cudaError_t launch_body(const GemvArgs& a, cudaStream_t s) {
+void pick_shape(const GemvArgs& a, uint64_t slabs_in_launch, int& W, uint32_t& S) {
   const uint64_t n_items = uint64_t(a.n_slabs) * a.chunks;
-  // Heuristic from tools/gemv_sweep.py (profiles/r01_sweep_v4.jsonl): one slab
-  // per CTA and the fewest warps per CTA that still put ~24 warps on every SM
-  // (more, smaller CTAs beat fewer, larger ones); never more warps than the
-  // slab has chunks; the k-quants (bigger register footprint) stop at 8.
-  // Huge-N / short-K matrices (logits) get 4 slabs per CTA so that every warp
-  // streams several items and the activation staging is amortised.
   const bool kq = B::C == 2;
-  int W = 4;
-  while (W < (kq ? 8 : 16) && uint64_t(a.n_slabs) * W < uint64_t(g_sm_count) * 24) W *= 2;
+  W = 4;
+  while (W < (kq ? 8 : 16) && slabs_in_launch * W < uint64_t(g_sm_count) * 24) W *= 2;
   if (a.chunks <= 4) W = 4;
   else if (a.chunks <= 8 && W > 8) W = 8;
-  uint32_t S = (a.chunks <= 10 && n_items >= uint64_t(g_sm_count) * 64 * 6) ? 4 : 1;
+  S = (a.chunks <= 10 && n_items >= uint64_t(g_sm_count) * 64 * 6) ? 4 : 1;
   if (g_warps) W = g_warps;
   if (g_slabs_per_cta) S = uint32_t(g_slabs_per_cta);
   while (S > 1 && a.act_bytes + size_t(S) * a.chunks * LLMI_SLAB * 4 > size_t(MAX_DYN_SMEM)) --S;
+}
+
+template <class B>
+cudaError_t launch_batch(const GemvArgs* args, int n, cudaStream_t s) {
+  GemvBatch b;
+  b.n = n;
+  uint64_t slabs = 0;
+  for (int i = 0; i < n; ++i) slabs += args[i].n_slabs;
+  int W = 4;
+  size_t smem = 0;
+  uint32_t ctas = 0;
+  for (int i = 0; i < n; ++i) {
+    int wi;
+    uint32_t si;
+    pick_shape<B>(args[i], slabs, wi, si);
+    if (wi > W) W = wi;
+    b.a[i] = args[i];
+    b.S[i] = si;
+    ctas += (args[i].n_slabs + si - 1) / si;
+    b.cta_end[i] = ctas;
+    const size_t need = args[i].act_bytes + size_t(si) * args[i].chunks * LLMI_SLAB * 4;
+    if (need > smem) smem = need;
+  }
+  for (int i = n; i < GEMV_MAX_BATCH; ++i) {
+    b.a[i] = args[0];
+    b.S[i] = 1;
+    b.cta_end[i] = ctas;
+  }
+  if (ctas == 0) return cudaSuccess;
   switch (W) {
-    case 4: return launch_w<B, 4>(a, S, s);
-    case 8: return launch_w<B, 8>(a, S, s);
-    default: return launch_w<B, 16>(a, S, s);
+    case 4: return llmi_launch(gemv_slab_kernel<B, 4>, dim3(ctas), dim3(128), smem, s, b);
+    case 8: return llmi_launch(gemv_slab_kernel<B, 8>, dim3(ctas), dim3(256), smem, s, b);
+    default: return llmi_launch(gemv_slab_kernel<B, 16>, dim3(ctas), dim3(512), smem, s, b);
   }
 }
 
@@ -657,23 +729,63 @@ static GemvArgs make_args(const llmi_weight_s& w, const llmi_act_s& a, float* ou
   g.n_cols = uint32_t(w.n_cols);
   g.units = units_of(w);
   g.chunks = llmi_gemv_chunks(w);
+  g.argmax_key = nullptr;
+  g.softcap = 0.0f;
+  g.row0 = uint32_t(w.row_begin);
   return g;
 }
 
-cudaError_t llmi_launch_gemv(const llmi_weight_s& w, const llmi_act_s& a, float* out, cudaStream_t s) {
-  if (w.n_slabs == 0) return cudaSuccess;
-  const GemvArgs g = make_args(w, a, out);
-  if (g.act_bytes > (uint32_t)MAX_DYN_SMEM) return cudaErrorInvalidValue;
-  switch (w.type) {
-    case LLMI_Q4_0: return launch_body<Q4_0>(g, s);
-    case LLMI_Q8_0: return launch_body<Q8_0>(g, s);
-    case LLMI_Q5_0: return launch_body<Q5_0>(g, s);
-    case LLMI_Q4_K: return launch_body<Q4_K>(g, s);
-    case LLMI_Q6_K: return launch_body<Q6_K>(g, s);
-    case LLMI_F16: return launch_body<F16>(g, s);
-    case LLMI_BF16: return launch_body<BF16>(g, s);
+// Set by llmi_launch_gemv_argmax for the duration of one launch.
+static unsigned long long* g_argmax_key = nullptr;
+static float g_argmax_softcap = 0.0f;
+
+// One launch for up to GEMV_MAX_BATCH matrices of the SAME format consuming the
+// same prepared activation (q/k/v, gate/up): the grid is the union of their CTAs.
+cudaError_t llmi_launch_gemv_batch(const llmi_weight_s* const* ws, float* const* outs, int n, const llmi_act_s& a,
+                                   cudaStream_t s) {
+  if (n < 1 || n > GEMV_MAX_BATCH) return cudaErrorInvalidValue;
+  GemvArgs args[GEMV_MAX_BATCH];
+  int m = 0;
+  for (int i = 0; i < n; ++i) {
+    if (ws[i]->type != ws[0]->type) return cudaErrorInvalidValue;
+    if (ws[i]->n_slabs == 0) continue;
+    args[m] = make_args(*ws[i], a, outs[i]);
+    args[m].argmax_key = g_argmax_key;
+    args[m].softcap = g_argmax_softcap;
+    if (args[m].act_bytes > (uint32_t)MAX_DYN_SMEM) return cudaErrorInvalidValue;
+    ++m;
+  }
+  if (m == 0) return cudaSuccess;
+  switch (ws[0]->type) {
+    case LLMI_Q4_0: return launch_batch<Q4_0>(args, m, s);
+    case LLMI_Q8_0: return launch_batch<Q8_0>(args, m, s);
+    case LLMI_Q5_0: return launch_batch<Q5_0>(args, m, s);
+    case LLMI_Q4_K: return launch_batch<Q4_K>(args, m, s);
+    case LLMI_Q6_K: return launch_batch<Q6_K>(args, m, s);
+    case LLMI_F16: return launch_batch<F16>(args, m, s);
+    case LLMI_BF16: return launch_batch<BF16>(args, m, s);
     default: return cudaErrorInvalidValue;
   }
+}
+
+cudaError_t llmi_launch_gemv(const llmi_weight_s& w, const llmi_act_s& a, float* out, cudaStream_t s) {
+  const llmi_weight_s* ws[1] = {&w};
+  float* outs[1] = {out};
+  return llmi_launch_gemv_batch(ws, outs, 1, a, s);
+}
+
+// Logits mat-vec with the fused soft-cap + argmax epilogue: every CTA folds its
+// rows into *key with one atomicMax per warp (key = ordered value bits << 32 |
+// ~row, so the maximum is the first index of the largest logit).  The caller
+// zeroes *key before and decodes it after (finish_token_kernel, glue.cu).
+cudaError_t llmi_launch_gemv_argmax(const llmi_weight_s& w, const llmi_act_s& a, float* out,
+                                    unsigned long long* key, float softcap, cudaStream_t s) {
+  g_argmax_key = key;
+  g_argmax_softcap = softcap;
+  const cudaError_t e = llmi_launch_gemv(w, a, out, s);
+  g_argmax_key = nullptr;
+  g_argmax_softcap = 0.0f;
+  return e;
 }
 
 cudaError_t llmi_launch_block_dots(const llmi_weight_s& w, const llmi_act_s& a, int32_t* dots_dev, cudaStream_t s) {

@@ -10,6 +10,7 @@
 #include <math.h>
 
 #include "glue.h"
+#include "launch.cuh"
 #include "quant_device.cuh"
 
 namespace {
@@ -65,6 +66,8 @@ __device__ float dequant_elem(const EmbedArgs& a, uint32_t row, uint32_t e) {
 
 // embed_tokens + scale_embeddings (model.cpp:240-344): h = dequant(row) * sqrt(float(E))
 __global__ void embed_kernel(EmbedArgs a, const int32_t* __restrict__ token, float scale, float* __restrict__ h) {
+  pdl_trigger();
+  pdl_wait();
   const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= a.n_cols) return;
   h[e] = dequant_elem(a, uint32_t(*token), e) * scale;
@@ -121,37 +124,54 @@ __device__ void emit_act(int kind, const float* xs, uint32_t n, uint8_t* buf) {
 // 915-924):   h += (rms_scale(y) * y) * w_post
 // Optional second stage (run_norm, model.cpp:346-386 + the quantizer of the
 // next mat-vec):   xn = (rms_scale(h) * h) * w ; act = quantize(xn)
-__global__ void norm_act_kernel(NormArgs a) {
+// Every global input (y, h, both norm weights) is loaded into registers up
+// front — one memory round trip instead of one per stage; the rest is two block
+// reductions and the quantizer.  NORM_PER elements per thread (n <= 6 * 1024).
+constexpr int NORM_PER = 6;
+__global__ void __launch_bounds__(1024) norm_act_kernel(NormArgs a) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float xs[];  // n floats
   __shared__ float red[32];
   const uint32_t n = a.n;
-  if (a.y) {
-    float ss = 0.0f;
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-      const float v = a.y[i];
-      ss += __fmul_rn(v, v);
-    }
-    const float sc = rms_scale(block_sum(ss, red), n, a.eps);
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-      // with a post-norm: h += (scale*y)*w (model.cpp:843-854); without: h += y
-      const float add = a.w_post ? __fmul_rn(__fmul_rn(sc, a.y[i]), a.w_post[i]) : a.y[i];
-      const float hv = __fadd_rn(a.h[i], add);
-      a.h[i] = hv;
-      xs[i] = hv;
-    }
-  } else {
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) xs[i] = a.h[i];
+  float yv[NORM_PER], hv[NORM_PER], wp[NORM_PER], wn[NORM_PER];
+#pragma unroll
+  for (int k = 0; k < NORM_PER; ++k) {
+    const uint32_t i = threadIdx.x + k * blockDim.x;
+    const bool ok = i < n;
+    hv[k] = ok ? a.h[i] : 0.0f;
+    yv[k] = (ok && a.y) ? a.y[i] : 0.0f;
+    wp[k] = (ok && a.y && a.w_post) ? a.w_post[i] : 0.0f;
+    wn[k] = (ok && a.w) ? a.w[i] : 0.0f;
   }
   if (a.pos_inc && threadIdx.x == 0) *a.pos_inc += 1;
+  if (a.y) {
+    float ss = 0.0f;
+#pragma unroll
+    for (int k = 0; k < NORM_PER; ++k) ss += __fmul_rn(yv[k], yv[k]);
+    const float sc = rms_scale(block_sum(ss, red), n, a.eps);
+#pragma unroll
+    for (int k = 0; k < NORM_PER; ++k) {
+      const uint32_t i = threadIdx.x + k * blockDim.x;
+      // with a post-norm: h += (scale*y)*w (model.cpp:843-854); without: h += y
+      const float add = a.w_post ? __fmul_rn(__fmul_rn(sc, yv[k]), wp[k]) : yv[k];
+      hv[k] = __fadd_rn(hv[k], add);
+      if (i < n) a.h[i] = hv[k];
+    }
+  }
   if (!a.w) return;
-  __syncthreads();
   float ss = 0.0f;
-  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) ss += __fmul_rn(xs[i], xs[i]);
+#pragma unroll
+  for (int k = 0; k < NORM_PER; ++k) ss += __fmul_rn(hv[k], hv[k]);
   const float sc = rms_scale(block_sum(ss, red), n, a.eps);
-  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-    const float v = __fmul_rn(__fmul_rn(sc, xs[i]), a.w[i]);
-    xs[i] = v;
-    if (a.xn_out) a.xn_out[i] = v;
+#pragma unroll
+  for (int k = 0; k < NORM_PER; ++k) {
+    const uint32_t i = threadIdx.x + k * blockDim.x;
+    if (i < n) {
+      const float v = __fmul_rn(__fmul_rn(sc, hv[k]), wn[k]);
+      xs[i] = v;
+      if (a.xn_out) a.xn_out[i] = v;
+    }
   }
   __syncthreads();
   emit_act(a.act_kind, xs, n, a.act_buf);
@@ -159,6 +179,8 @@ __global__ void norm_act_kernel(NormArgs a) {
 
 // Generic multi-CTA quantizer of a device vector (after attention).
 __global__ void act_kernel(const float* __restrict__ x, uint32_t n, int kind, uint8_t* buf) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
   if (kind == ACT_Q8_0) {
@@ -191,6 +213,8 @@ __global__ void act_kernel(const float* __restrict__ x, uint32_t n, int kind, ui
 // rope in the reference's object code: x0' = fma(v0, cos, -(v1*sin)),
 // x1' = fma(v0, sin, v1*cos); angle = (float(pos) * (1/powf(base, 2i/n_rot))) / scale.
 __global__ void qkv_post_kernel(QkvArgs a) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[32];
   const uint32_t D = a.D, half = D / 2, i = threadIdx.x;
   const uint32_t job = blockIdx.x;
@@ -240,6 +264,8 @@ __global__ void qkv_post_kernel(QkvArgs a) {
 //   phase 3  per element: v = f16(v*pse) on a new max; v = f16(fma(x, se, v))
 //   phase 4  out = f32(v) / s_acc                                     (:543-547)
 __global__ void attention_kernel(AttnArgs a) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) uint8_t smraw[];
   const uint32_t D = a.D, h = blockIdx.x, hkv = h / (a.H / a.HK);
   const int T = *a.pos + 1;
@@ -319,7 +345,30 @@ __global__ void attention_kernel(AttnArgs a) {
     qh[i] = __half2float(v);  // q no longer needed
   }
   __syncthreads();
-  for (uint32_t i = threadIdx.x; i < D; i += blockDim.x) a.out[h * D + i] = __fmul_rn(qh[i], s_inv);
+  for (uint32_t i = threadIdx.x; i < D; i += blockDim.x) {
+    const float o = __fmul_rn(qh[i], s_inv);
+    qh[i] = o;
+    a.out[h * D + i] = o;
+  }
+  // Fused quantizer of the attn_output mat-vec: this head's D outputs are whole
+  // Q8_0 blocks (and whole Q8_K super-blocks when D % 256 == 0).
+  if (a.act_kind == ACT_NONE) return;
+  __syncthreads();
+  const uint32_t n = a.H * D;
+  if (a.act_kind == ACT_Q8_0) {
+    for (uint32_t b = warp; b < D / 32; b += nw) warp_quantize_q8_0(qh[b * 32 + lane], h * (D / 32) + b, n, a.act_buf, lane);
+  } else if (a.act_kind == ACT_Q8_K) {
+    for (uint32_t sb = warp; sb < D / 256; sb += nw) {
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = qh[sb * 256 + lane * 8 + i];
+      warp_quantize_q8_k(v, h * (D / 256) + sb, n, a.act_buf, lane);
+    }
+  } else if (a.act_kind == ACT_F16) {
+    for (uint32_t i = threadIdx.x; i < D; i += blockDim.x) reinterpret_cast<uint16_t*>(a.act_buf)[h * D + i] = f2h(qh[i]);
+  } else if (a.act_kind == ACT_F32) {
+    for (uint32_t i = threadIdx.x; i < D; i += blockDim.x) reinterpret_cast<float*>(a.act_buf)[h * D + i] = qh[i];
+  }
 }
 
 // ------------------------------------------------------------------- GEGLU + act
@@ -335,6 +384,8 @@ __device__ __forceinline__ float geglu(float x, float up) {
 
 __global__ void geglu_act_kernel(const float* __restrict__ gate, const float* __restrict__ up, uint32_t n, int kind,
                                  uint8_t* buf, float* hidden_out) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
   if (kind == ACT_Q8_0) {
@@ -367,33 +418,16 @@ __global__ void geglu_act_kernel(const float* __restrict__ gate, const float* __
 
 // ------------------------------------------------------------ soft-cap + argmax
 // model.cpp:1036-1041 (final logit soft-cap) and main.cpp:193-194 (greedy:
-// std::max_element = FIRST index of the maximum).  Single CTA.
-__global__ void argmax_kernel(float* logits, uint32_t n, float softcap, int32_t* cur_tok, int32_t* gen,
-                              int32_t* gen_count) {
-  __shared__ unsigned long long best[32];
-  unsigned long long key = 0;
-  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-    float v = logits[i];
-    if (softcap > 0.0f) {
-      v = __fmul_rn(softcap, tanhf(__fdiv_rn(v, softcap)));
-      logits[i] = v;
-    }
-    // order-preserving float -> uint, ties broken towards the smaller index
-    uint32_t u = __float_as_uint(v);
-    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-    const unsigned long long k = (uint64_t(u) << 32) | uint32_t(0xffffffffu - i);
-    key = k > key ? k : key;
-  }
-#pragma unroll
-  for (int o = 16; o; o >>= 1) {
-    const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
-    key = other > key ? other : key;
-  }
-  if ((threadIdx.x & 31) == 0) best[threadIdx.x >> 5] = key;
-  __syncthreads();
+// std::max_element = FIRST index of the maximum) are fused into the epilogue of
+// the logits mat-vec (gemv.cu), which leaves a 64-bit key = ordered value bits
+// << 32 | ~index.  This kernel turns the key into the next token, appends it to
+// the generated list and re-arms the key.
+__global__ void finish_token_kernel(unsigned long long* key, int32_t* cur_tok, int32_t* gen, int32_t* gen_count) {
+  pdl_trigger();
+  pdl_wait();
   if (threadIdx.x == 0) {
-    for (uint32_t w = 1; w < (blockDim.x >> 5); ++w) key = best[w] > key ? best[w] : key;
-    const int32_t tok = int32_t(0xffffffffu - uint32_t(key));
+    const int32_t tok = int32_t(0xffffffffu - uint32_t(*key));
+    *key = 0ull;
     if (cur_tok) *cur_tok = tok;
     if (gen && gen_count) {
       gen[*gen_count] = tok;
@@ -403,6 +437,8 @@ __global__ void argmax_kernel(float* logits, uint32_t n, float softcap, int32_t*
 }
 
 __global__ void softcap_kernel(float* logits, uint32_t n, float softcap) {
+  pdl_trigger();
+  pdl_wait();
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) logits[i] = __fmul_rn(softcap, tanhf(__fdiv_rn(logits[i], softcap)));
 }
@@ -412,26 +448,22 @@ __global__ void softcap_kernel(float* logits, uint32_t n, float softcap) {
 // ------------------------------------------------------------------ launchers
 
 cudaError_t llmi_launch_embed(const EmbedArgs& a, const int32_t* token, float scale, float* h, cudaStream_t s) {
-  embed_kernel<<<(a.n_cols + 255) / 256, 256, 0, s>>>(a, token, scale, h);
-  return cudaGetLastError();
+  return llmi_launch(embed_kernel, dim3((a.n_cols + 255) / 256), dim3(256), 0, s, a, token, scale, h);
 }
 
 cudaError_t llmi_launch_norm_act(const NormArgs& a, cudaStream_t s) {
   const int threads = a.n >= 2048 ? 1024 : 512;
-  norm_act_kernel<<<1, threads, a.n * sizeof(float), s>>>(a);
-  return cudaGetLastError();
+  return llmi_launch(norm_act_kernel, dim3(1), dim3(threads), a.n * sizeof(float), s, a);
 }
 
 cudaError_t llmi_launch_act(const float* x, uint32_t n, int kind, uint8_t* buf, cudaStream_t s) {
   const uint32_t warps = kind == ACT_Q8_0 ? n / 32 : (kind == ACT_Q8_K ? n / 256 : (n + 31) / 32);
   const uint32_t blocks = (warps + 7) / 8 ? (warps + 7) / 8 : 1;
-  act_kernel<<<blocks, 256, 0, s>>>(x, n, kind, buf);
-  return cudaGetLastError();
+  return llmi_launch(act_kernel, dim3(blocks), dim3(256), 0, s, x, n, kind, buf);
 }
 
 cudaError_t llmi_launch_qkv_post(const QkvArgs& a, cudaStream_t s) {
-  qkv_post_kernel<<<a.H + 2 * a.HK, a.D / 2, 0, s>>>(a);
-  return cudaGetLastError();
+  return llmi_launch(qkv_post_kernel, dim3(a.H + 2 * a.HK), dim3(a.D / 2), 0, s, a);
 }
 
 size_t llmi_attention_smem(uint32_t t_max, uint32_t D) { return size_t(t_max) * (8 + 4 + 4 + 1) + size_t(D) * 4 + 16; }
@@ -442,25 +474,21 @@ cudaError_t llmi_attention_init(uint32_t t_max, uint32_t D) {
 }
 
 cudaError_t llmi_launch_attention(const AttnArgs& a, cudaStream_t s) {
-  attention_kernel<<<a.H, 256, llmi_attention_smem(a.t_max, a.D), s>>>(a);
-  return cudaGetLastError();
+  return llmi_launch(attention_kernel, dim3(a.H), dim3(256), llmi_attention_smem(a.t_max, a.D), s, a);
 }
 
 cudaError_t llmi_launch_geglu_act(const float* gate, const float* up, uint32_t n, int kind, uint8_t* buf,
                                   float* hidden_out, cudaStream_t s) {
   const uint32_t warps = kind == ACT_Q8_0 ? n / 32 : (kind == ACT_Q8_K ? n / 256 : (n + 31) / 32);
   const uint32_t blocks = (warps + 3) / 4 ? (warps + 3) / 4 : 1;
-  geglu_act_kernel<<<blocks, 128, 0, s>>>(gate, up, n, kind, buf, hidden_out);
-  return cudaGetLastError();
+  return llmi_launch(geglu_act_kernel, dim3(blocks), dim3(128), 0, s, gate, up, n, kind, buf, hidden_out);
 }
 
-cudaError_t llmi_launch_argmax(float* logits, uint32_t n, float softcap, int32_t* cur_tok, int32_t* gen,
-                               int32_t* gen_count, cudaStream_t s) {
-  argmax_kernel<<<1, 1024, 0, s>>>(logits, n, softcap, cur_tok, gen, gen_count);
-  return cudaGetLastError();
+cudaError_t llmi_launch_finish_token(unsigned long long* key, int32_t* cur_tok, int32_t* gen, int32_t* gen_count,
+                                     cudaStream_t s) {
+  return llmi_launch(finish_token_kernel, dim3(1), dim3(32), 0, s, key, cur_tok, gen, gen_count);
 }
 
 cudaError_t llmi_launch_softcap(float* logits, uint32_t n, float softcap, cudaStream_t s) {
-  softcap_kernel<<<(n + 255) / 256, 256, 0, s>>>(logits, n, softcap);
-  return cudaGetLastError();
+  return llmi_launch(softcap_kernel, dim3((n + 255) / 256), dim3(256), 0, s, logits, n, softcap);
 }

@@ -47,6 +47,8 @@ struct AttnArgs {
   const int32_t* pos;
   float softcap;
   float* out;  // [H*D]
+  int act_kind = ACT_NONE;  // fused quantizer for the attn_output mat-vec (ACT_NONE: caller quantizes)
+  uint8_t* act_buf = nullptr;
 };
 
 cudaError_t llmi_launch_embed(const EmbedArgs& a, const int32_t* token, float scale, float* h, cudaStream_t s);
@@ -58,6 +60,6 @@ cudaError_t llmi_attention_init(uint32_t t_max, uint32_t D);
 cudaError_t llmi_launch_attention(const AttnArgs& a, cudaStream_t s);
 cudaError_t llmi_launch_geglu_act(const float* gate, const float* up, uint32_t n, int kind, uint8_t* buf,
                                   float* hidden_out, cudaStream_t s);
-cudaError_t llmi_launch_argmax(float* logits, uint32_t n, float softcap, int32_t* cur_tok, int32_t* gen,
-                               int32_t* gen_count, cudaStream_t s);
+cudaError_t llmi_launch_finish_token(unsigned long long* key, int32_t* cur_tok, int32_t* gen, int32_t* gen_count,
+                                     cudaStream_t s);
 cudaError_t llmi_launch_softcap(float* logits, uint32_t n, float softcap, cudaStream_t s);

@@ -1,0 +1,39 @@
+// Kernel launch helper with programmatic dependent launch (PDL).
+//
+// A decode token is a chain of ~200 short dependent kernels; each costs ~2.3 us
+// of launch + ramp when serialized.  With the programmatic-stream-serialization
+// attribute the next kernel of the stream (or of the captured graph) is allowed
+// to start while its predecessor is still running.  Every kernel therefore
+//   * calls pdl_trigger() first thing (lets its own successor be scheduled), and
+//   * calls pdl_wait() before it reads or writes anything a predecessor touches
+//     (griddepcontrol.wait: returns when all prerequisite grids have completed
+//     and their memory is visible).
+// What runs before pdl_wait() overlaps the predecessor's tail: barrier setup
+// and — in the mat-vec kernel — the first weight loads, which depend on nothing.
+// Without the attribute (LLMI_NO_PDL=1, or a launch after a memcpy) both
+// instructions are no-ops.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <utility>
+
+extern bool g_llmi_pdl;
+
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+cudaError_t llmi_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_llmi_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}

@@ -87,7 +87,11 @@ cudaError_t llmi_launch_export_q8_k(const uint8_t* buf, uint64_t n, uint8_t* out
 // gemv.cu
 cudaError_t llmi_gemv_init();  // opt-in dynamic shared memory for every instantiation
 cudaError_t llmi_launch_gemv(const llmi_weight_s& w, const llmi_act_s& a, float* out, cudaStream_t s);
+cudaError_t llmi_launch_gemv_batch(const llmi_weight_s* const* ws, float* const* outs, int n, const llmi_act_s& a,
+                                   cudaStream_t s);  // same format, same activation, n <= 3
 uint32_t llmi_gemv_chunks(const llmi_weight_s& w);
 void llmi_gemv_set_shape(int warps, int slabs_per_cta);  // 0 = heuristic  // K-chunks (work items) per slab
+cudaError_t llmi_launch_gemv_argmax(const llmi_weight_s& w, const llmi_act_s& a, float* out, unsigned long long* key,
+                                    float softcap, cudaStream_t s);
 cudaError_t llmi_launch_block_dots(const llmi_weight_s& w, const llmi_act_s& a, int32_t* dots_dev, cudaStream_t s);
 int llmi_act_kind_for(uint32_t ggml_type);

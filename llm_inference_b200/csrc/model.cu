@@ -47,6 +47,7 @@ struct llmi_model_s {
   ActSet act_E, act_HD, act_F;
   __half *kcache = nullptr, *vcache = nullptr;
   int32_t *d_tok = nullptr, *d_pos = nullptr, *d_gen = nullptr, *d_gen_count = nullptr, *d_toks = nullptr;
+  unsigned long long* d_key = nullptr;  // running argmax key of the logits mat-vec epilogue
   uint32_t toks_cap = 0, gen_cap = 0;
   cudaStream_t stream = nullptr;
   cudaGraphExec_t decode_graph = nullptr;
@@ -129,6 +130,32 @@ int gemv(llmi_model_s* m, llmi_weight_t w, ActSet& set, float* out) {
   return LLMI_OK;
 }
 
+// Mat-vecs that consume the same activation vector: matrices of the same format
+// go out as one grid (llmi_launch_gemv_batch), in the order given.
+int gemv_group(llmi_model_s* m, std::initializer_list<llmi_weight_t> ws, std::initializer_list<float*> outs,
+               ActSet& set) {
+  std::vector<llmi_weight_t> w(ws);
+  std::vector<float*> o(outs);
+  std::vector<bool> done(w.size(), false);
+  for (size_t i = 0; i < w.size(); ++i) {
+    if (done[i]) continue;
+    const llmi_weight_s* bw[3];
+    float* bo[3];
+    int n = 0;
+    for (size_t j = i; j < w.size() && n < 3; ++j)
+      if (!done[j] && w[j]->type == w[i]->type) {
+        bw[n] = w[j];
+        bo[n] = o[j];
+        done[j] = true;
+        ++n;
+      }
+    llmi_act_t a = set.a[llmi_act_kind_for(w[i]->type)];
+    M_TRY(llmi_launch_gemv_batch(bw, bo, n, *a, m->stream));
+    m->launches_per_step++;
+  }
+  return LLMI_OK;
+}
+
 // One token through all layers.  tok: device pointer to the token id.
 int run_step(llmi_model_s* m, const int32_t* tok, bool want_logits, bool want_argmax) {
   cudaStream_t s = m->stream;
@@ -147,9 +174,8 @@ int run_step(llmi_model_s* m, const int32_t* tok, bool want_logits, bool want_ar
       m->launches_per_step++;
     }
     M_RC(extra_acts(m, m->act_E, m->xn, E, kq, {w.k, w.v}));
-    M_RC(gemv(m, w.q, m->act_E, m->q));  // model.cpp:754
-    M_RC(gemv(m, w.k, m->act_E, m->k));  // model.cpp:784
-    M_RC(gemv(m, w.v, m->act_E, m->v));  // model.cpp:803
+    // model.cpp:754 (Q), 784 (K), 803 (V): one grid per format group
+    M_RC(gemv_group(m, {w.q, w.k, w.v}, {m->q, m->k, m->v}, m->act_E));
     QkvArgs qa;
     qa.q = m->q; qa.k = m->k; qa.v = m->v; qa.wq_norm = w.q_norm; qa.wk_norm = w.k_norm;
     qa.H = m->H; qa.HK = m->HK; qa.D = m->D; qa.eps = m->eps;
@@ -161,10 +187,19 @@ int run_step(llmi_model_s* m, const int32_t* tok, bool want_logits, bool want_ar
     AttnArgs aa;
     aa.q = m->q_rot; aa.kcache = qa.kcache; aa.vcache = qa.vcache; aa.H = m->H; aa.HK = m->HK; aa.D = m->D;
     aa.t_max = m->t_max; aa.pos = m->d_pos; aa.softcap = m->attn_softcap; aa.out = m->attn;
-    M_TRY(llmi_launch_attention(aa, s));
     const int ko = llmi_act_kind_for(w.o->type);
-    M_TRY(llmi_launch_act(m->attn, HD, ko, get_act(m->act_HD, ko, HD)->buf, s));
-    m->launches_per_step += 3;
+    uint8_t* ko_buf = get_act(m->act_HD, ko, HD)->buf;
+    const bool fuse_act = ko != ACT_Q8_K || m->D % 256 == 0;  // a head holds whole quantization blocks
+    if (fuse_act) {
+      aa.act_kind = ko;
+      aa.act_buf = ko_buf;
+    }
+    M_TRY(llmi_launch_attention(aa, s));
+    m->launches_per_step += 2;
+    if (!fuse_act) {
+      M_TRY(llmi_launch_act(m->attn, HD, ko, ko_buf, s));
+      m->launches_per_step++;
+    }
     M_RC(gemv(m, w.o, m->act_HD, m->attn_out));  // model.cpp:557
     {
       const int kg = llmi_act_kind_for(w.gate->type);
@@ -175,8 +210,7 @@ int run_step(llmi_model_s* m, const int32_t* tok, bool want_logits, bool want_ar
       m->launches_per_step++;
       M_RC(extra_acts(m, m->act_E, m->xn, E, kg, {w.up}));
     }
-    M_RC(gemv(m, w.gate, m->act_E, m->gate));  // model.cpp:875
-    M_RC(gemv(m, w.up, m->act_E, m->up));      // model.cpp:877
+    M_RC(gemv_group(m, {w.gate, w.up}, {m->gate, m->up}, m->act_E));  // model.cpp:875, 877
     const int kd = llmi_act_kind_for(w.down->type);
     M_TRY(llmi_launch_geglu_act(m->gate, m->up, F, kd, get_act(m->act_F, kd, F)->buf, nullptr, s));
     m->launches_per_step++;
@@ -199,13 +233,17 @@ int run_step(llmi_model_s* m, const int32_t* tok, bool want_logits, bool want_ar
     }
   }
   if (want_logits) {
-    M_RC(gemv(m, m->embd, m->act_E, m->logits));  // model.cpp:1000 / 1027
-    if (want_argmax) {
-      M_TRY(llmi_launch_argmax(m->logits, m->V, m->final_softcap, m->d_tok, m->d_gen, m->d_gen_count, s));
-      m->launches_per_step++;
-    } else if (m->final_softcap > 0.0f) {  // model.cpp:1036-1041
-      M_TRY(llmi_launch_softcap(m->logits, m->V, m->final_softcap, s));
-      m->launches_per_step++;
+    if (want_argmax) {  // logits mat-vec (model.cpp:1000 / 1027) with the soft-cap + argmax epilogue
+      llmi_act_t la = m->act_E.a[llmi_act_kind_for(m->embd->type)];
+      M_TRY(llmi_launch_gemv_argmax(*m->embd, *la, m->logits, m->d_key, m->final_softcap, s));
+      M_TRY(llmi_launch_finish_token(m->d_key, m->d_tok, m->d_gen, m->d_gen_count, s));
+      m->launches_per_step += 2;
+    } else {
+      M_RC(gemv(m, m->embd, m->act_E, m->logits));
+      if (m->final_softcap > 0.0f) {  // model.cpp:1036-1041
+        M_TRY(llmi_launch_softcap(m->logits, m->V, m->final_softcap, s));
+        m->launches_per_step++;
+      }
     }
   }
   return LLMI_OK;
@@ -308,6 +346,8 @@ int load_impl(llmi_model_s* m, const uint8_t* image, uint64_t size, uint32_t t_m
   M_RC(dev_alloc(m, (void**)&m->d_tok, 16));
   M_RC(dev_alloc(m, (void**)&m->d_pos, 16));
   M_RC(dev_alloc(m, (void**)&m->d_gen_count, 16));
+  M_RC(dev_alloc(m, (void**)&m->d_key, 16));
+  M_TRY(cudaMemset(m->d_key, 0, 16));
   m->gen_cap = t_max + 1;
   M_RC(dev_alloc(m, (void**)&m->d_gen, size_t(m->gen_cap) * 4));
   m->toks_cap = t_max;

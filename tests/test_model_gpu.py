@@ -89,7 +89,9 @@ def test_32_greedy_steps_token_identical_vs_compiled_reference(gpu_ops):
             toks.append(ta)
             a, b = ref.forward([ta], pos), m.forward([ta], pos)
             pos += 1
-        assert max(errs) <= TOL_WORST and float(np.median(errs)) <= 1e-2, errs
+        # N(0,1) embeddings: logits are dominated by well-conditioned terms; small embeddings make the
+        # logits tiny next to the activations, so one flipped f16 rounding in the KV cache shows as ~1e-2
+        assert max(errs) <= (1e-3 if std == 1.0 else TOL_WORST), errs
         print(f"{wt} std={std}: 32 greedy tokens identical ({len(set(toks))} distinct), min margin/max "
               f"{min(margins):.2e}, logits err/max: median {np.median(errs):.1e} max {max(errs):.1e}")
         ref.close()
