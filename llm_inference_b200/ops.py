@@ -69,7 +69,7 @@ class DeviceWeight:
     """One uploaded + repacked matrix (llmi_weight_upload)."""
 
     def __init__(self, blocks: np.ndarray, ggml_type: int, n_cols: int, n_rows: int,
-                 row_begin: int = 0, row_end: int | None = None, handle=None) -> None:
+                 row_begin: int = 0, row_end: int | None = None, handle=None, blocks_are_shard: bool = False) -> None:
         L = _need_init()
         self.type, self.n_cols, self.n_rows = ggml_type, n_cols, n_rows
         self.row_begin = row_begin
@@ -77,8 +77,11 @@ class DeviceWeight:
         self.owned = handle is None
         if handle is None:
             raw = np.ascontiguousarray(blocks).view(np.uint8).ravel()
+            base = _ptr(raw)
+            if blocks_are_shard:  # `blocks` holds only rows [row_begin,row_end): address of the virtual row 0
+                base -= self.row_begin * row_bytes(ggml_type, n_cols)
             h = C.c_void_p()
-            _lib.check(L.llmi_weight_upload(_ptr(raw), ggml_type, n_cols, n_rows, self.row_begin, self.row_end,
+            _lib.check(L.llmi_weight_upload(base, ggml_type, n_cols, n_rows, self.row_begin, self.row_end,
                                             C.byref(h)))
             handle = h
         self.h = handle
@@ -118,6 +121,19 @@ class DeviceVector:
         if self.p:
             _lib.load().llmi_dev_free(self.p)
             self.p = None
+
+
+class TorchVector:
+    """fp32 torch CUDA tensor viewed as a device vector (for torch.distributed collectives)."""
+
+    def __init__(self, tensor) -> None:
+        assert tensor.is_cuda and tensor.dtype.is_floating_point and tensor.element_size() == 4
+        self.t = tensor
+        self.n = tensor.numel()
+        self.p = C.c_void_p(tensor.data_ptr())
+
+    def close(self) -> None:
+        self.t = None
 
 
 class Activation:
@@ -277,6 +293,6 @@ def registry_clear() -> None:
 __all__ = [
     "init_ops", "mat_vec_mul", "mat_vec_mul_q4_0", "mat_vec_mul_q4_k", "mat_vec_mul_q6_k", "mat_vec_mul_q8_0",
     "mat_vec_mul_q5_0", "mat_vec_mul_bf16", "mat_vec_mul_fp16", "quantize_row_q8_0", "quantize_row_q8_k",
-    "DeviceWeight", "DeviceVector", "Activation", "gemv", "mat_vec_mul_dev", "block_dots", "set_gemv_shape",
+    "DeviceWeight", "DeviceVector", "TorchVector", "Activation", "gemv", "mat_vec_mul_dev", "block_dots", "set_gemv_shape",
     "device_sync", "registry_clear", "row_bytes",
 ]

@@ -1,0 +1,78 @@
+"""N > 1 host logic on CPU: world_size-2 (and 3) gloo process groups.  Each rank
+computes its row shard with the port oracle standing in for the device kernel
+(rows are independent, ops.cpp:439-448), the slices are all-gathered in place,
+and the result must equal the unsharded mat-vec bit for bit."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from llm_inference_b200 import shard, synth
+
+
+def test_row_ranges_are_slab_aligned_and_cover():
+    for n, w in [(6912, 2), (21504, 8), (1152, 8), (1030, 4), (5, 2), (262208, 8), (8, 4)]:
+        rs = shard.row_ranges(n, w)
+        assert len(rs) == w and rs[0][0] == 0 and rs[-1][1] == n
+        for (b0, e0), (b1, e1) in zip(rs, rs[1:]):
+            assert e0 == b1 and b0 <= e0
+        assert all(b % 8 == 0 for b, e in rs if e > b)
+        sizes = [e - b for b, e in rs]
+        assert max(sizes) - min(sizes) < 16 or n < 8 * w  # one slab of imbalance + a ragged last slab
+    assert shard.equal_ranges(21504, 8) == [(i * 2688, (i + 1) * 2688) for i in range(8)]
+    assert shard.equal_ranges(1030, 4) is None
+
+
+def _free_port() -> int:
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank: int, world: int, port: int, cases, out_q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle.binding import Port
+    P = Port()
+    ok = True
+    for t, k, n in cases:
+        w = synth.random_blocks(t, n, k, seed=t + k + n)          # every rank holds the same file
+        x = np.random.default_rng(k).standard_normal(k).astype(np.float32)
+        ranges = shard.row_ranges(n, world)
+        rb = synth.row_bytes(t, k)
+        b, e = ranges[rank]
+        full = torch.full((n,), float("nan"))
+        if e > b:
+            mine = P.mat_vec_mul(t, shard.shard_blocks(w, rb, (b, e)), x, e - b, k)
+            full[b:e] = torch.from_numpy(mine)
+        shard.allgather_rows(full, ranges, rank)
+        ref = P.mat_vec_mul(t, w, x, n, k)
+        ok &= bool(np.array_equal(full.numpy().view(np.uint32), ref.view(np.uint32)))
+    res = torch.tensor([1 if ok else 0])
+    dist.all_reduce(res, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        out_q.put(int(res.item()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_matvec_allgather_equals_unsharded(world):
+    cases = [(synth.Q4_0, 1152, 6912), (synth.Q4_0, 1152, 1030), (synth.Q8_0, 256, 40), (synth.Q4_K, 512, 136),
+             (synth.F16, 128, 520), (synth.Q6_K, 256, 5)]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, cases, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=180)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) == 1
