@@ -120,6 +120,11 @@ int llmi_act_export_q8_k(llmi_act_t a, void* host_blocks);
  * _q5_0/_bf16/_fp16 (ops.cpp:188-931).  out_dev is the FULL n_rows-long fp32
  * vector; only this handle's row range is written. */
 int llmi_gemv(llmi_weight_t w, llmi_act_t a, float* out_dev, llmi_stream_t s);
+/* Up to 3 matrices of the SAME format that consume the same prepared activation
+ * (q/k/v, gate/up: model.cpp:754,784,803 and 875,877) as ONE grid: the launch
+ * floor is paid once and the small matrices fill the SMs together.  Results are
+ * identical to n separate llmi_gemv calls. */
+int llmi_gemv_batch(const llmi_weight_t* ws, float* const* outs_dev, int n, llmi_act_t a, llmi_stream_t s);
 /* llmi_act_prepare + llmi_gemv: exactly one reference mat_vec_mul call. */
 int llmi_mat_vec_mul_dev(llmi_weight_t w, const float* x_dev, llmi_act_t a,
                          float* out_dev, llmi_stream_t s);

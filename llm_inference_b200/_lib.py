@@ -40,6 +40,7 @@ SIGNATURES = {
     "llmi_act_export_q8_0": (_int, [_vp, _vp]),
     "llmi_act_export_q8_k": (_int, [_vp, _vp]),
     "llmi_gemv": (_int, [_vp, _vp, _vp, _vp]),
+    "llmi_gemv_batch": (_int, [_vp, _vp, _int, _vp, _vp]),
     "llmi_mat_vec_mul_dev": (_int, [_vp, _vp, _vp, _vp, _vp]),
     "llmi_set_gemv_shape": (_int, [_int, _int]),
     "llmi_debug_block_dots": (_int, [_vp, _vp, _vp]),

@@ -346,6 +346,22 @@ int llmi_gemv(llmi_weight_t w, llmi_act_t a, float* out, llmi_stream_t s) {
   return LLMI_OK;
 }
 
+int llmi_gemv_batch(const llmi_weight_t* ws, float* const* outs, int n, llmi_act_t a, llmi_stream_t s) {
+  LLMI_NEED_INIT();
+  if (!ws || !outs || !a || n < 1 || n > 3) return llmi_fail(LLMI_ERR_ARG, "llmi_gemv_batch: need 1..3 matrices");
+  const llmi_weight_s* w[3];
+  for (int i = 0; i < n; ++i) {
+    if (!ws[i] || !outs[i]) return llmi_fail(LLMI_ERR_ARG, "llmi_gemv_batch: null pointer");
+    if (ws[i]->type != ws[0]->type) return llmi_fail(LLMI_ERR_TYPE, "llmi_gemv_batch: matrices must share one format");
+    if (a->kind != llmi_act_kind_for(ws[i]->type))
+      return llmi_fail(LLMI_ERR_STATE, "llmi_gemv_batch: activation was not prepared for this weight format");
+    if (a->n != ws[i]->n_cols) return llmi_fail(LLMI_ERR_SIZE, "mat_vec_mul: input vector size mismatch");
+    w[i] = ws[i];
+  }
+  LLMI_CUDA_TRY(llmi_launch_gemv_batch(w, outs, n, *a, (cudaStream_t)s));
+  return LLMI_OK;
+}
+
 int llmi_mat_vec_mul_dev(llmi_weight_t w, const float* x, llmi_act_t a, float* out, llmi_stream_t s) {
   if (int rc = llmi_act_prepare(w, x, a, s)) return rc;
   return llmi_gemv(w, a, out, s);

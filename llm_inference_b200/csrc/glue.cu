@@ -130,19 +130,24 @@ __device__ void emit_act(int kind, const float* xs, uint32_t n, uint8_t* buf) {
 constexpr int NORM_PER = 6;
 __global__ void __launch_bounds__(1024) norm_act_kernel(NormArgs a) {
   pdl_trigger();
-  pdl_wait();
   extern __shared__ float xs[];  // n floats
   __shared__ float red[32];
   const uint32_t n = a.n;
   float yv[NORM_PER], hv[NORM_PER], wp[NORM_PER], wn[NORM_PER];
+#pragma unroll
+  for (int k = 0; k < NORM_PER; ++k) {  // norm weights are static: fetch them under the predecessor's tail
+    const uint32_t i = threadIdx.x + k * blockDim.x;
+    const bool ok = i < n;
+    wp[k] = (ok && a.y && a.w_post) ? a.w_post[i] : 0.0f;
+    wn[k] = (ok && a.w) ? a.w[i] : 0.0f;
+  }
+  pdl_wait();
 #pragma unroll
   for (int k = 0; k < NORM_PER; ++k) {
     const uint32_t i = threadIdx.x + k * blockDim.x;
     const bool ok = i < n;
     hv[k] = ok ? a.h[i] : 0.0f;
     yv[k] = (ok && a.y) ? a.y[i] : 0.0f;
-    wp[k] = (ok && a.y && a.w_post) ? a.w_post[i] : 0.0f;
-    wn[k] = (ok && a.w) ? a.w[i] : 0.0f;
   }
   if (a.pos_inc && threadIdx.x == 0) *a.pos_inc += 1;
   if (a.y) {
@@ -203,94 +208,169 @@ __global__ void act_kernel(const float* __restrict__ x, uint32_t n, int kind, ui
   }
 }
 
-// ------------------------------------------------------- q/k norm, RoPE, KV append
-// One CTA per head job: blockIdx.x in [0,H) = q head, [H,H+HK) = k head,
-// [H+HK, H+2HK) = v head.  blockDim = D/2; thread i owns elements i and i+D/2
-// (the NEOX rotation pair, ops.cpp:85-92).
-//   q: run_norm (model.cpp:388-423) -> rope (ops.cpp:67-95) -> scale (ops.cpp:97-105)
-//   k: run_norm -> rope -> f32_to_f16 -> cache[pos] (model.cpp:442-474)
-//   v: f32_to_f16 -> cache[pos]
+// ------------------------------------- q/k norm, RoPE, KV append, attention
+// One CTA per query head for one token (grid = H, 1024 threads; D <= 512):
+//   q: run_norm (model.cpp:388-423) -> rope (ops.cpp:67-95) -> scale (:97-105)
+//   k: run_norm -> rope -> f32_to_f16 ; v: f32_to_f16 ; append to the cache at
+//      `pos` (model.cpp:442-474).  Every query head of a GQA group derives the
+//      new K/V row itself (cheap) and keeps it in shared memory, the first head
+//      of the group also writes it to the cache — so no CTA depends on another.
+//   Model::run_attn (model.cpp:476-550): the reference walks the cached
+//   positions sequentially with an fp16 value accumulator that is rounded at
+//   every step (vec_mad_f16 / vec_scale_f16, ops.cpp:1084-1099).  That
+//   recurrence is kept element by element (phase 3); everything that does not
+//   depend on it is computed in parallel first:
+//     phase 1  score[t] = sum_i double(f16(k[t][i]) * f16(q[i]))      (:504-509)
+//     phase 2  running max M (prefix max of float(score)), and per position
+//              new_max / score_exp / prev_score_exp exactly as :520-533
+//     phase 3  per element: v = f16(v*pse) on a new max; v = f16(fma(x, se, v))
+//     phase 4  out = f32(v) / s_acc (:543-547) + the quantizer of attn_output
 // rope in the reference's object code: x0' = fma(v0, cos, -(v1*sin)),
 // x1' = fma(v0, sin, v1*cos); angle = (float(pos) * (1/powf(base, 2i/n_rot))) / scale.
-__global__ void qkv_post_kernel(QkvArgs a) {
-  pdl_trigger();
-  pdl_wait();
-  __shared__ float red[32];
-  const uint32_t D = a.D, half = D / 2, i = threadIdx.x;
-  const uint32_t job = blockIdx.x;
-  const int pos = *a.pos;
-  if (job >= a.H + a.HK) {  // v head
-    const uint32_t hv = job - a.H - a.HK;
-    const float* v = a.v + hv * D;
-    __half* dst = a.vcache + (size_t(pos) * a.HK + hv) * D;
-    dst[i] = __float2half_rn(v[i]);
-    dst[i + half] = __float2half_rn(v[i + half]);
-    return;
-  }
-  const bool is_q = job < a.H;
-  const uint32_t hd = is_q ? job : job - a.H;
-  const float* src = (is_q ? a.q : a.k) + hd * D;
-  const float* w = is_q ? a.wq_norm : a.wk_norm;
-  float v0 = src[i], v1 = src[i + half];
-  const float ss = block_sum(__fadd_rn(__fmul_rn(v0, v0), __fmul_rn(v1, v1)), red);
-  const float sc = rms_scale(ss, D, a.eps);
-  v0 = __fmul_rn(__fmul_rn(sc, v0), w[i]);
-  v1 = __fmul_rn(__fmul_rn(sc, v1), w[i + half]);
-  const float freq = __fdiv_rn(1.0f, powf(a.rope_base, __fdiv_rn(float(2 * i), float(int(D)))));
-  const float ang = __fdiv_rn(__fmul_rn(float(pos), freq), a.rope_scale);
+constexpr int ATT_TILE = 128;
+
+// RoPE factors for every (position, pair): ops.cpp:80-83 —
+//   freq = 1.0f / powf(base, float(2i)/n_rot); val = float(pos) * freq / scale; cosf(val), sinf(val)
+__global__ void rope_table_kernel(float2* table, uint32_t t_max, uint32_t D, float base, float scale) {
+  const uint32_t half = D / 2;
+  const uint64_t idx = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+  if (idx >= uint64_t(t_max) * half) return;
+  const uint32_t pos = uint32_t(idx / half), i = uint32_t(idx % half);
+  const float freq = __fdiv_rn(1.0f, powf(base, __fdiv_rn(float(2 * i), float(int(D)))));
+  const float ang = __fdiv_rn(__fmul_rn(float(pos), freq), scale);
   float sn, cs;
   sincosf(ang, &sn, &cs);
-  float x0 = __fmaf_rn(v0, cs, -__fmul_rn(v1, sn));
-  float x1 = __fmaf_rn(v0, sn, __fmul_rn(v1, cs));
-  if (is_q) {
-    a.q_out[hd * D + i] = __fmul_rn(x0, a.attn_scale);
-    a.q_out[hd * D + i + half] = __fmul_rn(x1, a.attn_scale);
-  } else {
-    __half* dst = a.kcache + (size_t(pos) * a.HK + hd) * D;
-    dst[i] = __float2half_rn(x0);
-    dst[i + half] = __float2half_rn(x1);
-  }
+  table[idx] = make_float2(cs, sn);
 }
 
-// ---------------------------------------------------------------- attention
-// Model::run_attn (model.cpp:476-550) for one query token, one CTA per head.
-// The reference walks the cached positions sequentially with an fp16 value
-// accumulator that is rounded at every step (vec_mad_f16 / vec_scale_f16,
-// ops.cpp:1084-1099) — that recurrence is kept element by element (phase 3);
-// everything that does not depend on it is computed in parallel first:
-//   phase 1  score[t] = sum_i double(f16(k[t][i]) * f16(q[i]))      (:504-509)
-//   phase 2  running max M (prefix max of float(score)), and per position
-//            new_max / score_exp / prev_score_exp exactly as :520-533
-//   phase 3  per element: v = f16(v*pse) on a new max; v = f16(fma(x, se, v))
-//   phase 4  out = f32(v) / s_acc                                     (:543-547)
-__global__ void attention_kernel(AttnArgs a) {
-  pdl_trigger();
-  pdl_wait();
-  extern __shared__ __align__(16) uint8_t smraw[];
-  const uint32_t D = a.D, h = blockIdx.x, hkv = h / (a.H / a.HK);
-  const int T = *a.pos + 1;
-  double* sc = reinterpret_cast<double*>(smraw);                 // [Tmax]
-  float* se = reinterpret_cast<float*>(sc + a.t_max);            // [Tmax]
-  float* pse = se + a.t_max;                                     // [Tmax] (first holds M_prev)
-  float* qh = pse + a.t_max;                                     // [D]
-  uint8_t* nm = reinterpret_cast<uint8_t*>(qh + D);              // [Tmax]
-  __shared__ float s_inv;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (uint32_t i = threadIdx.x; i < D; i += blockDim.x) qh[i] = __half2float(__float2half_rn(a.q[h * D + i]));
+// Stages rows [t0, t0+nt) of one KV head into shared memory with 16-byte
+// cp.async copies (all threads, all copies in flight at once); the row of the
+// current token comes from shared memory (it may not be in the cache yet).
+__device__ __forceinline__ void load_kv_tile(__half* tile, const __half* cache, int t0, int nt, int pos,
+                                             const __half* newrow, uint32_t HK, uint32_t hkv, uint32_t D) {
+  const uint32_t cpr = D / 8;  // 16-byte chunks per row
+  for (uint32_t c = threadIdx.x; c < uint32_t(nt) * cpr; c += blockDim.x) {
+    const uint32_t r = c / cpr, k = c - r * cpr;
+    const int t = t0 + int(r);
+    __half* dst = tile + size_t(r) * D + k * 8;
+    if (t == pos) {
+      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(newrow + k * 8);
+    } else {
+      const __half* src = cache + (size_t(t) * HK + hkv) * D + k * 8;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src)
+                   : "memory");
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
-  // phase 1
-  for (int t = warp; t < T; t += nw) {
-    const __half* kp = a.kcache + (size_t(t) * a.HK + hkv) * D;
-    double s = 0.0;
-    for (uint32_t i = lane; i < D; i += 32) s += double(__fmul_rn(__half2float(kp[i]), qh[i]));
-#pragma unroll
-    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) {
-      if (a.softcap > 0.0f) s = double(__fmul_rn(a.softcap, tanhf(float(s / double(a.softcap)))));
-      sc[t] = s;
+}
+
+__global__ void __launch_bounds__(1024) attention_kernel(AttnArgs a) {
+  pdl_trigger();
+  extern __shared__ __align__(16) uint8_t smraw[];
+  __shared__ float red[32];
+  __shared__ float s_inv;
+  const uint32_t D = a.D, half = D / 2, h = blockIdx.x, group = a.H / a.HK, hkv = h / group;
+  double* sc = reinterpret_cast<double*>(smraw);                 // [t_max]
+  float* se = reinterpret_cast<float*>(sc + a.t_max);            // [t_max]
+  float* pse = se + a.t_max;                                     // [t_max] (first holds M_prev)
+  float* qh = pse + a.t_max;                                     // [D]
+  __half* knew = reinterpret_cast<__half*>(qh + D);              // [D] this token's K row (f16)
+  __half* vnew = knew + D;                                       // [D] this token's V row (f16)
+  __half* tile = vnew + D;                                       // [ATT_TILE][D] staged K or V rows
+  uint8_t* nm = reinterpret_cast<uint8_t*>(tile + size_t(ATT_TILE) * D);  // [t_max]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const uint32_t i = threadIdx.x;
+  const bool pair = i < half;  // thread i owns the rotation pair (i, i + D/2)
+  // static inputs, fetched under the predecessor's tail
+  float wq0 = 0.0f, wq1 = 0.0f, wk0 = 0.0f, wk1 = 0.0f;
+  if (pair) {
+    wq0 = a.wq_norm[i];
+    wq1 = a.wq_norm[i + half];
+    wk0 = a.wk_norm[i];
+    wk1 = a.wk_norm[i + half];
+  }
+  pdl_wait();
+  const int pos = *a.pos, T = pos + 1;
+  float q0 = 0.0f, q1 = 0.0f, k0 = 0.0f, k1 = 0.0f, v0 = 0.0f, v1 = 0.0f;
+  if (pair) {
+    q0 = a.q[h * D + i];
+    q1 = a.q[h * D + i + half];
+    k0 = a.k[hkv * D + i];
+    k1 = a.k[hkv * D + i + half];
+    v0 = a.v[hkv * D + i];
+    v1 = a.v[hkv * D + i + half];
+  }
+  const float ssq = block_sum(__fadd_rn(__fmul_rn(q0, q0), __fmul_rn(q1, q1)), red);
+  const float ssk = block_sum(__fadd_rn(__fmul_rn(k0, k0), __fmul_rn(k1, k1)), red);
+  if (pair) {
+    const float scq = rms_scale(ssq, D, a.eps), sck = rms_scale(ssk, D, a.eps);
+    q0 = __fmul_rn(__fmul_rn(scq, q0), wq0);
+    q1 = __fmul_rn(__fmul_rn(scq, q1), wq1);
+    k0 = __fmul_rn(__fmul_rn(sck, k0), wk0);
+    k1 = __fmul_rn(__fmul_rn(sck, k1), wk1);
+    // (cos, sin) of (float(pos) * (1/powf(base, 2i/D))) / scale: tabulated per position at
+    // load time by rope_table_kernel with exactly this arithmetic
+    const float2 csn = a.rope_table[size_t(pos) * half + i];
+    const float cs = csn.x, sn = csn.y;
+    const float qa = __fmul_rn(__fmaf_rn(q0, cs, -__fmul_rn(q1, sn)), a.attn_scale);
+    const float qb = __fmul_rn(__fmaf_rn(q0, sn, __fmul_rn(q1, cs)), a.attn_scale);
+    qh[i] = __half2float(__float2half_rn(qa));  // Q is rounded to f16 for the scores (model.cpp:506)
+    qh[i + half] = __half2float(__float2half_rn(qb));
+    const __half ka = __float2half_rn(__fmaf_rn(k0, cs, -__fmul_rn(k1, sn)));
+    const __half kb = __float2half_rn(__fmaf_rn(k0, sn, __fmul_rn(k1, cs)));
+    const __half va = __float2half_rn(v0), vb = __float2half_rn(v1);
+    knew[i] = ka;
+    knew[i + half] = kb;
+    vnew[i] = va;
+    vnew[i + half] = vb;
+    if (h % group == 0) {  // one writer per KV head
+      __half* kd = a.kcache + (size_t(pos) * a.HK + hkv) * D;
+      __half* vd = a.vcache + (size_t(pos) * a.HK + hkv) * D;
+      kd[i] = ka;
+      kd[i + half] = kb;
+      vd[i] = va;
+      vd[i + half] = vb;
     }
   }
   __syncthreads();
+  // phase 1: scores.  K rows of this KV head are staged in shared-memory tiles
+  // of ATT_TILE positions with cp.async (one memory round trip per tile instead
+  // of one per position: only H CTAs run, so latency, not bandwidth, is the cost).
+  // One warp per position, each lane a contiguous run of D/32 elements.
+  {
+    const uint32_t vec = D / 32;  // 2, 4, 8 or 16 halves per lane
+    for (int t0 = 0; t0 < T; t0 += ATT_TILE) {
+      const int nt = min(ATT_TILE, T - t0);
+      load_kv_tile(tile, a.kcache, t0, nt, pos, knew, a.HK, hkv, D);
+      for (int r = warp; r < nt; r += nw) {
+        const __half* kp = tile + size_t(r) * D + lane * vec;
+        __half kv[16];
+        if (vec == 8) {
+          *reinterpret_cast<uint4*>(kv) = *reinterpret_cast<const uint4*>(kp);
+        } else if (vec == 4) {
+          *reinterpret_cast<uint2*>(kv) = *reinterpret_cast<const uint2*>(kp);
+        } else if (vec == 16) {
+          *reinterpret_cast<uint4*>(kv) = *reinterpret_cast<const uint4*>(kp);
+          *reinterpret_cast<uint4*>(kv + 8) = *reinterpret_cast<const uint4*>(kp + 8);
+        } else {
+          *reinterpret_cast<uint32_t*>(kv) = *reinterpret_cast<const uint32_t*>(kp);
+        }
+        double s = 0.0;
+#pragma unroll
+        for (uint32_t j = 0; j < 16; ++j)
+          if (j < vec) s += double(__fmul_rn(__half2float(kv[j]), qh[lane * vec + j]));
+#pragma unroll
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) {
+          if (a.softcap > 0.0f) s = double(__fmul_rn(a.softcap, tanhf(float(s / double(a.softcap)))));
+          sc[t0 + r] = s;
+        }
+      }
+      __syncthreads();  // tile is reused
+    }
+  }
   // phase 2a: exclusive prefix max of float(score) (warp 0)
   if (warp == 0) {
     const int chunk = (T + 31) / 32, t0 = lane * chunk, t1 = min(T, t0 + chunk);
@@ -326,29 +406,76 @@ __global__ void attention_kernel(AttnArgs a) {
     }
   }
   __syncthreads();
-  // phase 2c: s_acc = s_acc*pse + se, sequential, no FMA (model.cpp:540)
+  // phase 2c: s_acc = s_acc*pse + se, sequential, no FMA (model.cpp:540).  The
+  // operands are fetched 8 positions at a time so that only the mul+add chain is
+  // serial, not the shared-memory latency.
   if (threadIdx.x == blockDim.x - 1) {
     float s = 0.0f;
-    for (int t = 0; t < T; ++t) s = __fadd_rn(__fmul_rn(s, pse[t]), se[t]);
+    int t = 0;
+    for (; t + 8 <= T; t += 8) {
+      float p8[8], e8[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        p8[j] = pse[t + j];
+        e8[j] = se[t + j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s = __fadd_rn(__fmul_rn(s, p8[j]), e8[j]);
+    }
+    for (; t < T; ++t) s = __fadd_rn(__fmul_rn(s, pse[t]), se[t]);
     s_inv = s == 0.0f ? 0.0f : __fdiv_rn(1.0f, s);
   }
-  // phase 3
-  for (uint32_t i = threadIdx.x; i < D; i += blockDim.x) {
-    const __half* vp = a.vcache + size_t(hkv) * D + i;
-    const size_t stride = size_t(a.HK) * D;
-    __half v = __float2half_rn(0.0f);
-    for (int t = 0; t < T; ++t) {
-      const float x = __half2float(vp[t * stride]);
-      if (nm[t]) v = __float2half_rn(__fmul_rn(__half2float(v), pse[t]));
-      v = __float2half_rn(__fmaf_rn(x, se[t], __half2float(v)));
+  // phase 3: the fp16 accumulator recurrence, one thread per element, V rows
+  // staged tile by tile like K.  The per-position factors of 8 positions are
+  // fetched together, then folded in order.
+  {
+    __half vacc[2] = {__float2half_rn(0.0f), __float2half_rn(0.0f)};  // elements tid, tid + blockDim (D <= 512)
+    for (int t0 = 0; t0 < T; t0 += ATT_TILE) {
+      const int nt = min(ATT_TILE, T - t0);
+      load_kv_tile(tile, a.vcache, t0, nt, pos, vnew, a.HK, hkv, D);
+#pragma unroll
+      for (int w = 0; w < 2; ++w) {
+        const uint32_t e = threadIdx.x + w * blockDim.x;
+        if (e < D) {
+          __half v = vacc[w];
+          int r = 0;
+          for (; r + 8 <= nt; r += 8) {
+            __half x8[8];
+            float e8[8], p8[8];
+            uint8_t n8[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              x8[j] = tile[size_t(r + j) * D + e];
+              e8[j] = se[t0 + r + j];
+              p8[j] = pse[t0 + r + j];
+              n8[j] = nm[t0 + r + j];
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (n8[j]) v = __float2half_rn(__fmul_rn(__half2float(v), p8[j]));
+              v = __float2half_rn(__fmaf_rn(__half2float(x8[j]), e8[j], __half2float(v)));
+            }
+          }
+          for (; r < nt; ++r) {
+            if (nm[t0 + r]) v = __float2half_rn(__fmul_rn(__half2float(v), pse[t0 + r]));
+            v = __float2half_rn(__fmaf_rn(__half2float(tile[size_t(r) * D + e]), se[t0 + r], __half2float(v)));
+          }
+          vacc[w] = v;
+        }
+      }
+      __syncthreads();  // tile is reused
     }
-    qh[i] = __half2float(v);  // q no longer needed
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+      const uint32_t e = threadIdx.x + w * blockDim.x;
+      if (e < D) qh[e] = __half2float(vacc[w]);  // q no longer needed
+    }
   }
   __syncthreads();
-  for (uint32_t i = threadIdx.x; i < D; i += blockDim.x) {
-    const float o = __fmul_rn(qh[i], s_inv);
-    qh[i] = o;
-    a.out[h * D + i] = o;
+  for (uint32_t e = threadIdx.x; e < D; e += blockDim.x) {
+    const float o = __fmul_rn(qh[e], s_inv);
+    qh[e] = o;
+    a.out[h * D + e] = o;
   }
   // Fused quantizer of the attn_output mat-vec: this head's D outputs are whole
   // Q8_0 blocks (and whole Q8_K super-blocks when D % 256 == 0).
@@ -361,13 +488,13 @@ __global__ void attention_kernel(AttnArgs a) {
     for (uint32_t sb = warp; sb < D / 256; sb += nw) {
       float v[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = qh[sb * 256 + lane * 8 + i];
+      for (int j = 0; j < 8; ++j) v[j] = qh[sb * 256 + lane * 8 + j];
       warp_quantize_q8_k(v, h * (D / 256) + sb, n, a.act_buf, lane);
     }
   } else if (a.act_kind == ACT_F16) {
-    for (uint32_t i = threadIdx.x; i < D; i += blockDim.x) reinterpret_cast<uint16_t*>(a.act_buf)[h * D + i] = f2h(qh[i]);
+    for (uint32_t e = threadIdx.x; e < D; e += blockDim.x) reinterpret_cast<uint16_t*>(a.act_buf)[h * D + e] = f2h(qh[e]);
   } else if (a.act_kind == ACT_F32) {
-    for (uint32_t i = threadIdx.x; i < D; i += blockDim.x) reinterpret_cast<float*>(a.act_buf)[h * D + i] = qh[i];
+    for (uint32_t e = threadIdx.x; e < D; e += blockDim.x) reinterpret_cast<float*>(a.act_buf)[h * D + e] = qh[e];
   }
 }
 
@@ -462,11 +589,15 @@ cudaError_t llmi_launch_act(const float* x, uint32_t n, int kind, uint8_t* buf, 
   return llmi_launch(act_kernel, dim3(blocks), dim3(256), 0, s, x, n, kind, buf);
 }
 
-cudaError_t llmi_launch_qkv_post(const QkvArgs& a, cudaStream_t s) {
-  return llmi_launch(qkv_post_kernel, dim3(a.H + 2 * a.HK), dim3(a.D / 2), 0, s, a);
+cudaError_t llmi_launch_rope_table(float2* table, uint32_t t_max, uint32_t D, float base, float scale, cudaStream_t s) {
+  const uint64_t n = uint64_t(t_max) * (D / 2);
+  rope_table_kernel<<<unsigned((n + 255) / 256), 256, 0, s>>>(table, t_max, D, base, scale);
+  return cudaGetLastError();
 }
 
-size_t llmi_attention_smem(uint32_t t_max, uint32_t D) { return size_t(t_max) * (8 + 4 + 4 + 1) + size_t(D) * 4 + 16; }
+size_t llmi_attention_smem(uint32_t t_max, uint32_t D) {
+  return size_t(t_max) * (8 + 4 + 4 + 1) + size_t(D) * 8 + size_t(128) * D * 2 + 16;  // + one K/V tile
+}
 
 cudaError_t llmi_attention_init(uint32_t t_max, uint32_t D) {
   return cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -474,7 +605,7 @@ cudaError_t llmi_attention_init(uint32_t t_max, uint32_t D) {
 }
 
 cudaError_t llmi_launch_attention(const AttnArgs& a, cudaStream_t s) {
-  return llmi_launch(attention_kernel, dim3(a.H), dim3(256), llmi_attention_smem(a.t_max, a.D), s, a);
+  return llmi_launch(attention_kernel, dim3(a.H), dim3(1024), llmi_attention_smem(a.t_max, a.D), s, a);
 }
 
 cudaError_t llmi_launch_geglu_act(const float* gate, const float* up, uint32_t n, int kind, uint8_t* buf,

@@ -29,21 +29,14 @@ struct NormArgs {
   int32_t* pos_inc = nullptr;     // optional device counter to bump (end of a token step)
 };
 
-struct QkvArgs {
-  const float *q, *k, *v;
-  const float *wq_norm, *wk_norm;
-  uint32_t H, HK, D;
-  double eps;
-  float rope_base, rope_scale, attn_scale;
-  const int32_t* pos;
-  float* q_out;
-  __half *kcache, *vcache;  // this layer's [t_max][HK][D]
-};
-
 struct AttnArgs {
-  const float* q;  // [H*D], already normed/rotated/scaled
-  const __half *kcache, *vcache;
+  const float *q, *k, *v;          // raw outputs of the q/k/v mat-vecs: [H*D], [HK*D], [HK*D]
+  const float *wq_norm, *wk_norm;  // [D]
+  __half *kcache, *vcache;         // this layer's [t_max][HK][D]; row `pos` is appended
   uint32_t H, HK, D, t_max;
+  double eps;
+  float attn_scale;
+  const float2* rope_table;  // [t_max][D/2] (cos, sin) for this layer's rope base
   const int32_t* pos;
   float softcap;
   float* out;  // [H*D]
@@ -54,7 +47,7 @@ struct AttnArgs {
 cudaError_t llmi_launch_embed(const EmbedArgs& a, const int32_t* token, float scale, float* h, cudaStream_t s);
 cudaError_t llmi_launch_norm_act(const NormArgs& a, cudaStream_t s);
 cudaError_t llmi_launch_act(const float* x, uint32_t n, int kind, uint8_t* buf, cudaStream_t s);
-cudaError_t llmi_launch_qkv_post(const QkvArgs& a, cudaStream_t s);
+cudaError_t llmi_launch_rope_table(float2* table, uint32_t t_max, uint32_t D, float base, float scale, cudaStream_t s);
 size_t llmi_attention_smem(uint32_t t_max, uint32_t D);
 cudaError_t llmi_attention_init(uint32_t t_max, uint32_t D);
 cudaError_t llmi_launch_attention(const AttnArgs& a, cudaStream_t s);

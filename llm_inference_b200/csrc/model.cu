@@ -48,6 +48,7 @@ struct llmi_model_s {
   __half *kcache = nullptr, *vcache = nullptr;
   int32_t *d_tok = nullptr, *d_pos = nullptr, *d_gen = nullptr, *d_gen_count = nullptr, *d_toks = nullptr;
   unsigned long long* d_key = nullptr;  // running argmax key of the logits mat-vec epilogue
+  float2 *rope_swa = nullptr, *rope_global = nullptr;  // [t_max][D/2] (cos, sin) per rope base
   uint32_t toks_cap = 0, gen_cap = 0;
   cudaStream_t stream = nullptr;
   cudaGraphExec_t decode_graph = nullptr;
@@ -176,17 +177,14 @@ int run_step(llmi_model_s* m, const int32_t* tok, bool want_logits, bool want_ar
     M_RC(extra_acts(m, m->act_E, m->xn, E, kq, {w.k, w.v}));
     // model.cpp:754 (Q), 784 (K), 803 (V): one grid per format group
     M_RC(gemv_group(m, {w.q, w.k, w.v}, {m->q, m->k, m->v}, m->act_E));
-    QkvArgs qa;
-    qa.q = m->q; qa.k = m->k; qa.v = m->v; qa.wq_norm = w.q_norm; qa.wk_norm = w.k_norm;
-    qa.H = m->H; qa.HK = m->HK; qa.D = m->D; qa.eps = m->eps;
-    qa.rope_base = w.swa ? 10000.0f : m->rope_base;  // model.cpp:732
-    qa.rope_scale = m->rope_scale; qa.attn_scale = m->attn_scale; qa.pos = m->d_pos; qa.q_out = m->q_rot;
-    qa.kcache = m->kcache + size_t(l) * m->t_max * m->HK * m->D;
-    qa.vcache = m->vcache + size_t(l) * m->t_max * m->HK * m->D;
-    M_TRY(llmi_launch_qkv_post(qa, s));
-    AttnArgs aa;
-    aa.q = m->q_rot; aa.kcache = qa.kcache; aa.vcache = qa.vcache; aa.H = m->H; aa.HK = m->HK; aa.D = m->D;
-    aa.t_max = m->t_max; aa.pos = m->d_pos; aa.softcap = m->attn_softcap; aa.out = m->attn;
+    AttnArgs aa;  // q/k norm, RoPE, KV append and attention in one kernel
+    aa.q = m->q; aa.k = m->k; aa.v = m->v; aa.wq_norm = w.q_norm; aa.wk_norm = w.k_norm;
+    aa.kcache = m->kcache + size_t(l) * m->t_max * m->HK * m->D;
+    aa.vcache = m->vcache + size_t(l) * m->t_max * m->HK * m->D;
+    aa.H = m->H; aa.HK = m->HK; aa.D = m->D; aa.t_max = m->t_max; aa.eps = m->eps;
+    aa.rope_table = w.swa ? m->rope_swa : m->rope_global;  // base 10000 on SWA layers (model.cpp:732)
+    aa.attn_scale = m->attn_scale; aa.pos = m->d_pos;
+    aa.softcap = m->attn_softcap; aa.out = m->attn;
     const int ko = llmi_act_kind_for(w.o->type);
     uint8_t* ko_buf = get_act(m->act_HD, ko, HD)->buf;
     const bool fuse_act = ko != ACT_Q8_K || m->D % 256 == 0;  // a head holds whole quantization blocks
@@ -195,7 +193,7 @@ int run_step(llmi_model_s* m, const int32_t* tok, bool want_logits, bool want_ar
       aa.act_buf = ko_buf;
     }
     M_TRY(llmi_launch_attention(aa, s));
-    m->launches_per_step += 2;
+    m->launches_per_step++;
     if (!fuse_act) {
       M_TRY(llmi_launch_act(m->attn, HD, ko, ko_buf, s));
       m->launches_per_step++;
@@ -279,7 +277,7 @@ int load_impl(llmi_model_s* m, const uint8_t* image, uint64_t size, uint32_t t_m
   const uint32_t Dv = uint32_t(kv_f(g, a + ".attention.value_length", double(m->D)));
   if (Dv != m->D || g.find(a + ".attention.key_length_swa") || g.find(a + ".attention.value_length_swa"))
     return llmi_fail(LLMI_ERR_TYPE, "llmi_model_load: per-layer / asymmetric head sizes are not supported");
-  if (m->D % 64 || m->H == 0 || m->HK == 0 || m->H % m->HK)
+  if (m->D % 64 || m->D > 512 || m->H == 0 || m->HK == 0 || m->H % m->HK)
     return llmi_fail(LLMI_ERR_SIZE, "llmi_model_load: head_dim must be a multiple of 64 and n_head a multiple of n_head_kv");
   if (kv_f(g, a + ".attention.max_alibi_bias", 0.0) > 0.0)
     return llmi_fail(LLMI_ERR_TYPE, "llmi_model_load: ALiBi is not supported");
@@ -359,6 +357,11 @@ int load_impl(llmi_model_s* m, const uint8_t* image, uint64_t size, uint32_t t_m
   M_TRY(cudaEventCreate(&m->ev0));
   M_TRY(cudaEventCreate(&m->ev1));
   M_TRY(llmi_attention_init(t_max, m->D));
+  M_RC(dev_alloc(m, (void**)&m->rope_swa, size_t(t_max) * (m->D / 2) * sizeof(float2)));
+  M_RC(dev_alloc(m, (void**)&m->rope_global, size_t(t_max) * (m->D / 2) * sizeof(float2)));
+  M_TRY(llmi_launch_rope_table(m->rope_swa, t_max, m->D, 10000.0f, m->rope_scale, m->stream));
+  M_TRY(llmi_launch_rope_table(m->rope_global, t_max, m->D, m->rope_base, m->rope_scale, m->stream));
+  M_TRY(cudaStreamSynchronize(m->stream));
   return LLMI_OK;
 }
 

@@ -174,6 +174,14 @@ def gemv(w: DeviceWeight, act: Activation, out: DeviceVector, stream=None) -> No
     _lib.check(_lib.load().llmi_gemv(w.h, act.h, out.p, stream))
 
 
+def gemv_batch(ws, act: Activation, outs, stream=None) -> None:
+    """Up to 3 same-format matrices consuming one activation, as one grid (llmi_gemv_batch)."""
+    n = len(ws)
+    wa = (C.c_void_p * n)(*[w.h for w in ws])
+    oa = (C.c_void_p * n)(*[o.p for o in outs])
+    _lib.check(_lib.load().llmi_gemv_batch(wa, oa, n, act.h, stream))
+
+
 def mat_vec_mul_dev(w: DeviceWeight, x: DeviceVector, act: Activation, out: DeviceVector, stream=None) -> None:
     _lib.check(_lib.load().llmi_mat_vec_mul_dev(w.h, x.p, act.h, out.p, stream))
 
@@ -293,6 +301,6 @@ def registry_clear() -> None:
 __all__ = [
     "init_ops", "mat_vec_mul", "mat_vec_mul_q4_0", "mat_vec_mul_q4_k", "mat_vec_mul_q6_k", "mat_vec_mul_q8_0",
     "mat_vec_mul_q5_0", "mat_vec_mul_bf16", "mat_vec_mul_fp16", "quantize_row_q8_0", "quantize_row_q8_k",
-    "DeviceWeight", "DeviceVector", "TorchVector", "Activation", "gemv", "mat_vec_mul_dev", "block_dots", "set_gemv_shape",
+    "DeviceWeight", "DeviceVector", "TorchVector", "Activation", "gemv", "gemv_batch", "mat_vec_mul_dev", "block_dots", "set_gemv_shape",
     "device_sync", "registry_clear", "row_bytes",
 ]

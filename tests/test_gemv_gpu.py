@@ -278,3 +278,29 @@ def test_reference_known_answers_on_gpu(gpu_ops):
     for t, blk, k, expect, tol in cases:
         o, _ = _run(ops, t, blk, np.ones(k, np.float32), 1, k)
         assert abs(o[0] - expect) < tol, (synth.TYPE_NAMES[t], o[0])
+
+
+def test_batched_launch_equals_separate_launches(gpu_ops, port):
+    # q/k/v (and gate/up) of a layer go out as one grid: same bits as three calls
+    ops = gpu_ops
+    k = 1152
+    x = np.random.default_rng(5).standard_normal(k).astype(np.float32)
+    dx, act = ops.DeviceVector(k, x), ops.Activation(k)
+    for t in (Q4_0, Q8_0, F16):
+        shapes = [1024, 256, 264]
+        ws = [_weights(t, n, k, seed=n) for n in shapes]
+        dws = [ops.DeviceWeight(w, t, k, n) for w, n in zip(ws, shapes)]
+        outs_b = [ops.DeviceVector(n) for n in shapes]
+        outs_s = [ops.DeviceVector(n) for n in shapes]
+        act.prepare(dws[0], dx)
+        ops.gemv_batch(dws, act, outs_b)
+        for w, o in zip(dws, outs_s):
+            ops.gemv(w, act, o)
+        ops.device_sync()
+        for w, n, ob, os_ in zip(ws, shapes, outs_b, outs_s):
+            assert np.array_equal(ob.get().view(np.uint32), os_.get().view(np.uint32))
+            _check(ob.get(), port.mat_vec_mul(t, w, x, n, k), "batched")
+    w4, w8 = ops.DeviceWeight(_weights(Q4_0, 8, k, 1), Q4_0, k, 8), ops.DeviceWeight(_weights(Q8_0, 8, k, 1), Q8_0, k, 8)
+    act.prepare(w4, dx)
+    with pytest.raises(RuntimeError, match="share one format"):
+        ops.gemv_batch([w4, w8], act, [ops.DeviceVector(8), ops.DeviceVector(8)])
