@@ -229,6 +229,13 @@ __global__ void act_kernel(const float* __restrict__ x, uint32_t n, int kind, ui
 // x1' = fma(v0, sin, v1*cos); angle = (float(pos) * (1/powf(base, 2i/n_rot))) / scale.
 constexpr int ATT_TILE = 128;
 
+#ifdef LLMI_ATTN_TIMING  // dev only (tools/attn_bench.cu): cycle stamps of CTA 0 at the phase boundaries
+__device__ long long g_attn_stamp[16];
+#define ATTN_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_attn_stamp[i] = clock64(); } while (0)
+#else
+#define ATTN_STAMP(i) do { } while (0)
+#endif
+
 // RoPE factors for every (position, pair): ops.cpp:80-83 —
 //   freq = 1.0f / powf(base, float(2i)/n_rot); val = float(pos) * freq / scale; cosf(val), sinf(val)
 __global__ void rope_table_kernel(float2* table, uint32_t t_max, uint32_t D, float base, float scale) {
@@ -291,9 +298,11 @@ __global__ void __launch_bounds__(1024) attention_kernel(AttnArgs a) {
     wk0 = a.wk_norm[i];
     wk1 = a.wk_norm[i + half];
   }
+  ATTN_STAMP(0);
   pdl_wait();
   const int pos = *a.pos, T = pos + 1;
   float q0 = 0.0f, q1 = 0.0f, k0 = 0.0f, k1 = 0.0f, v0 = 0.0f, v1 = 0.0f;
+  float2 csn = make_float2(1.0f, 0.0f);
   if (pair) {
     q0 = a.q[h * D + i];
     q1 = a.q[h * D + i + half];
@@ -301,18 +310,34 @@ __global__ void __launch_bounds__(1024) attention_kernel(AttnArgs a) {
     k1 = a.k[hkv * D + i + half];
     v0 = a.v[hkv * D + i];
     v1 = a.v[hkv * D + i + half];
+    // (cos, sin) of (float(pos) * (1/powf(base, 2i/D))) / scale: tabulated per position at
+    // load time by rope_table_kernel with exactly this arithmetic
+    csn = a.rope_table[size_t(pos) * half + i];
   }
-  const float ssq = block_sum(__fadd_rn(__fmul_rn(q0, q0), __fmul_rn(q1, q1)), red);
-  const float ssk = block_sum(__fadd_rn(__fmul_rn(k0, k0), __fmul_rn(k1, k1)), red);
+  ATTN_STAMP(1);
+  // sums of squares of the q and k head: only the first D/64 warps hold data
+  float sq = __fadd_rn(__fmul_rn(q0, q0), __fmul_rn(q1, q1)), sk = __fadd_rn(__fmul_rn(k0, k0), __fmul_rn(k1, k1));
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    sk += __shfl_xor_sync(0xffffffffu, sk, o);
+  }
+  if (lane == 0 && warp < 16) {
+    red[warp] = sq;
+    red[16 + warp] = sk;
+  }
+  __syncthreads();
+  float ssq = 0.0f, ssk = 0.0f;
+  for (uint32_t w = 0; w < (half + 31) / 32; ++w) {
+    ssq += red[w];
+    ssk += red[16 + w];
+  }
   if (pair) {
     const float scq = rms_scale(ssq, D, a.eps), sck = rms_scale(ssk, D, a.eps);
     q0 = __fmul_rn(__fmul_rn(scq, q0), wq0);
     q1 = __fmul_rn(__fmul_rn(scq, q1), wq1);
     k0 = __fmul_rn(__fmul_rn(sck, k0), wk0);
     k1 = __fmul_rn(__fmul_rn(sck, k1), wk1);
-    // (cos, sin) of (float(pos) * (1/powf(base, 2i/D))) / scale: tabulated per position at
-    // load time by rope_table_kernel with exactly this arithmetic
-    const float2 csn = a.rope_table[size_t(pos) * half + i];
     const float cs = csn.x, sn = csn.y;
     const float qa = __fmul_rn(__fmaf_rn(q0, cs, -__fmul_rn(q1, sn)), a.attn_scale);
     const float qb = __fmul_rn(__fmaf_rn(q0, sn, __fmul_rn(q1, cs)), a.attn_scale);
@@ -335,15 +360,20 @@ __global__ void __launch_bounds__(1024) attention_kernel(AttnArgs a) {
     }
   }
   __syncthreads();
+  ATTN_STAMP(2);
   // phase 1: scores.  K rows of this KV head are staged in shared-memory tiles
   // of ATT_TILE positions with cp.async (one memory round trip per tile instead
   // of one per position: only H CTAs run, so latency, not bandwidth, is the cost).
   // One warp per position, each lane a contiguous run of D/32 elements.
   {
     const uint32_t vec = D / 32;  // 2, 4, 8 or 16 halves per lane
+    float qreg[16];               // this lane's slice of q, loop-invariant (registers: no bank conflicts)
+#pragma unroll
+    for (uint32_t j = 0; j < 16; ++j) qreg[j] = j < vec ? qh[lane * vec + j] : 0.0f;
     for (int t0 = 0; t0 < T; t0 += ATT_TILE) {
       const int nt = min(ATT_TILE, T - t0);
       load_kv_tile(tile, a.kcache, t0, nt, pos, knew, a.HK, hkv, D);
+      ATTN_STAMP(8);
       for (int r = warp; r < nt; r += nw) {
         const __half* kp = tile + size_t(r) * D + lane * vec;
         __half kv[16];
@@ -360,7 +390,7 @@ __global__ void __launch_bounds__(1024) attention_kernel(AttnArgs a) {
         double s = 0.0;
 #pragma unroll
         for (uint32_t j = 0; j < 16; ++j)
-          if (j < vec) s += double(__fmul_rn(__half2float(kv[j]), qh[lane * vec + j]));
+          if (j < vec) s += double(__fmul_rn(__half2float(kv[j]), qreg[j]));
 #pragma unroll
         for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (lane == 0) {
@@ -371,6 +401,7 @@ __global__ void __launch_bounds__(1024) attention_kernel(AttnArgs a) {
       __syncthreads();  // tile is reused
     }
   }
+  ATTN_STAMP(3);
   // phase 2a: exclusive prefix max of float(score) (warp 0)
   if (warp == 0) {
     const int chunk = (T + 31) / 32, t0 = lane * chunk, t1 = min(T, t0 + chunk);
@@ -406,6 +437,7 @@ __global__ void __launch_bounds__(1024) attention_kernel(AttnArgs a) {
     }
   }
   __syncthreads();
+  ATTN_STAMP(4);
   // phase 2c: s_acc = s_acc*pse + se, sequential, no FMA (model.cpp:540).  The
   // operands are fetched 8 positions at a time so that only the mul+add chain is
   // serial, not the shared-memory latency.
@@ -429,36 +461,45 @@ __global__ void __launch_bounds__(1024) attention_kernel(AttnArgs a) {
   // staged tile by tile like K.  The per-position factors of 8 positions are
   // fetched together, then folded in order.
   {
-    __half vacc[2] = {__float2half_rn(0.0f), __float2half_rn(0.0f)};  // elements tid, tid + blockDim (D <= 512)
+    // The accumulator is kept as an fp32 register that always holds an
+    // f16-representable value: r16(x) = f32(f16(x)) is the rounding the reference
+    // applies at every step.  A new running maximum (rare: ~ln T positions)
+    // rescales first; chunks of 8 positions without one take the short chain.
+    float vacc[2] = {0.0f, 0.0f};  // elements tid, tid + blockDim (D <= 512)
     for (int t0 = 0; t0 < T; t0 += ATT_TILE) {
       const int nt = min(ATT_TILE, T - t0);
+      ATTN_STAMP(9);
       load_kv_tile(tile, a.vcache, t0, nt, pos, vnew, a.HK, hkv, D);
+      ATTN_STAMP(10);
 #pragma unroll
       for (int w = 0; w < 2; ++w) {
         const uint32_t e = threadIdx.x + w * blockDim.x;
         if (e < D) {
-          __half v = vacc[w];
+          float v = vacc[w];
           int r = 0;
           for (; r + 8 <= nt; r += 8) {
-            __half x8[8];
-            float e8[8], p8[8];
-            uint8_t n8[8];
+            float x8[8], e8[8];
+            uint32_t any = 0;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              x8[j] = tile[size_t(r + j) * D + e];
+              x8[j] = __half2float(tile[size_t(r + j) * D + e]);
               e8[j] = se[t0 + r + j];
-              p8[j] = pse[t0 + r + j];
-              n8[j] = nm[t0 + r + j];
+              any |= nm[t0 + r + j];
             }
+            if (!any) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              if (n8[j]) v = __float2half_rn(__fmul_rn(__half2float(v), p8[j]));
-              v = __float2half_rn(__fmaf_rn(__half2float(x8[j]), e8[j], __half2float(v)));
+              for (int j = 0; j < 8; ++j) v = __half2float(__float2half_rn(__fmaf_rn(x8[j], e8[j], v)));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                if (nm[t0 + r + j]) v = __half2float(__float2half_rn(__fmul_rn(v, pse[t0 + r + j])));
+                v = __half2float(__float2half_rn(__fmaf_rn(x8[j], e8[j], v)));
+              }
             }
           }
           for (; r < nt; ++r) {
-            if (nm[t0 + r]) v = __float2half_rn(__fmul_rn(__half2float(v), pse[t0 + r]));
-            v = __float2half_rn(__fmaf_rn(__half2float(tile[size_t(r) * D + e]), se[t0 + r], __half2float(v)));
+            if (nm[t0 + r]) v = __half2float(__float2half_rn(__fmul_rn(v, pse[t0 + r])));
+            v = __half2float(__float2half_rn(__fmaf_rn(__half2float(tile[size_t(r) * D + e]), se[t0 + r], v)));
           }
           vacc[w] = v;
         }
@@ -468,15 +509,17 @@ __global__ void __launch_bounds__(1024) attention_kernel(AttnArgs a) {
 #pragma unroll
     for (int w = 0; w < 2; ++w) {
       const uint32_t e = threadIdx.x + w * blockDim.x;
-      if (e < D) qh[e] = __half2float(vacc[w]);  // q no longer needed
+      if (e < D) qh[e] = vacc[w];  // q no longer needed
     }
   }
+  ATTN_STAMP(5);
   __syncthreads();
   for (uint32_t e = threadIdx.x; e < D; e += blockDim.x) {
     const float o = __fmul_rn(qh[e], s_inv);
     qh[e] = o;
     a.out[h * D + e] = o;
   }
+  ATTN_STAMP(6);
   // Fused quantizer of the attn_output mat-vec: this head's D outputs are whole
   // Q8_0 blocks (and whole Q8_K super-blocks when D % 256 == 0).
   if (a.act_kind == ACT_NONE) return;
