@@ -9,6 +9,8 @@
 #include <cuda_fp16.h>
 #include <math.h>
 
+#include <type_traits>
+
 #include "glue.h"
 #include "launch.cuh"
 #include "quant_device.cuh"
@@ -227,13 +229,25 @@ __global__ void act_kernel(const float* __restrict__ x, uint32_t n, int kind, ui
 //     phase 4  out = f32(v) / s_acc (:543-547) + the quantizer of attn_output
 // rope in the reference's object code: x0' = fma(v0, cos, -(v1*sin)),
 // x1' = fma(v0, sin, v1*cos); angle = (float(pos) * (1/powf(base, 2i/n_rot))) / scale.
-constexpr int ATT_TILE = 128;
+// K/V rows stream through a ring of shared-memory tiles of ATT_TILE_BYTES each
+// (16384/D positions per tile), filled by per-row bulk async copies
+// (cp.async.bulk -> UBLKCP) that complete on one mbarrier per tile.
+constexpr int ATT_TILE_BYTES = 32768;
+constexpr int ATT_MAX_BUF = 6;
 
-#ifdef LLMI_ATTN_TIMING  // dev only (tools/attn_bench.cu): cycle stamps of CTA 0 at the phase boundaries
+#ifdef LLMI_ATTN_TIMING  // dev only (tools/attn_bench.cu): cycle stamps of CTA 0 at the phase boundaries.
+// BAR.SYNC does not block at issue, so the stamp is made to depend on the barrier's result.
 __device__ long long g_attn_stamp[16];
-#define ATTN_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_attn_stamp[i] = clock64(); } while (0)
+#define ATTN_STAMP(i)                                                     \
+  do {                                                                    \
+    const int c_ = __syncthreads_count(1);                                \
+    if (c_ < 0) return;                                                   \
+    if (blockIdx.x == 0 && threadIdx.x == 0) g_attn_stamp[i] = clock64(); \
+  } while (0)
+#define ATTN_RAW(i, tid) do { if (blockIdx.x == 0 && threadIdx.x == (tid)) g_attn_stamp[i] = clock64(); } while (0)
 #else
 #define ATTN_STAMP(i) do { } while (0)
+#define ATTN_RAW(i, tid) do { } while (0)
 #endif
 
 // RoPE factors for every (position, pair): ops.cpp:80-83 —
@@ -250,89 +264,122 @@ __global__ void rope_table_kernel(float2* table, uint32_t t_max, uint32_t D, flo
   table[idx] = make_float2(cs, sn);
 }
 
-// Stages rows [t0, t0+nt) of one KV head into shared memory with 16-byte
-// cp.async copies (all threads, all copies in flight at once); the row of the
-// current token comes from shared memory (it may not be in the cache yet).
-__device__ __forceinline__ void load_kv_tile(__half* tile, const __half* cache, int t0, int nt, int pos,
-                                             const __half* newrow, uint32_t HK, uint32_t hkv, uint32_t D) {
-  const uint32_t cpr = D / 8;  // 16-byte chunks per row
-  for (uint32_t c = threadIdx.x; c < uint32_t(nt) * cpr; c += blockDim.x) {
-    const uint32_t r = c / cpr, k = c - r * cpr;
-    const int t = t0 + int(r);
-    __half* dst = tile + size_t(r) * D + k * 8;
-    if (t == pos) {
-      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(newrow + k * 8);
-    } else {
-      const __half* src = cache + (size_t(t) * HK + hkv) * D + k * 8;
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src)
-                   : "memory");
-    }
-  }
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncthreads();
-}
+__device__ __forceinline__ float r16(float x) { return __half2float(__float2half_rn(x)); }
 
-__global__ void __launch_bounds__(1024) attention_kernel(AttnArgs a) {
+// The K cache holds, per element, the HIGH WORD OF THE DOUBLE that equals the
+// f16-rounded key (the low word of such a double is zero).  The reference's
+// score is sum_i double(f32(k_i) * f32(q_i)) (model.cpp:504-509); the product
+// of two f16 values is exact in fp32, so fma(double(k_i), double(q_i), s)
+// rounds exactly the same sum — one DFMA per element and no conversion in the
+// loop (F2F.F64.F32 runs at 16 lanes/clk/SM and would bound the phase).
+__device__ __forceinline__ uint32_t f16_as_double_hi(__half h) { return uint32_t(__double2hiint(double(__half2float(h)))); }
+
+template <int D>
+__global__ void __launch_bounds__(1024) attention_kernel(AttnArgs a, uint32_t nbuf) {
   pdl_trigger();
-  extern __shared__ __align__(16) uint8_t smraw[];
+  constexpr int HALF = D / 2, VEC = D / 32;           // elements per lane in phase 1
+  constexpr int RTK = ATT_TILE_BYTES / (4 * D);       // K rows per tile (4 bytes per element)
+  constexpr int RTV = ATT_TILE_BYTES / (2 * D);       // V rows per tile (f16)
+  constexpr int PIECES = VEC >= 4 ? VEC / 4 : 1, PW = VEC >= 4 ? 4 : VEC;  // 16-byte pieces per lane / words per piece
+  extern __shared__ __align__(128) uint8_t smraw[];
   __shared__ float red[32];
+  __shared__ float wmax[32];
   __shared__ float s_inv;
-  const uint32_t D = a.D, half = D / 2, h = blockIdx.x, group = a.H / a.HK, hkv = h / group;
-  double* sc = reinterpret_cast<double*>(smraw);                 // [t_max]
-  float* se = reinterpret_cast<float*>(sc + a.t_max);            // [t_max]
-  float* pse = se + a.t_max;                                     // [t_max] (first holds M_prev)
-  float* qh = pse + a.t_max;                                     // [D]
-  __half* knew = reinterpret_cast<__half*>(qh + D);              // [D] this token's K row (f16)
-  __half* vnew = knew + D;                                       // [D] this token's V row (f16)
-  __half* tile = vnew + D;                                       // [ATT_TILE][D] staged K or V rows
-  uint8_t* nm = reinterpret_cast<uint8_t*>(tile + size_t(ATT_TILE) * D);  // [t_max]
+  __shared__ __align__(8) uint64_t bars[ATT_MAX_BUF];
+  const uint32_t h = blockIdx.x, group = a.H / a.HK, hkv = h / group;
+  const uint32_t tp = (a.t_max + 15) & ~15u;
+  uint8_t* tiles = smraw;                                                    // [nbuf][ATT_TILE_BYTES]
+  double* sc = reinterpret_cast<double*>(smraw + size_t(nbuf) * ATT_TILE_BYTES);  // [tp] scores
+  float* se = reinterpret_cast<float*>(sc + tp);                             // [tp] score_exp
+  float* pse = se + tp;                                                      // [tp] prev_score_exp
+  float* qh = pse + tp;                                                      // [D] output staging
+  uint32_t* qhi = reinterpret_cast<uint32_t*>(qh + D);                       // [D] f16(q) as double high words
+  uint32_t* knew = qhi + D;                                                  // [D] this token's K row (double high words)
+  __half* vnew = reinterpret_cast<__half*>(knew + D);                        // [D] this token's V row (f16)
+  uint8_t* nm = reinterpret_cast<uint8_t*>(vnew + D);                        // [tp] 1 where the running max moves
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const uint32_t i = threadIdx.x;
-  const bool pair = i < half;  // thread i owns the rotation pair (i, i + D/2)
+  const bool pair = i < HALF;  // thread i owns the rotation pair (i, i + D/2)
   // static inputs, fetched under the predecessor's tail
   float wq0 = 0.0f, wq1 = 0.0f, wk0 = 0.0f, wk1 = 0.0f;
   if (pair) {
     wq0 = a.wq_norm[i];
-    wq1 = a.wq_norm[i + half];
+    wq1 = a.wq_norm[i + HALF];
     wk0 = a.wk_norm[i];
-    wk1 = a.wk_norm[i + half];
+    wk1 = a.wk_norm[i + HALF];
   }
+  if (threadIdx.x == 0)
+    for (uint32_t b = 0; b < nbuf; ++b) mbar_init(&bars[b], 1);
   ATTN_STAMP(0);
   pdl_wait();
   const int pos = *a.pos, T = pos + 1;
+  // The tile stream: K tiles 0..n_tk-1, then V tiles 0..n_tv-1, through the ring.
+  // Rows of one KV head are contiguous ([HK][t_max][D]): one bulk copy per tile.
+  // Row `pos` (always the last row of the last tile) is not in the cache yet: it
+  // is taken from knew/vnew, so a tile's copy never depends on this kernel's stores.
+  const int n_tk = (T + RTK - 1) / RTK, n_tv = (T + RTV - 1) / RTV, n_stream = n_tk + n_tv;
+  auto issue_tile = [&](int j, int buf) {  // one thread
+    uint64_t* bar = &bars[buf];
+    uint8_t* dst = tiles + size_t(buf) * ATT_TILE_BYTES;
+    if (j < n_tk) {
+      const int t0 = j * RTK, n_cached = min(RTK, T - t0) - (j == n_tk - 1 ? 1 : 0);
+      mbar_expect_tx(bar, uint32_t(n_cached) * D * 4);
+      if (n_cached) bulk_g2s(dst, a.kcache + (size_t(hkv) * a.t_max + t0) * D, uint32_t(n_cached) * D * 4, bar);
+    } else {
+      const int jj = j - n_tk, t0 = jj * RTV, n_cached = min(RTV, T - t0) - (jj == n_tv - 1 ? 1 : 0);
+      mbar_expect_tx(bar, uint32_t(n_cached) * D * 2);
+      if (n_cached) bulk_g2s(dst, a.vcache + (size_t(hkv) * a.t_max + t0) * D, uint32_t(n_cached) * D * 2, bar);
+    }
+  };
+  if (threadIdx.x == 0)
+    for (int j = 0; j < min(int(nbuf), n_stream); ++j) issue_tile(j, j);
+  int cbuf = 0;          // ring position of the tile being consumed
+  uint32_t cpar = 0;     // its mbarrier phase parity
+  int cj = 0;            // its index in the stream
+  auto tile_done = [&]() {  // all threads; the consumed tile is refilled with the tile nbuf further down
+    __syncthreads();
+    if (threadIdx.x == 0 && cj + int(nbuf) < n_stream) issue_tile(cj + int(nbuf), cbuf);
+    ++cj;
+    if (++cbuf == int(nbuf)) {
+      cbuf = 0;
+      cpar ^= 1;
+    }
+  };
   float q0 = 0.0f, q1 = 0.0f, k0 = 0.0f, k1 = 0.0f, v0 = 0.0f, v1 = 0.0f;
   float2 csn = make_float2(1.0f, 0.0f);
   if (pair) {
     q0 = a.q[h * D + i];
-    q1 = a.q[h * D + i + half];
+    q1 = a.q[h * D + i + HALF];
     k0 = a.k[hkv * D + i];
-    k1 = a.k[hkv * D + i + half];
+    k1 = a.k[hkv * D + i + HALF];
     v0 = a.v[hkv * D + i];
-    v1 = a.v[hkv * D + i + half];
+    v1 = a.v[hkv * D + i + HALF];
     // (cos, sin) of (float(pos) * (1/powf(base, 2i/D))) / scale: tabulated per position at
     // load time by rope_table_kernel with exactly this arithmetic
-    csn = a.rope_table[size_t(pos) * half + i];
+    csn = a.rope_table[size_t(pos) * HALF + i];
   }
   ATTN_STAMP(1);
   // sums of squares of the q and k head: only the first D/64 warps hold data
-  float sq = __fadd_rn(__fmul_rn(q0, q0), __fmul_rn(q1, q1)), sk = __fadd_rn(__fmul_rn(k0, k0), __fmul_rn(k1, k1));
+  if (warp < (HALF + 31) / 32) {
+    float sq = __fadd_rn(__fmul_rn(q0, q0), __fmul_rn(q1, q1)), sk = __fadd_rn(__fmul_rn(k0, k0), __fmul_rn(k1, k1));
 #pragma unroll
-  for (int o = 16; o; o >>= 1) {
-    sq += __shfl_xor_sync(0xffffffffu, sq, o);
-    sk += __shfl_xor_sync(0xffffffffu, sk, o);
-  }
-  if (lane == 0 && warp < 16) {
-    red[warp] = sq;
-    red[16 + warp] = sk;
+    for (int o = 16; o; o >>= 1) {
+      sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      sk += __shfl_xor_sync(0xffffffffu, sk, o);
+    }
+    if (lane == 0) {
+      red[warp] = sq;
+      red[16 + warp] = sk;
+    }
   }
   __syncthreads();
-  float ssq = 0.0f, ssk = 0.0f;
-  for (uint32_t w = 0; w < (half + 31) / 32; ++w) {
-    ssq += red[w];
-    ssk += red[16 + w];
-  }
   if (pair) {
+    float ssq = 0.0f, ssk = 0.0f;
+#pragma unroll
+    for (int w = 0; w < (HALF + 31) / 32; ++w) {
+      ssq += red[w];
+      ssk += red[16 + w];
+    }
     const float scq = rms_scale(ssq, D, a.eps), sck = rms_scale(ssk, D, a.eps);
     q0 = __fmul_rn(__fmul_rn(scq, q0), wq0);
     q1 = __fmul_rn(__fmul_rn(scq, q1), wq1);
@@ -341,183 +388,244 @@ __global__ void __launch_bounds__(1024) attention_kernel(AttnArgs a) {
     const float cs = csn.x, sn = csn.y;
     const float qa = __fmul_rn(__fmaf_rn(q0, cs, -__fmul_rn(q1, sn)), a.attn_scale);
     const float qb = __fmul_rn(__fmaf_rn(q0, sn, __fmul_rn(q1, cs)), a.attn_scale);
-    qh[i] = __half2float(__float2half_rn(qa));  // Q is rounded to f16 for the scores (model.cpp:506)
-    qh[i + half] = __half2float(__float2half_rn(qb));
+    qhi[i] = f16_as_double_hi(__float2half_rn(qa));  // Q is rounded to f16 for the scores (model.cpp:506)
+    qhi[i + HALF] = f16_as_double_hi(__float2half_rn(qb));
     const __half ka = __float2half_rn(__fmaf_rn(k0, cs, -__fmul_rn(k1, sn)));
     const __half kb = __float2half_rn(__fmaf_rn(k0, sn, __fmul_rn(k1, cs)));
     const __half va = __float2half_rn(v0), vb = __float2half_rn(v1);
-    knew[i] = ka;
-    knew[i + half] = kb;
+    const uint32_t kah = f16_as_double_hi(ka), kbh = f16_as_double_hi(kb);
+    knew[i] = kah;
+    knew[i + HALF] = kbh;
     vnew[i] = va;
-    vnew[i + half] = vb;
+    vnew[i + HALF] = vb;
     if (h % group == 0) {  // one writer per KV head
-      __half* kd = a.kcache + (size_t(pos) * a.HK + hkv) * D;
-      __half* vd = a.vcache + (size_t(pos) * a.HK + hkv) * D;
-      kd[i] = ka;
-      kd[i + half] = kb;
+      uint32_t* kd = a.kcache + (size_t(hkv) * a.t_max + pos) * D;
+      __half* vd = a.vcache + (size_t(hkv) * a.t_max + pos) * D;
+      kd[i] = kah;
+      kd[i + HALF] = kbh;
       vd[i] = va;
-      vd[i + half] = vb;
+      vd[i + HALF] = vb;
     }
   }
   __syncthreads();
   ATTN_STAMP(2);
-  // phase 1: scores.  K rows of this KV head are staged in shared-memory tiles
-  // of ATT_TILE positions with cp.async (one memory round trip per tile instead
-  // of one per position: only H CTAs run, so latency, not bandwidth, is the cost).
-  // One warp per position, each lane a contiguous run of D/32 elements.
+  // phase 1: scores.  One warp per position, four positions in flight per warp.
+  // A lane owns the 16-byte pieces {c*128 + 4*lane .. +3} of the row (conflict-free
+  // LDS.128); its slice of q stays in registers as doubles.
   {
-    const uint32_t vec = D / 32;  // 2, 4, 8 or 16 halves per lane
-    float qreg[16];               // this lane's slice of q, loop-invariant (registers: no bank conflicts)
+    double qd[VEC];
 #pragma unroll
-    for (uint32_t j = 0; j < 16; ++j) qreg[j] = j < vec ? qh[lane * vec + j] : 0.0f;
-    for (int t0 = 0; t0 < T; t0 += ATT_TILE) {
-      const int nt = min(ATT_TILE, T - t0);
-      load_kv_tile(tile, a.kcache, t0, nt, pos, knew, a.HK, hkv, D);
-      ATTN_STAMP(8);
-      for (int r = warp; r < nt; r += nw) {
-        const __half* kp = tile + size_t(r) * D + lane * vec;
-        __half kv[16];
-        if (vec == 8) {
-          *reinterpret_cast<uint4*>(kv) = *reinterpret_cast<const uint4*>(kp);
-        } else if (vec == 4) {
-          *reinterpret_cast<uint2*>(kv) = *reinterpret_cast<const uint2*>(kp);
-        } else if (vec == 16) {
-          *reinterpret_cast<uint4*>(kv) = *reinterpret_cast<const uint4*>(kp);
-          *reinterpret_cast<uint4*>(kv + 8) = *reinterpret_cast<const uint4*>(kp + 8);
+    for (int c = 0; c < PIECES; ++c)
+#pragma unroll
+      for (int w = 0; w < PW; ++w) qd[c * PW + w] = __hiloint2double(int(qhi[c * 32 * PW + lane * PW + w]), 0);
+    auto lane_dot = [&](const uint32_t* row) {
+      double s = 0.0;
+#pragma unroll
+      for (int c = 0; c < PIECES; ++c) {
+        uint32_t w[4] = {0, 0, 0, 0};
+        const uint32_t* p = row + c * 32 * PW + lane * PW;
+        if (PW == 4) {
+          const uint4 u = *reinterpret_cast<const uint4*>(p);
+          w[0] = u.x; w[1] = u.y; w[2] = u.z; w[3] = u.w;
         } else {
-          *reinterpret_cast<uint32_t*>(kv) = *reinterpret_cast<const uint32_t*>(kp);
+          const uint2 u = *reinterpret_cast<const uint2*>(p);
+          w[0] = u.x; w[1] = u.y;
         }
-        double s = 0.0;
 #pragma unroll
-        for (uint32_t j = 0; j < 16; ++j)
-          if (j < vec) s += double(__fmul_rn(__half2float(kv[j]), qreg[j]));
-#pragma unroll
-        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) {
-          if (a.softcap > 0.0f) s = double(__fmul_rn(a.softcap, tanhf(float(s / double(a.softcap)))));
-          sc[t0 + r] = s;
+        for (int k = 0; k < PW; ++k) s = __fma_rn(__hiloint2double(int(w[k]), 0), qd[c * PW + k], s);
+      }
+      return s;
+    };
+    // K tiles are consumed in sweeps of up to 4 tiles (all of them in flight
+    // since the kernel started or since the previous sweep), so that every warp
+    // has four positions and the CTA synchronizes once per sweep.
+    const uint32_t* tiles32 = reinterpret_cast<const uint32_t*>(tiles);
+    const int G = min(4, int(nbuf));
+    while (cj < n_tk) {
+      const int g = min(n_tk - cj, G);
+      {
+        int b2 = cbuf;
+        uint32_t p2 = cpar;
+        for (int x = 0; x < g; ++x) {
+          mbar_wait(&bars[b2], p2);
+          if (++b2 == int(nbuf)) {
+            b2 = 0;
+            p2 ^= 1;
+          }
         }
       }
-      __syncthreads();  // tile is reused
+      const int t0 = cj * RTK, nt = min(g * RTK, T - t0);
+      for (int r = 4 * warp; r < nt; r += 4 * nw) {
+        double s[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const int rr = min(r + p, nt - 1);
+          int slot = cbuf + rr / RTK;
+          if (slot >= int(nbuf)) slot -= int(nbuf);
+          s[p] = lane_dot(t0 + rr == pos ? knew : tiles32 + size_t(slot) * (ATT_TILE_BYTES / 4) + size_t(rr % RTK) * D);
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1)
+#pragma unroll
+          for (int p = 0; p < 4; ++p) s[p] += __shfl_xor_sync(0xffffffffu, s[p], o);
+        if (lane < 4 && r + lane < nt) {
+          double v = lane == 0 ? s[0] : (lane == 1 ? s[1] : (lane == 2 ? s[2] : s[3]));
+          if (a.softcap > 0.0f) v = double(__fmul_rn(a.softcap, tanhf(float(v / double(a.softcap)))));
+          sc[t0 + r + lane] = v;
+        }
+      }
+      __syncthreads();  // the sweep's tiles are free: refill them with the tiles nbuf further down the stream
+      for (int x = 0; x < g; ++x) {
+        if (threadIdx.x == 0 && cj + int(nbuf) < n_stream) issue_tile(cj + int(nbuf), cbuf);
+        ++cj;
+        if (++cbuf == int(nbuf)) {
+          cbuf = 0;
+          cpar ^= 1;
+        }
+      }
     }
   }
   ATTN_STAMP(3);
-  // phase 2a: exclusive prefix max of float(score) (warp 0)
-  if (warp == 0) {
-    const int chunk = (T + 31) / 32, t0 = lane * chunk, t1 = min(T, t0 + chunk);
-    float m = -INFINITY;
-    for (int t = t0; t < t1; ++t) m = fmaxf(m, float(sc[t]));
-    float run = m;  // inclusive scan of chunk maxima
+  // phase 2a/2b: one position per thread (blocks of blockDim positions).  The
+  // running max M before position t (model.cpp:520-533) is an exclusive prefix
+  // max of float(score): warp scan, then the maxima of the preceding warps.
+  {
+    float carry = -INFINITY;  // max over all earlier blocks
+    for (int base = 0; base < T; base += int(blockDim.x)) {
+      const int t = base + int(threadIdx.x);
+      const double s = t < T ? sc[t] : 0.0;
+      const float fs = t < T ? float(s) : -INFINITY;
+      float inc = fs;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const float other = __shfl_up_sync(0xffffffffu, run, o);
-      if (lane >= o) run = fmaxf(run, other);
-    }
-    float prev = __shfl_up_sync(0xffffffffu, run, 1);
-    if (lane == 0) prev = -INFINITY;
-    for (int t = t0; t < t1; ++t) {
-      pse[t] = prev;
-      prev = fmaxf(prev, float(sc[t]));
+      for (int o = 1; o < 32; o <<= 1) {
+        const float other = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc = fmaxf(inc, other);
+      }
+      float exc = __shfl_up_sync(0xffffffffu, inc, 1);
+      if (lane == 0) exc = -INFINITY;
+      if (lane == 31) wmax[warp] = inc;
+      __syncthreads();
+      float wm = wmax[lane];  // blockDim is 1024: one entry per warp
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float other = __shfl_up_sync(0xffffffffu, wm, o);
+        if (lane >= o) wm = fmaxf(wm, other);
+      }
+      float prevw = __shfl_sync(0xffffffffu, wm, warp ? warp - 1 : 0);
+      if (warp == 0) prevw = -INFINITY;
+      const float M = fmaxf(fmaxf(carry, prevw), exc);
+      carry = fmaxf(carry, __shfl_sync(0xffffffffu, wm, 31));
+      if (t < T) {
+        if (s > double(M)) {
+          nm[t] = 1;
+          se[t] = 1.0f;
+          pse[t] = expf(__fsub_rn(M, fs));
+        } else {
+          nm[t] = 0;
+          se[t] = expf(float(s - double(M)));
+          pse[t] = 1.0f;
+        }
+      }
+      __syncthreads();
     }
   }
-  __syncthreads();
-  // phase 2b
-  for (int t = threadIdx.x; t < T; t += blockDim.x) {
-    const float M = pse[t];
-    const double s = sc[t];
-    if (s > double(M)) {
-      const float fs = float(s);
-      nm[t] = 1;
-      se[t] = 1.0f;
-      pse[t] = expf(__fsub_rn(M, fs));
-    } else {
-      nm[t] = 0;
-      se[t] = expf(float(s - double(M)));
-      pse[t] = 1.0f;
-    }
-  }
-  __syncthreads();
   ATTN_STAMP(4);
-  // phase 2c: s_acc = s_acc*pse + se, sequential, no FMA (model.cpp:540).  The
-  // operands are fetched 8 positions at a time so that only the mul+add chain is
-  // serial, not the shared-memory latency.
+  // phase 2c: s_acc = s_acc*pse + se, sequential, no FMA (model.cpp:540), on a
+  // thread of a warp that idles in phase 3.  The operands are fetched 8 positions
+  // at a time so that only the mul+add chain is serial, not the shared-memory latency.
   if (threadIdx.x == blockDim.x - 1) {
+    ATTN_RAW(8, 1023);
     float s = 0.0f;
     int t = 0;
     for (; t + 8 <= T; t += 8) {
-      float p8[8], e8[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        p8[j] = pse[t + j];
-        e8[j] = se[t + j];
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) s = __fadd_rn(__fmul_rn(s, p8[j]), e8[j]);
+      const float4 pa = *reinterpret_cast<const float4*>(pse + t), pb = *reinterpret_cast<const float4*>(pse + t + 4);
+      const float4 ea = *reinterpret_cast<const float4*>(se + t), eb = *reinterpret_cast<const float4*>(se + t + 4);
+      s = __fadd_rn(__fmul_rn(s, pa.x), ea.x);
+      s = __fadd_rn(__fmul_rn(s, pa.y), ea.y);
+      s = __fadd_rn(__fmul_rn(s, pa.z), ea.z);
+      s = __fadd_rn(__fmul_rn(s, pa.w), ea.w);
+      s = __fadd_rn(__fmul_rn(s, pb.x), eb.x);
+      s = __fadd_rn(__fmul_rn(s, pb.y), eb.y);
+      s = __fadd_rn(__fmul_rn(s, pb.z), eb.z);
+      s = __fadd_rn(__fmul_rn(s, pb.w), eb.w);
     }
     for (; t < T; ++t) s = __fadd_rn(__fmul_rn(s, pse[t]), se[t]);
     s_inv = s == 0.0f ? 0.0f : __fdiv_rn(1.0f, s);
+    ATTN_RAW(9, 1023);
   }
-  // phase 3: the fp16 accumulator recurrence, one thread per element, V rows
-  // staged tile by tile like K.  The per-position factors of 8 positions are
-  // fetched together, then folded in order.
+  // phase 3: the fp16 accumulator recurrence, one thread per element.  The
+  // accumulator is an fp32 register that always holds an f16-representable
+  // value; r16(x) = f32(f16(x)) is the rounding the reference applies at every
+  // step (vec_mad_f16, ops.cpp:1084-1099).  A new running maximum (rare: ~ln T
+  // positions) rescales first; chunks of 8 positions without one take the short
+  // chain.  The raw operands of the next chunk are fetched before this one folds
+  // and converted after, so the shared-memory latency hides under the chain.
   {
-    // The accumulator is kept as an fp32 register that always holds an
-    // f16-representable value: r16(x) = f32(f16(x)) is the rounding the reference
-    // applies at every step.  A new running maximum (rare: ~ln T positions)
-    // rescales first; chunks of 8 positions without one take the short chain.
-    float vacc[2] = {0.0f, 0.0f};  // elements tid, tid + blockDim (D <= 512)
-    for (int t0 = 0; t0 < T; t0 += ATT_TILE) {
-      const int nt = min(ATT_TILE, T - t0);
-      ATTN_STAMP(9);
-      load_kv_tile(tile, a.vcache, t0, nt, pos, vnew, a.HK, hkv, D);
-      ATTN_STAMP(10);
+    const uint32_t e = threadIdx.x;
+    const bool active = e < D;
+    float v = 0.0f;
+    for (int jj = 0; jj < n_tv; ++jj) {
+      const int t0 = jj * RTV, nt = min(RTV, T - t0);
+      const int nc = nt - (jj == n_tv - 1 ? 1 : 0);  // rows that came from the cache
+      const __half* col = reinterpret_cast<const __half*>(tiles + size_t(cbuf) * ATT_TILE_BYTES) + e;
+      mbar_wait(&bars[cbuf], cpar);
+      if (jj == 0) ATTN_RAW(10, 0);
+      if (active) {
+        // chunk of up to 16 positions at rows r..r+15 (t0 + r is a multiple of 16): fetch, then fold
+        auto chunk = [&](int r, int rem, auto full) {
+          constexpr bool FULL = decltype(full)::value;
+          __half xr[16];
 #pragma unroll
-      for (int w = 0; w < 2; ++w) {
-        const uint32_t e = threadIdx.x + w * blockDim.x;
-        if (e < D) {
-          float v = vacc[w];
-          int r = 0;
-          for (; r + 8 <= nt; r += 8) {
-            float x8[8], e8[8];
-            uint32_t any = 0;
+          for (int k = 0; k < 16; ++k) xr[k] = col[(FULL ? r + k : min(r + k, nc - 1)) * D];
+          float e16[16];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              x8[j] = __half2float(tile[size_t(r + j) * D + e]);
-              e8[j] = se[t0 + r + j];
-              any |= nm[t0 + r + j];
+          for (int k = 0; k < 4; ++k) {
+            const float4 f = *reinterpret_cast<const float4*>(se + t0 + r + 4 * k);
+            e16[4 * k] = f.x; e16[4 * k + 1] = f.y; e16[4 * k + 2] = f.z; e16[4 * k + 3] = f.w;
+          }
+          const uint4 mk = *reinterpret_cast<const uint4*>(nm + t0 + r);
+          if ((mk.x | mk.y | mk.z | mk.w) == 0) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+              if (FULL || k < rem) v = r16(__fmaf_rn(__half2float(xr[k]), e16[k], v));
+          } else {
+            // a new running maximum in the chunk: v = f16(v * prev_score_exp) first (model.cpp:528-533);
+            // prev_score_exp is 1.0f elsewhere, which leaves the f16-valued v unchanged
+            float p16[16];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float4 f = *reinterpret_cast<const float4*>(pse + t0 + r + 4 * k);
+              p16[4 * k] = f.x; p16[4 * k + 1] = f.y; p16[4 * k + 2] = f.z; p16[4 * k + 3] = f.w;
             }
-            if (!any) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v = __half2float(__float2half_rn(__fmaf_rn(x8[j], e8[j], v)));
-            } else {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                if (nm[t0 + r + j]) v = __half2float(__float2half_rn(__fmul_rn(v, pse[t0 + r + j])));
-                v = __half2float(__float2half_rn(__fmaf_rn(x8[j], e8[j], v)));
+            for (int k = 0; k < 16; ++k) {
+              if (FULL || k < rem) {
+                v = r16(__fmul_rn(v, p16[k]));
+                v = r16(__fmaf_rn(__half2float(xr[k]), e16[k], v));
               }
             }
           }
-          for (; r < nt; ++r) {
-            if (nm[t0 + r]) v = __half2float(__float2half_rn(__fmul_rn(v, pse[t0 + r])));
-            v = __half2float(__float2half_rn(__fmaf_rn(__half2float(tile[size_t(r) * D + e]), se[t0 + r], v)));
-          }
-          vacc[w] = v;
-        }
+        };
+        int r = 0;
+        for (; r + 16 <= nc; r += 16) chunk(r, 16, std::true_type{});
+        if (r < nc) chunk(r, nc - r, std::false_type{});
       }
-      __syncthreads();  // tile is reused
+      if (jj == 0) ATTN_RAW(11, 0);
+      tile_done();
+      if (jj == 0) ATTN_RAW(12, 0);
     }
-#pragma unroll
-    for (int w = 0; w < 2; ++w) {
-      const uint32_t e = threadIdx.x + w * blockDim.x;
-      if (e < D) qh[e] = vacc[w];  // q no longer needed
+    if (active) {  // the current token's own row
+      if (nm[pos]) v = r16(__fmul_rn(v, pse[pos]));
+      v = r16(__fmaf_rn(__half2float(vnew[e]), se[pos], v));
+      qh[e] = v;
     }
   }
   ATTN_STAMP(5);
   __syncthreads();
-  for (uint32_t e = threadIdx.x; e < D; e += blockDim.x) {
-    const float o = __fmul_rn(qh[e], s_inv);
-    qh[e] = o;
-    a.out[h * D + e] = o;
+  if (threadIdx.x < D) {
+    const float o = __fmul_rn(qh[threadIdx.x], s_inv);
+    qh[threadIdx.x] = o;
+    a.out[h * D + threadIdx.x] = o;
   }
   ATTN_STAMP(6);
   // Fused quantizer of the attn_output mat-vec: this head's D outputs are whole
@@ -528,11 +636,13 @@ __global__ void __launch_bounds__(1024) attention_kernel(AttnArgs a) {
   if (a.act_kind == ACT_Q8_0) {
     for (uint32_t b = warp; b < D / 32; b += nw) warp_quantize_q8_0(qh[b * 32 + lane], h * (D / 32) + b, n, a.act_buf, lane);
   } else if (a.act_kind == ACT_Q8_K) {
-    for (uint32_t sb = warp; sb < D / 256; sb += nw) {
-      float v[8];
+    if constexpr (D >= 256) {
+      for (uint32_t sb = warp; sb < uint32_t(D / 256); sb += nw) {
+        float v[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = qh[sb * 256 + lane * 8 + j];
-      warp_quantize_q8_k(v, h * (D / 256) + sb, n, a.act_buf, lane);
+        for (int j = 0; j < 8; ++j) v[j] = qh[sb * 256 + lane * 8 + j];
+        warp_quantize_q8_k(v, h * (D / 256) + sb, n, a.act_buf, lane);
+      }
     }
   } else if (a.act_kind == ACT_F16) {
     for (uint32_t e = threadIdx.x; e < D; e += blockDim.x) reinterpret_cast<uint16_t*>(a.act_buf)[h * D + e] = f2h(qh[e]);
@@ -638,17 +748,53 @@ cudaError_t llmi_launch_rope_table(float2* table, uint32_t t_max, uint32_t D, fl
   return cudaGetLastError();
 }
 
+// Dynamic shared memory of the attention kernel: the per-position arrays plus as
+// many K/V tiles (2..ATT_MAX_BUF) as fit next to them.  0 = t_max too large.
+static size_t attention_fixed_smem(uint32_t t_max, uint32_t D) {
+  const size_t tp = (t_max + 15) & ~15u;
+  return tp * (8 + 4 + 4 + 1) + size_t(D) * (4 + 4 + 4 + 2);
+}
+
+static uint32_t attention_nbuf(uint32_t t_max, uint32_t D) {
+  const size_t fixed = attention_fixed_smem(t_max, D);
+  const size_t room = 232448 - 1024;  // 227 KB per CTA minus the static part
+  if (fixed + 2 * size_t(ATT_TILE_BYTES) > room) return 0;
+  const size_t n = (room - fixed) / ATT_TILE_BYTES;
+  return uint32_t(n > ATT_MAX_BUF ? ATT_MAX_BUF : n);
+}
+
 size_t llmi_attention_smem(uint32_t t_max, uint32_t D) {
-  return size_t(t_max) * (8 + 4 + 4 + 1) + size_t(D) * 8 + size_t(128) * D * 2 + 16;  // + one K/V tile
+  const uint32_t nbuf = attention_nbuf(t_max, D);
+  return nbuf ? attention_fixed_smem(t_max, D) + size_t(nbuf) * ATT_TILE_BYTES : 0;
+}
+
+template <int D>
+static cudaError_t attention_set_smem(size_t smem) {
+  return cudaFuncSetAttribute(attention_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
 }
 
 cudaError_t llmi_attention_init(uint32_t t_max, uint32_t D) {
-  return cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              int(llmi_attention_smem(t_max, D)));
+  const size_t smem = llmi_attention_smem(t_max, D);
+  if (!smem) return cudaErrorInvalidValue;
+  switch (D) {
+    case 64: return attention_set_smem<64>(smem);
+    case 128: return attention_set_smem<128>(smem);
+    case 256: return attention_set_smem<256>(smem);
+    case 512: return attention_set_smem<512>(smem);
+    default: return cudaErrorInvalidValue;
+  }
 }
 
 cudaError_t llmi_launch_attention(const AttnArgs& a, cudaStream_t s) {
-  return llmi_launch(attention_kernel, dim3(a.H), dim3(1024), llmi_attention_smem(a.t_max, a.D), s, a);
+  const size_t smem = llmi_attention_smem(a.t_max, a.D);
+  const uint32_t nbuf = attention_nbuf(a.t_max, a.D);
+  switch (a.D) {
+    case 64: return llmi_launch(attention_kernel<64>, dim3(a.H), dim3(1024), smem, s, a, nbuf);
+    case 128: return llmi_launch(attention_kernel<128>, dim3(a.H), dim3(1024), smem, s, a, nbuf);
+    case 256: return llmi_launch(attention_kernel<256>, dim3(a.H), dim3(1024), smem, s, a, nbuf);
+    case 512: return llmi_launch(attention_kernel<512>, dim3(a.H), dim3(1024), smem, s, a, nbuf);
+    default: return cudaErrorInvalidValue;
+  }
 }
 
 cudaError_t llmi_launch_geglu_act(const float* gate, const float* up, uint32_t n, int kind, uint8_t* buf,

@@ -32,7 +32,8 @@ struct NormArgs {
 struct AttnArgs {
   const float *q, *k, *v;          // raw outputs of the q/k/v mat-vecs: [H*D], [HK*D], [HK*D]
   const float *wq_norm, *wk_norm;  // [D]
-  __half *kcache, *vcache;         // this layer's [t_max][HK][D]; row `pos` is appended
+  uint32_t* kcache;                // this layer's keys [HK][t_max][D]: high word of double(f16 value) per element
+  __half* vcache;                  // this layer's values [HK][t_max][D] (f16); row `pos` of every head is appended
   uint32_t H, HK, D, t_max;
   double eps;
   float attn_scale;

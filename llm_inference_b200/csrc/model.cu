@@ -45,7 +45,8 @@ struct llmi_model_s {
   float *h = nullptr, *xn = nullptr, *q = nullptr, *k = nullptr, *v = nullptr, *q_rot = nullptr, *attn = nullptr,
         *attn_out = nullptr, *gate = nullptr, *up = nullptr, *ffn_out = nullptr, *logits = nullptr;
   ActSet act_E, act_HD, act_F;
-  __half *kcache = nullptr, *vcache = nullptr;
+  uint32_t* kcache = nullptr;  // [L][HK][t_max][D] keys as double high words (glue.cu attention_kernel)
+  __half* vcache = nullptr;    // [L][HK][t_max][D] values, f16
   int32_t *d_tok = nullptr, *d_pos = nullptr, *d_gen = nullptr, *d_gen_count = nullptr, *d_toks = nullptr;
   unsigned long long* d_key = nullptr;  // running argmax key of the logits mat-vec epilogue
   float2 *rope_swa = nullptr, *rope_global = nullptr;  // [t_max][D/2] (cos, sin) per rope base
@@ -339,7 +340,7 @@ int load_impl(llmi_model_s* m, const uint8_t* image, uint64_t size, uint32_t t_m
   M_RC(dev_alloc(m, (void**)&m->ffn_out, E * 4));
   M_RC(dev_alloc(m, (void**)&m->logits, size_t(m->V) * 4));
   const size_t kv_elems = size_t(m->L) * t_max * KD;
-  M_RC(dev_alloc(m, (void**)&m->kcache, kv_elems * 2));
+  M_RC(dev_alloc(m, (void**)&m->kcache, kv_elems * 4));
   M_RC(dev_alloc(m, (void**)&m->vcache, kv_elems * 2));
   M_RC(dev_alloc(m, (void**)&m->d_tok, 16));
   M_RC(dev_alloc(m, (void**)&m->d_pos, 16));

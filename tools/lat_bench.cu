@@ -12,8 +12,8 @@ __device__ __forceinline__ float r16_alu(float x) {
 }
 template <int MODE>
 __global__ void chain(float* out, const float* in, int n, long long* cyc) {
-  float v = in[threadIdx.x], x = in[32 + threadIdx.x], e = in[64 + threadIdx.x];
-  double d = in[96 + threadIdx.x];
+  float v = in[threadIdx.x & 31], x = in[32 + (threadIdx.x & 31)], e = in[64 + (threadIdx.x & 31)];
+  double d = in[96 + (threadIdx.x & 31)];
   const long long t0 = clock64();
   for (int i = 0; i < n; ++i) {
     if (MODE == 0) v = r16_cvt(__fmaf_rn(x, e, v));
@@ -21,9 +21,12 @@ __global__ void chain(float* out, const float* in, int n, long long* cyc) {
     if (MODE == 2) v = __fmaf_rn(x, e, v);
     if (MODE == 3) d += double(__fmul_rn(x, v));
     if (MODE == 4) d = __dadd_rn(d, 1.0000001);
+    if (MODE == 5) { v = __fmul_rn(v, x); d += double(v); }             // fmul + F2F.F64.F32 + dadd, not hoistable
+    if (MODE == 6) d = __fma_rn(d, 1.0000001, double(e));                // dfma chain
+    if (MODE == 7) { v = __fmul_rn(v, x); e += __half2float(__float2half_rn(v)); }  // F2FP + HADD2 off the critical chain
   }
   const long long t1 = clock64();
-  out[threadIdx.x] = v + float(d);
+  out[threadIdx.x] = v + float(d) + e;
   if (threadIdx.x == 0) cyc[0] = t1 - t0;
 }
 __global__ void check_r16(unsigned long long* bad) {
@@ -36,7 +39,7 @@ __global__ void check_r16(unsigned long long* bad) {
 }
 int main() {
   float *in, *out; long long* cyc; unsigned long long* bad;
-  cudaMalloc(&in, 1024); cudaMalloc(&out, 1024); cudaMalloc(&cyc, 8); cudaMalloc(&bad, 8);
+  cudaMalloc(&in, 1024); cudaMalloc(&out, 4096); cudaMalloc(&cyc, 8); cudaMalloc(&bad, 8);
   float h[256]; for (int i = 0; i < 256; ++i) h[i] = 0.001f * (i % 7 + 1);
   cudaMemcpy(in, h, 1024, cudaMemcpyHostToDevice); cudaMemset(bad, 0, 8);
   const int n = 4096; long long c;
@@ -51,11 +54,16 @@ int main() {
     cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
     printf("%-40s %.1f cycles/step (1 warp)\n", names[m], double(c) / n);
   }
-  // throughput of the FP64 path with a full SM: 32 warps
-  for (int m = 3; m < 5; ++m) {
-    if (m == 3) chain<3><<<1, 1024>>>(out, in, n, cyc); else chain<4><<<1, 1024>>>(out, in, n, cyc);
-    cudaDeviceSynchronize(); cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
-    printf("%-40s %.1f cycles/step (32 warps on one SM)\n", names[m], double(c) / n);
+  // throughput with 8 and 32 warps on one SM
+  const char* n2[] = {"fma + F2FP + HADD2 chain", "", "fma only", "", "dadd only", "fmul + F2F.F64.F32 + dadd", "dfma chain", "fmul; F2FP+HADD2+fadd"};
+  for (int m : {0, 2, 4, 5, 6, 7}) {
+    for (int th : {32, 256, 1024}) {
+      if (m == 0) chain<0><<<1, th>>>(out, in, n, cyc); if (m == 2) chain<2><<<1, th>>>(out, in, n, cyc);
+      if (m == 4) chain<4><<<1, th>>>(out, in, n, cyc); if (m == 5) chain<5><<<1, th>>>(out, in, n, cyc);
+      if (m == 6) chain<6><<<1, th>>>(out, in, n, cyc); if (m == 7) chain<7><<<1, th>>>(out, in, n, cyc);
+      cudaDeviceSynchronize(); cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
+      printf("%-32s %6.1f cycles/step (%d warps on one SM)\n", n2[m], double(c) / n, th / 32);
+    }
   }
   check_r16<<<148 * 8, 256>>>(bad); cudaDeviceSynchronize();
   unsigned long long nb; cudaMemcpy(&nb, bad, 8, cudaMemcpyDeviceToHost);
