@@ -165,9 +165,14 @@ int llmi_model_free(llmi_model_t m);
 /* dims[8] = {n_layer, n_embd, n_ff, n_head, n_head_kv, head_dim, vocab, max_positions} */
 int llmi_model_info(llmi_model_t m, uint32_t* dims, uint64_t* weight_bytes);
 /* Model::forward(tokens, pos) (model.h:91, model.cpp:706-1048): host token ids
- * in, host logits of the last token out; activations and KV stay on the device;
- * prefill is the reference's per-token loop.  Synchronous. */
+ * in, host logits of the last token out; activations and KV stay on the device.
+ * A prompt (n_tokens > 1) goes through each layer in batches of up to 64 tokens
+ * (env LLMI_PREFILL_BATCH) — the reference's layer-major loop with the tokens
+ * inside — with bit-identical results to feeding the tokens one by one
+ * (LLMI_NO_PREFILL=1 forces that).  Synchronous. */
 int llmi_model_forward(llmi_model_t m, const int32_t* tokens, int n_tokens, int pos, float* logits_host);
+/* CUDA-event time and kernel launches of the last llmi_model_forward (either pointer may be NULL) */
+int llmi_model_last_forward_stats(llmi_model_t m, float* ms_device, int* launches);
 /* Greedy generation loop of main.cpp:172-221 entirely on the device (argmax of
  * step i feeds step i+1; one CUDA graph launch per token): consumes first_token
  * at position pos, returns n_steps token ids and the CUDA-event time. */

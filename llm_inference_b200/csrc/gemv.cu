@@ -66,6 +66,8 @@ struct GemvArgs {
   unsigned long long* argmax_key;
   float softcap;
   uint32_t row0;  // global index of this handle's first row
+  // token-batched launches (prefill): n_tok activation buffers act_stride bytes apart, outputs out_stride floats apart
+  uint32_t n_tok, act_stride, out_stride;
 };
 
 // ------------------------------------------------ integer block dot products
@@ -516,6 +518,74 @@ __global__ void __launch_bounds__(W * 32) gemv_slab_kernel(const GemvBatch batch
   }
 }
 
+// ------------------------------------------------------ token-batched (prefill)
+// The same work decomposition for M tokens at once: a warp loads the weights
+// of its item ONCE and folds them against the activations of MT tokens staged
+// in shared memory (one bulk copy per token tile: the M activation buffers are
+// contiguous).  Per (token, row) the arithmetic and the summation order are
+// exactly those of gemv_slab_kernel, so a prompt processed in batches gives the
+// bits the token-by-token path gives.  Weights are re-read once per token tile
+// (from L2 when a layer fits).
+template <class B, int W>
+__global__ void __launch_bounds__(W * 32) gemv_slab_tok_kernel(const GemvBatch batch, const uint32_t MT) {
+  extern __shared__ __align__(128) uint8_t sm_act[];  // [MT][act_stride] then [MT][S * chunks * 8 floats]
+  __shared__ __align__(8) uint64_t bar;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = lane & 7, sub = lane >> 3;
+  int mi = 0;
+  while (mi + 1 < batch.n && blockIdx.x >= batch.cta_end[mi]) ++mi;
+  const GemvArgs& a = batch.a[mi];
+  const uint32_t S = batch.S[mi];
+  const uint32_t cta = blockIdx.x - (mi ? batch.cta_end[mi - 1] : 0u);
+  pdl_trigger();
+  if (threadIdx.x == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  constexpr int N = B::C;
+  const uint32_t J = a.chunks;
+  const uint32_t slab0 = cta * S;
+  const uint32_t n_sl = min(S, a.n_slabs - slab0);
+  const uint32_t n_items = n_sl * J;
+  float* part = reinterpret_cast<float*>(sm_act + size_t(MT) * a.act_stride);
+  uint32_t parity = 0;
+  pdl_wait();
+  for (uint32_t m0 = 0; m0 < a.n_tok; m0 += MT) {
+    const uint32_t mt = min(MT, a.n_tok - m0);
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(&bar, mt * a.act_stride);
+      bulk_g2s(sm_act, a.act + size_t(m0) * a.act_stride, mt * a.act_stride, &bar);
+    }
+    bool waited = false;
+#pragma unroll 1
+    for (uint32_t t = warp; t < n_items; t += W) {
+      const uint32_t sl = t / J, j = t - sl * J;
+      FragSet<B, N> f;
+      load_item<B, N>(f, a, slab0 + sl, j, r, sub);
+      if (!waited) {
+        mbar_wait(&bar, parity);
+        waited = true;
+      }
+#pragma unroll 1
+      for (uint32_t m = 0; m < mt; ++m) {
+        const float v = compute_item<B, N>(f, a, sm_act + size_t(m) * a.act_stride, j, sub);
+        if (lane < LLMI_SLAB) part[(size_t(m) * n_items + t) * LLMI_SLAB + lane] = v;
+      }
+    }
+    if (!waited) mbar_wait(&bar, parity);
+    parity ^= 1;
+    __syncthreads();
+    for (uint32_t idx = threadIdx.x; idx < mt * n_sl * LLMI_SLAB; idx += W * 32) {
+      const uint32_t m = idx / (n_sl * LLMI_SLAB), rem = idx - m * (n_sl * LLMI_SLAB);
+      const uint32_t sl = rem / LLMI_SLAB, rr = rem % LLMI_SLAB;
+      const float* p = part + (size_t(m) * n_items + size_t(sl) * J) * LLMI_SLAB + rr;
+      float sum = p[0];
+      for (uint32_t j = 1; j < J; ++j) sum += p[j * LLMI_SLAB];  // canonical order
+      const uint32_t row = (slab0 + sl) * LLMI_SLAB + rr;
+      if (row < a.n_local) a.out[size_t(m0 + m) * a.out_stride + row] = sum;
+    }
+    __syncthreads();  // the tile and the partials are reused
+  }
+}
+
 // --------------------------------------------------------------- debug dump
 // One thread per (local row, block): recomputes the integer block dot with the
 // same device functions and planes as the GEMV.
@@ -629,6 +699,50 @@ cudaError_t launch_batch(const GemvArgs* args, int n, cudaStream_t s) {
   }
 }
 
+constexpr size_t TOK_TILE_BYTES = 64 * 1024;  // activations of one token tile in shared memory
+constexpr int TOK_MAX_TILE = 8;
+
+template <class B>
+cudaError_t launch_tokens(const GemvArgs* args, int n, cudaStream_t s) {
+  GemvBatch b;
+  b.n = n;
+  uint64_t slabs = 0;
+  for (int i = 0; i < n; ++i) slabs += args[i].n_slabs;
+  int W = 4;
+  uint32_t ctas = 0, MT = TOK_MAX_TILE;
+  for (int i = 0; i < n; ++i) {
+    const uint32_t fit = uint32_t(TOK_TILE_BYTES / args[i].act_stride);
+    if (fit < MT) MT = fit;
+  }
+  if (MT == 0) return cudaErrorInvalidValue;
+  if (MT > args[0].n_tok) MT = args[0].n_tok;
+  size_t smem = 0;
+  for (int i = 0; i < n; ++i) {
+    int wi;
+    uint32_t si;
+    pick_shape<B>(args[i], slabs, wi, si);
+    if (wi > W) W = wi;
+    b.a[i] = args[i];
+    b.S[i] = si;
+    ctas += (args[i].n_slabs + si - 1) / si;
+    b.cta_end[i] = ctas;
+    const size_t need = size_t(MT) * (args[i].act_stride + size_t(si) * args[i].chunks * LLMI_SLAB * 4);
+    if (need > smem) smem = need;
+  }
+  for (int i = n; i < GEMV_MAX_BATCH; ++i) {
+    b.a[i] = args[0];
+    b.S[i] = 1;
+    b.cta_end[i] = ctas;
+  }
+  if (ctas == 0) return cudaSuccess;
+  if (smem > size_t(MAX_DYN_SMEM)) return cudaErrorInvalidValue;
+  switch (W) {
+    case 4: return llmi_launch(gemv_slab_tok_kernel<B, 4>, dim3(ctas), dim3(128), smem, s, b, MT);
+    case 8: return llmi_launch(gemv_slab_tok_kernel<B, 8>, dim3(ctas), dim3(256), smem, s, b, MT);
+    default: return llmi_launch(gemv_slab_tok_kernel<B, 16>, dim3(ctas), dim3(512), smem, s, b, MT);
+  }
+}
+
 template <class B>
 cudaError_t optin() {
   cudaError_t e;
@@ -636,7 +750,13 @@ cudaError_t optin() {
                                 MAX_DYN_SMEM)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(gemv_slab_kernel<B, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 MAX_DYN_SMEM)) != cudaSuccess) return e;
-  return cudaFuncSetAttribute(gemv_slab_kernel<B, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
+  if ((e = cudaFuncSetAttribute(gemv_slab_kernel<B, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                MAX_DYN_SMEM)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(gemv_slab_tok_kernel<B, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                MAX_DYN_SMEM)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(gemv_slab_tok_kernel<B, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                MAX_DYN_SMEM)) != cudaSuccess) return e;
+  return cudaFuncSetAttribute(gemv_slab_tok_kernel<B, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
 }
 
 uint32_t units_of(const llmi_weight_s& w) {
@@ -702,6 +822,9 @@ static GemvArgs make_args(const llmi_weight_s& w, const llmi_act_s& a, float* ou
   g.argmax_key = nullptr;
   g.softcap = 0.0f;
   g.row0 = uint32_t(w.row_begin);
+  g.n_tok = 1;
+  g.act_stride = g.act_bytes;
+  g.out_stride = 0;
   return g;
 }
 
@@ -734,6 +857,39 @@ cudaError_t llmi_launch_gemv_batch(const llmi_weight_s* const* ws, float* const*
     case LLMI_Q6_K: return launch_batch<Q6_K>(args, m, s);
     case LLMI_F16: return launch_batch<F16>(args, m, s);
     case LLMI_BF16: return launch_batch<BF16>(args, m, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// Token-batched form (prefill): `n_tok` activations of kind/length (act_kind, act_n), act_bytes() apart
+// starting at act_base; matrix i writes token m's rows to outs[i] + m * out_strides[i].
+cudaError_t llmi_launch_gemv_tokens(const llmi_weight_s* const* ws, float* const* outs, const uint32_t* out_strides,
+                                    int n, int act_kind, uint64_t act_n, const uint8_t* act_base, uint32_t n_tok,
+                                    cudaStream_t s) {
+  if (n < 1 || n > GEMV_MAX_BATCH || n_tok == 0) return cudaErrorInvalidValue;
+  llmi_act_s a;
+  a.kind = act_kind;
+  a.n = act_n;
+  a.buf = const_cast<uint8_t*>(act_base);
+  GemvArgs args[GEMV_MAX_BATCH];
+  int m = 0;
+  for (int i = 0; i < n; ++i) {
+    if (ws[i]->type != ws[0]->type) return cudaErrorInvalidValue;
+    if (ws[i]->n_slabs == 0) continue;
+    args[m] = make_args(*ws[i], a, outs[i]);
+    args[m].n_tok = n_tok;
+    args[m].out_stride = out_strides[i];
+    ++m;
+  }
+  if (m == 0) return cudaSuccess;
+  switch (ws[0]->type) {
+    case LLMI_Q4_0: return launch_tokens<Q4_0>(args, m, s);
+    case LLMI_Q8_0: return launch_tokens<Q8_0>(args, m, s);
+    case LLMI_Q5_0: return launch_tokens<Q5_0>(args, m, s);
+    case LLMI_Q4_K: return launch_tokens<Q4_K>(args, m, s);
+    case LLMI_Q6_K: return launch_tokens<Q6_K>(args, m, s);
+    case LLMI_F16: return launch_tokens<F16>(args, m, s);
+    case LLMI_BF16: return launch_tokens<BF16>(args, m, s);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -70,9 +70,9 @@ __device__ float dequant_elem(const EmbedArgs& a, uint32_t row, uint32_t e) {
 __global__ void embed_kernel(EmbedArgs a, const int32_t* __restrict__ token, float scale, float* __restrict__ h) {
   pdl_trigger();
   pdl_wait();
-  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x, m = blockIdx.y;  // m: token of a prefill batch
   if (e >= a.n_cols) return;
-  h[e] = dequant_elem(a, uint32_t(*token), e) * scale;
+  h[size_t(m) * a.n_cols + e] = dequant_elem(a, uint32_t(token[m]), e) * scale;
 }
 
 // ----------------------------------------------------------------- reductions
@@ -135,6 +135,13 @@ __global__ void __launch_bounds__(1024) norm_act_kernel(NormArgs a) {
   extern __shared__ float xs[];  // n floats
   __shared__ float red[32];
   const uint32_t n = a.n;
+  {  // one CTA per token of a prefill batch (a single CTA when decoding)
+    const size_t off = size_t(blockIdx.x) * n;
+    if (a.y) a.y += off;
+    a.h += off;
+    if (a.xn_out) a.xn_out += off;
+    if (a.act_buf) a.act_buf += size_t(blockIdx.x) * a.act_stride;
+  }
   float yv[NORM_PER], hv[NORM_PER], wp[NORM_PER], wn[NORM_PER];
 #pragma unroll
   for (int k = 0; k < NORM_PER; ++k) {  // norm weights are static: fetch them under the predecessor's tail
@@ -151,7 +158,7 @@ __global__ void __launch_bounds__(1024) norm_act_kernel(NormArgs a) {
     hv[k] = ok ? a.h[i] : 0.0f;
     yv[k] = (ok && a.y) ? a.y[i] : 0.0f;
   }
-  if (a.pos_inc && threadIdx.x == 0) *a.pos_inc += 1;
+  if (a.pos_inc && threadIdx.x == 0 && blockIdx.x == 0) *a.pos_inc += int32_t(gridDim.x);
   if (a.y) {
     float ss = 0.0f;
 #pragma unroll
@@ -274,7 +281,11 @@ __device__ __forceinline__ float r16(float x) { return __half2float(__float2half
 // loop (F2F.F64.F32 runs at 16 lanes/clk/SM and would bound the phase).
 __device__ __forceinline__ uint32_t f16_as_double_hi(__half h) { return uint32_t(__double2hiint(double(__half2float(h)))); }
 
-template <int D>
+// MODE 0: decode — prologue (q/k norm, RoPE, KV append) and attention for one token in one kernel.
+// Prefill processes a batch of tokens (blockIdx.y) in two kernels, because a token attends to rows the
+// other CTAs of the batch append:  MODE 1 = prologue only (appends K/V, leaves f16(q) as double high
+// words in a.qbuf);  MODE 2 = attention only (q from a.qbuf, every row — its own included — from the cache).
+template <int D, int MODE>
 __global__ void __launch_bounds__(1024) attention_kernel(AttnArgs a, uint32_t nbuf) {
   pdl_trigger();
   constexpr int HALF = D / 2, VEC = D / 32;           // elements per lane in phase 1
@@ -312,7 +323,15 @@ __global__ void __launch_bounds__(1024) attention_kernel(AttnArgs a, uint32_t nb
     for (uint32_t b = 0; b < nbuf; ++b) mbar_init(&bars[b], 1);
   ATTN_STAMP(0);
   pdl_wait();
-  const int pos = *a.pos, T = pos + 1;
+  const uint32_t tok = blockIdx.y;  // token of a prefill batch (0 when decoding)
+  const int pos = *a.pos + int(tok), T = pos + 1;
+  a.q += size_t(tok) * a.H * D;
+  a.k += size_t(tok) * a.HK * D;
+  a.v += size_t(tok) * a.HK * D;
+  a.out += size_t(tok) * a.H * D;
+  if (a.act_buf) a.act_buf += size_t(tok) * a.act_stride;
+  uint32_t* qglob = a.qbuf ? a.qbuf + (size_t(tok) * a.H + h) * D : nullptr;
+  constexpr int OWN = MODE == 0 ? 1 : 0;  // the token's own K/V row comes from shared memory, not from the cache
   // The tile stream: K tiles 0..n_tk-1, then V tiles 0..n_tv-1, through the ring.
   // Rows of one KV head are contiguous ([HK][t_max][D]): one bulk copy per tile.
   // Row `pos` (always the last row of the last tile) is not in the cache yet: it
@@ -322,16 +341,16 @@ __global__ void __launch_bounds__(1024) attention_kernel(AttnArgs a, uint32_t nb
     uint64_t* bar = &bars[buf];
     uint8_t* dst = tiles + size_t(buf) * ATT_TILE_BYTES;
     if (j < n_tk) {
-      const int t0 = j * RTK, n_cached = min(RTK, T - t0) - (j == n_tk - 1 ? 1 : 0);
+      const int t0 = j * RTK, n_cached = min(RTK, T - t0) - (j == n_tk - 1 ? OWN : 0);
       mbar_expect_tx(bar, uint32_t(n_cached) * D * 4);
       if (n_cached) bulk_g2s(dst, a.kcache + (size_t(hkv) * a.t_max + t0) * D, uint32_t(n_cached) * D * 4, bar);
     } else {
-      const int jj = j - n_tk, t0 = jj * RTV, n_cached = min(RTV, T - t0) - (jj == n_tv - 1 ? 1 : 0);
+      const int jj = j - n_tk, t0 = jj * RTV, n_cached = min(RTV, T - t0) - (jj == n_tv - 1 ? OWN : 0);
       mbar_expect_tx(bar, uint32_t(n_cached) * D * 2);
       if (n_cached) bulk_g2s(dst, a.vcache + (size_t(hkv) * a.t_max + t0) * D, uint32_t(n_cached) * D * 2, bar);
     }
   };
-  if (threadIdx.x == 0)
+  if (MODE != 1 && threadIdx.x == 0)
     for (int j = 0; j < min(int(nbuf), n_stream); ++j) issue_tile(j, j);
   int cbuf = 0;          // ring position of the tile being consumed
   uint32_t cpar = 0;     // its mbarrier phase parity
@@ -345,6 +364,9 @@ __global__ void __launch_bounds__(1024) attention_kernel(AttnArgs a, uint32_t nb
       cpar ^= 1;
     }
   };
+  if (MODE == 2) {  // q was normalized, rotated and rounded by the MODE 1 kernel
+    for (uint32_t e = threadIdx.x; e < D; e += blockDim.x) qhi[e] = qglob[e];
+  } else {
   float q0 = 0.0f, q1 = 0.0f, k0 = 0.0f, k1 = 0.0f, v0 = 0.0f, v1 = 0.0f;
   float2 csn = make_float2(1.0f, 0.0f);
   if (pair) {
@@ -388,16 +410,25 @@ __global__ void __launch_bounds__(1024) attention_kernel(AttnArgs a, uint32_t nb
     const float cs = csn.x, sn = csn.y;
     const float qa = __fmul_rn(__fmaf_rn(q0, cs, -__fmul_rn(q1, sn)), a.attn_scale);
     const float qb = __fmul_rn(__fmaf_rn(q0, sn, __fmul_rn(q1, cs)), a.attn_scale);
-    qhi[i] = f16_as_double_hi(__float2half_rn(qa));  // Q is rounded to f16 for the scores (model.cpp:506)
-    qhi[i + HALF] = f16_as_double_hi(__float2half_rn(qb));
+    const uint32_t qah = f16_as_double_hi(__float2half_rn(qa));  // Q is rounded to f16 for the scores (model.cpp:506)
+    const uint32_t qbh = f16_as_double_hi(__float2half_rn(qb));
+    if (MODE == 1) {
+      qglob[i] = qah;
+      qglob[i + HALF] = qbh;
+    } else {
+      qhi[i] = qah;
+      qhi[i + HALF] = qbh;
+    }
     const __half ka = __float2half_rn(__fmaf_rn(k0, cs, -__fmul_rn(k1, sn)));
     const __half kb = __float2half_rn(__fmaf_rn(k0, sn, __fmul_rn(k1, cs)));
     const __half va = __float2half_rn(v0), vb = __float2half_rn(v1);
     const uint32_t kah = f16_as_double_hi(ka), kbh = f16_as_double_hi(kb);
-    knew[i] = kah;
-    knew[i + HALF] = kbh;
-    vnew[i] = va;
-    vnew[i + HALF] = vb;
+    if (MODE == 0) {
+      knew[i] = kah;
+      knew[i + HALF] = kbh;
+      vnew[i] = va;
+      vnew[i + HALF] = vb;
+    }
     if (h % group == 0) {  // one writer per KV head
       uint32_t* kd = a.kcache + (size_t(hkv) * a.t_max + pos) * D;
       __half* vd = a.vcache + (size_t(hkv) * a.t_max + pos) * D;
@@ -406,6 +437,8 @@ __global__ void __launch_bounds__(1024) attention_kernel(AttnArgs a, uint32_t nb
       vd[i] = va;
       vd[i + HALF] = vb;
     }
+  }
+  if (MODE == 1) return;
   }
   __syncthreads();
   ATTN_STAMP(2);
@@ -462,7 +495,8 @@ __global__ void __launch_bounds__(1024) attention_kernel(AttnArgs a, uint32_t nb
           const int rr = min(r + p, nt - 1);
           int slot = cbuf + rr / RTK;
           if (slot >= int(nbuf)) slot -= int(nbuf);
-          s[p] = lane_dot(t0 + rr == pos ? knew : tiles32 + size_t(slot) * (ATT_TILE_BYTES / 4) + size_t(rr % RTK) * D);
+          s[p] = lane_dot(OWN && t0 + rr == pos ? knew
+                                                : tiles32 + size_t(slot) * (ATT_TILE_BYTES / 4) + size_t(rr % RTK) * D);
         }
 #pragma unroll
         for (int o = 16; o; o >>= 1)
@@ -566,7 +600,7 @@ __global__ void __launch_bounds__(1024) attention_kernel(AttnArgs a, uint32_t nb
     float v = 0.0f;
     for (int jj = 0; jj < n_tv; ++jj) {
       const int t0 = jj * RTV, nt = min(RTV, T - t0);
-      const int nc = nt - (jj == n_tv - 1 ? 1 : 0);  // rows that came from the cache
+      const int nc = nt - (jj == n_tv - 1 ? OWN : 0);  // rows that came from the cache
       const __half* col = reinterpret_cast<const __half*>(tiles + size_t(cbuf) * ATT_TILE_BYTES) + e;
       mbar_wait(&bars[cbuf], cpar);
       if (jj == 0) ATTN_RAW(10, 0);
@@ -614,9 +648,11 @@ __global__ void __launch_bounds__(1024) attention_kernel(AttnArgs a, uint32_t nb
       tile_done();
       if (jj == 0) ATTN_RAW(12, 0);
     }
-    if (active) {  // the current token's own row
-      if (nm[pos]) v = r16(__fmul_rn(v, pse[pos]));
-      v = r16(__fmaf_rn(__half2float(vnew[e]), se[pos], v));
+    if (active) {
+      if (OWN) {  // the current token's own row
+        if (nm[pos]) v = r16(__fmul_rn(v, pse[pos]));
+        v = r16(__fmaf_rn(__half2float(vnew[e]), se[pos], v));
+      }
       qh[e] = v;
     }
   }
@@ -663,9 +699,13 @@ __device__ __forceinline__ float geglu(float x, float up) {
 }
 
 __global__ void geglu_act_kernel(const float* __restrict__ gate, const float* __restrict__ up, uint32_t n, int kind,
-                                 uint8_t* buf, float* hidden_out) {
+                                 uint8_t* buf, float* hidden_out, uint32_t act_stride) {
   pdl_trigger();
   pdl_wait();
+  gate += size_t(blockIdx.y) * n;  // blockIdx.y: token of a prefill batch
+  up += size_t(blockIdx.y) * n;
+  buf += size_t(blockIdx.y) * act_stride;
+  if (hidden_out) hidden_out += size_t(blockIdx.y) * n;
   const int lane = threadIdx.x & 31;
   const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
   if (kind == ACT_Q8_0) {
@@ -727,13 +767,14 @@ __global__ void softcap_kernel(float* logits, uint32_t n, float softcap) {
 
 // ------------------------------------------------------------------ launchers
 
-cudaError_t llmi_launch_embed(const EmbedArgs& a, const int32_t* token, float scale, float* h, cudaStream_t s) {
-  return llmi_launch(embed_kernel, dim3((a.n_cols + 255) / 256), dim3(256), 0, s, a, token, scale, h);
+cudaError_t llmi_launch_embed(const EmbedArgs& a, const int32_t* token, float scale, float* h, cudaStream_t s,
+                              uint32_t n_tok) {
+  return llmi_launch(embed_kernel, dim3((a.n_cols + 255) / 256, n_tok), dim3(256), 0, s, a, token, scale, h);
 }
 
 cudaError_t llmi_launch_norm_act(const NormArgs& a, cudaStream_t s) {
   const int threads = a.n >= 2048 ? 1024 : 512;
-  return llmi_launch(norm_act_kernel, dim3(1), dim3(threads), a.n * sizeof(float), s, a);
+  return llmi_launch(norm_act_kernel, dim3(a.n_tok ? a.n_tok : 1), dim3(threads), a.n * sizeof(float), s, a);
 }
 
 cudaError_t llmi_launch_act(const float* x, uint32_t n, int kind, uint8_t* buf, cudaStream_t s) {
@@ -770,7 +811,9 @@ size_t llmi_attention_smem(uint32_t t_max, uint32_t D) {
 
 template <int D>
 static cudaError_t attention_set_smem(size_t smem) {
-  return cudaFuncSetAttribute(attention_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  cudaError_t e = cudaFuncSetAttribute(attention_kernel<D, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(attention_kernel<D, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
 }
 
 cudaError_t llmi_attention_init(uint32_t t_max, uint32_t D) {
@@ -785,23 +828,34 @@ cudaError_t llmi_attention_init(uint32_t t_max, uint32_t D) {
   }
 }
 
-cudaError_t llmi_launch_attention(const AttnArgs& a, cudaStream_t s) {
+template <int D>
+static cudaError_t attention_launch(const AttnArgs& a, uint32_t n_tok, cudaStream_t s) {
   const size_t smem = llmi_attention_smem(a.t_max, a.D);
   const uint32_t nbuf = attention_nbuf(a.t_max, a.D);
+  if (n_tok <= 1 && !a.qbuf) return llmi_launch(attention_kernel<D, 0>, dim3(a.H), dim3(1024), smem, s, a, nbuf);
+  if (!a.qbuf) return cudaErrorInvalidValue;
+  cudaError_t e = llmi_launch(attention_kernel<D, 1>, dim3(a.H, n_tok), dim3(1024), 0, s, a, nbuf);
+  if (e != cudaSuccess) return e;
+  return llmi_launch(attention_kernel<D, 2>, dim3(a.H, n_tok), dim3(1024), smem, s, a, nbuf);
+}
+
+// n_tok > 1 (prefill batch): two launches, a.qbuf required (n_tok * H * D words).
+cudaError_t llmi_launch_attention(const AttnArgs& a, cudaStream_t s, uint32_t n_tok) {
   switch (a.D) {
-    case 64: return llmi_launch(attention_kernel<64>, dim3(a.H), dim3(1024), smem, s, a, nbuf);
-    case 128: return llmi_launch(attention_kernel<128>, dim3(a.H), dim3(1024), smem, s, a, nbuf);
-    case 256: return llmi_launch(attention_kernel<256>, dim3(a.H), dim3(1024), smem, s, a, nbuf);
-    case 512: return llmi_launch(attention_kernel<512>, dim3(a.H), dim3(1024), smem, s, a, nbuf);
+    case 64: return attention_launch<64>(a, n_tok, s);
+    case 128: return attention_launch<128>(a, n_tok, s);
+    case 256: return attention_launch<256>(a, n_tok, s);
+    case 512: return attention_launch<512>(a, n_tok, s);
     default: return cudaErrorInvalidValue;
   }
 }
 
 cudaError_t llmi_launch_geglu_act(const float* gate, const float* up, uint32_t n, int kind, uint8_t* buf,
-                                  float* hidden_out, cudaStream_t s) {
+                                  float* hidden_out, cudaStream_t s, uint32_t n_tok, uint32_t act_stride) {
   const uint32_t warps = kind == ACT_Q8_0 ? n / 32 : (kind == ACT_Q8_K ? n / 256 : (n + 31) / 32);
   const uint32_t blocks = (warps + 3) / 4 ? (warps + 3) / 4 : 1;
-  return llmi_launch(geglu_act_kernel, dim3(blocks), dim3(128), 0, s, gate, up, n, kind, buf, hidden_out);
+  return llmi_launch(geglu_act_kernel, dim3(blocks, n_tok), dim3(128), 0, s, gate, up, n, kind, buf, hidden_out,
+                     act_stride);
 }
 
 cudaError_t llmi_launch_finish_token(unsigned long long* key, int32_t* cur_tok, int32_t* gen, int32_t* gen_count,

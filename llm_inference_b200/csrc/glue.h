@@ -26,7 +26,9 @@ struct NormArgs {
   float* xn_out = nullptr;        // optional fp32 copy of the normalized vector
   int act_kind = ACT_NONE;
   uint8_t* act_buf = nullptr;
-  int32_t* pos_inc = nullptr;     // optional device counter to bump (end of a token step)
+  int32_t* pos_inc = nullptr;     // optional device counter to bump (end of a token step) by the number of tokens
+  uint32_t n_tok = 1;             // prefill batch: one CTA per token, vectors n apart, activations act_stride apart
+  uint32_t act_stride = 0;
 };
 
 struct AttnArgs {
@@ -43,17 +45,22 @@ struct AttnArgs {
   float* out;  // [H*D]
   int act_kind = ACT_NONE;  // fused quantizer for the attn_output mat-vec (ACT_NONE: caller quantizes)
   uint8_t* act_buf = nullptr;
+  // prefill batch (grid.y = token): q/k/v/out are H*D resp. HK*D apart, activations act_stride apart, *pos is
+  // the position of token 0; qbuf [n_tok][H][D] carries the rotated q between the two kernels
+  uint32_t* qbuf = nullptr;
+  uint32_t act_stride = 0;
 };
 
-cudaError_t llmi_launch_embed(const EmbedArgs& a, const int32_t* token, float scale, float* h, cudaStream_t s);
+cudaError_t llmi_launch_embed(const EmbedArgs& a, const int32_t* token, float scale, float* h, cudaStream_t s,
+                              uint32_t n_tok = 1);
 cudaError_t llmi_launch_norm_act(const NormArgs& a, cudaStream_t s);
 cudaError_t llmi_launch_act(const float* x, uint32_t n, int kind, uint8_t* buf, cudaStream_t s);
 cudaError_t llmi_launch_rope_table(float2* table, uint32_t t_max, uint32_t D, float base, float scale, cudaStream_t s);
 size_t llmi_attention_smem(uint32_t t_max, uint32_t D);
 cudaError_t llmi_attention_init(uint32_t t_max, uint32_t D);
-cudaError_t llmi_launch_attention(const AttnArgs& a, cudaStream_t s);
+cudaError_t llmi_launch_attention(const AttnArgs& a, cudaStream_t s, uint32_t n_tok = 1);
 cudaError_t llmi_launch_geglu_act(const float* gate, const float* up, uint32_t n, int kind, uint8_t* buf,
-                                  float* hidden_out, cudaStream_t s);
+                                  float* hidden_out, cudaStream_t s, uint32_t n_tok = 1, uint32_t act_stride = 0);
 cudaError_t llmi_launch_finish_token(unsigned long long* key, int32_t* cur_tok, int32_t* gen, int32_t* gen_count,
                                      cudaStream_t s);
 cudaError_t llmi_launch_softcap(float* logits, uint32_t n, float softcap, cudaStream_t s);

@@ -87,6 +87,10 @@ cudaError_t llmi_launch_export_q8_k(const uint8_t* buf, uint64_t n, uint8_t* out
 // gemv.cu
 cudaError_t llmi_gemv_init();  // opt-in dynamic shared memory for every instantiation
 cudaError_t llmi_launch_gemv(const llmi_weight_s& w, const llmi_act_s& a, float* out, cudaStream_t s);
+// token-batched mat-vec (prefill): n_tok activations act_bytes(kind, n) apart, outputs out_strides[i] floats apart
+cudaError_t llmi_launch_gemv_tokens(const llmi_weight_s* const* ws, float* const* outs, const uint32_t* out_strides,
+                                    int n, int act_kind, uint64_t act_n, const uint8_t* act_base, uint32_t n_tok,
+                                    cudaStream_t s);
 cudaError_t llmi_launch_gemv_batch(const llmi_weight_s* const* ws, float* const* outs, int n, const llmi_act_s& a,
                                    cudaStream_t s);  // same format, same activation, n <= 3
 uint32_t llmi_gemv_chunks(const llmi_weight_s& w);

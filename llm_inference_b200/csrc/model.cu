@@ -57,6 +57,14 @@ struct llmi_model_s {
   float* logits_pinned = nullptr;
   uint64_t weight_bytes = 0;
   int launches_per_step = 0;
+  // prefill: up to `batch` prompt tokens go through a layer together (run_batch).  The fp32 vectors above are
+  // allocated `batch` deep; quantized activations of a batch live in bact_* (batch x act_bytes, lazily per kind)
+  uint32_t batch = 1;
+  uint8_t *bact_E[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}, *bact_HD[5] = {nullptr, nullptr, nullptr, nullptr, nullptr},
+          *bact_F[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  uint32_t* qbuf = nullptr;  // [batch][H][D] rotated q between the two prefill attention kernels
+  bool prefill_ok = true;
+  int prefill_launches = 0;
 };
 
 namespace {
@@ -248,6 +256,130 @@ int run_step(llmi_model_s* m, const int32_t* tok, bool want_logits, bool want_ar
   return LLMI_OK;
 }
 
+// Quantized activations of a prefill batch: `batch` buffers act_bytes(kind, n) apart.
+uint8_t* get_bact(llmi_model_s* m, uint8_t** set, int kind, uint64_t n) {
+  if (!set[kind]) {
+    if (dev_alloc(m, (void**)&set[kind], size_t(m->batch) * act_bytes(kind, n)) != LLMI_OK) return nullptr;
+  }
+  return set[kind];
+}
+
+// Mat-vecs of a batch that consume the same activations: one grid per format group.
+int gemv_tokens_group(llmi_model_s* m, std::initializer_list<llmi_weight_t> ws, std::initializer_list<float*> outs,
+                      std::initializer_list<uint32_t> strides, uint8_t** set, uint64_t n, uint32_t n_tok) {
+  std::vector<llmi_weight_t> w(ws);
+  std::vector<float*> o(outs);
+  std::vector<uint32_t> st(strides);
+  std::vector<bool> done(w.size(), false);
+  for (size_t i = 0; i < w.size(); ++i) {
+    if (done[i]) continue;
+    const llmi_weight_s* bw[3];
+    float* bo[3];
+    uint32_t bs[3];
+    int k = 0;
+    for (size_t j = i; j < w.size() && k < 3; ++j)
+      if (!done[j] && w[j]->type == w[i]->type) {
+        bw[k] = w[j];
+        bo[k] = o[j];
+        bs[k] = st[j];
+        done[j] = true;
+        ++k;
+      }
+    const int kind = llmi_act_kind_for(w[i]->type);
+    M_TRY(llmi_launch_gemv_tokens(bw, bo, bs, k, kind, n, set[kind], n_tok, m->stream));
+    m->prefill_launches++;
+  }
+  return LLMI_OK;
+}
+
+// n_tok <= batch prompt tokens through all layers together (the loop nest of the reference's forward is
+// layer-major with the tokens inside, model.cpp:714-960).  Per token the arithmetic is the one run_step
+// does — same kernels with a token index — so the KV cache and the logits are bit-identical to feeding the
+// tokens one by one; what changes is that every weight matrix is read once per 8 tokens instead of once per
+// token and a layer costs 9 launches per batch instead of 8 per token.  Requires prefill_ok (every
+// consumer of a vector takes the same activation kind).  Logits (of the last token) only if want_logits.
+int run_batch(llmi_model_s* m, const int32_t* toks, uint32_t n_tok, bool want_logits) {
+  cudaStream_t s = m->stream;
+  const uint32_t E = m->E, F = m->F, HD = m->H * m->D, KD = m->HK * m->D;
+  M_TRY(llmi_launch_embed(make_embed_args(*m->embd), toks, std::sqrt(float(E)), m->h, s, n_tok));
+  m->prefill_launches++;
+  for (uint32_t l = 0; l < m->L; ++l) {
+    LayerW& w = m->layers[l];
+    const int kq = llmi_act_kind_for(w.q->type);
+    if (l == 0) {
+      NormArgs na;
+      na.h = m->h; na.w = w.attn_norm; na.n = E; na.eps = m->eps; na.xn_out = m->xn;
+      na.act_kind = kq; na.act_buf = get_bact(m, m->bact_E, kq, E); na.n_tok = n_tok;
+      na.act_stride = uint32_t(act_bytes(kq, E));
+      M_TRY(llmi_launch_norm_act(na, s));
+      m->prefill_launches++;
+    }
+    M_RC(gemv_tokens_group(m, {w.q, w.k, w.v}, {m->q, m->k, m->v}, {HD, KD, KD}, m->bact_E, E, n_tok));
+    AttnArgs aa;
+    aa.q = m->q; aa.k = m->k; aa.v = m->v; aa.wq_norm = w.q_norm; aa.wk_norm = w.k_norm;
+    aa.kcache = m->kcache + size_t(l) * m->t_max * m->HK * m->D;
+    aa.vcache = m->vcache + size_t(l) * m->t_max * m->HK * m->D;
+    aa.H = m->H; aa.HK = m->HK; aa.D = m->D; aa.t_max = m->t_max; aa.eps = m->eps;
+    aa.rope_table = w.swa ? m->rope_swa : m->rope_global;
+    aa.attn_scale = m->attn_scale; aa.pos = m->d_pos;
+    aa.softcap = m->attn_softcap; aa.out = m->attn;
+    const int ko = llmi_act_kind_for(w.o->type);
+    aa.act_kind = ko; aa.act_buf = get_bact(m, m->bact_HD, ko, HD); aa.act_stride = uint32_t(act_bytes(ko, HD));
+    aa.qbuf = m->qbuf;
+    M_TRY(llmi_launch_attention(aa, s, n_tok));
+    m->prefill_launches += 2;
+    M_RC(gemv_tokens_group(m, {w.o}, {m->attn_out}, {E}, m->bact_HD, HD, n_tok));
+    {
+      const int kg = llmi_act_kind_for(w.gate->type);
+      NormArgs na;
+      na.y = m->attn_out; na.w_post = w.post_attn_norm; na.h = m->h; na.w = w.ffn_norm; na.n = E; na.eps = m->eps;
+      na.xn_out = m->xn; na.act_kind = kg; na.act_buf = get_bact(m, m->bact_E, kg, E); na.n_tok = n_tok;
+      na.act_stride = uint32_t(act_bytes(kg, E));
+      M_TRY(llmi_launch_norm_act(na, s));
+      m->prefill_launches++;
+    }
+    M_RC(gemv_tokens_group(m, {w.gate, w.up}, {m->gate, m->up}, {F, F}, m->bact_E, E, n_tok));
+    const int kd = llmi_act_kind_for(w.down->type);
+    M_TRY(llmi_launch_geglu_act(m->gate, m->up, F, kd, get_bact(m, m->bact_F, kd, F), nullptr, s, n_tok,
+                                uint32_t(act_bytes(kd, F))));
+    m->prefill_launches++;
+    M_RC(gemv_tokens_group(m, {w.down}, {m->ffn_out}, {E}, m->bact_F, F, n_tok));
+    {
+      NormArgs na;
+      na.y = m->ffn_out; na.w_post = w.post_ffw_norm; na.h = m->h; na.n = E; na.eps = m->eps; na.xn_out = m->xn;
+      na.n_tok = n_tok;
+      if (l + 1 < m->L) {
+        const int kn = llmi_act_kind_for(m->layers[l + 1].q->type);
+        na.w = m->layers[l + 1].attn_norm; na.act_kind = kn; na.act_buf = get_bact(m, m->bact_E, kn, E);
+        na.act_stride = uint32_t(act_bytes(kn, E));
+      } else {
+        na.pos_inc = m->d_pos;  // the batch is done: += n_tok
+        if (want_logits) {
+          const int kl = llmi_act_kind_for(m->embd->type);
+          na.w = m->out_norm; na.act_kind = kl; na.act_buf = get_bact(m, m->bact_E, kl, E);
+          na.act_stride = uint32_t(act_bytes(kl, E));
+        }
+      }
+      M_TRY(llmi_launch_norm_act(na, s));
+      m->prefill_launches++;
+    }
+  }
+  if (want_logits) {  // logits of the last token of the batch: the ordinary one-token mat-vec
+    const int kl = llmi_act_kind_for(m->embd->type);
+    llmi_act_s la;
+    la.kind = kl;
+    la.n = E;
+    la.buf = m->bact_E[kl] + size_t(n_tok - 1) * act_bytes(kl, E);
+    M_TRY(llmi_launch_gemv(*m->embd, la, m->logits, s));
+    m->prefill_launches++;
+    if (m->final_softcap > 0.0f) {
+      M_TRY(llmi_launch_softcap(m->logits, m->V, m->final_softcap, s));
+      m->prefill_launches++;
+    }
+  }
+  return LLMI_OK;
+}
+
 double kv_f(const llmi::GgufImage& g, const std::string& key, double dflt, bool* found = nullptr) {
   const llmi::GgufValue* v = g.find(key);
   if (found) *found = v != nullptr;
@@ -327,17 +459,32 @@ int load_impl(llmi_model_s* m, const uint8_t* image, uint64_t size, uint32_t t_m
     M_RC(upload_matrix(m, T("ffn_down"), F, E, &w.down, "ffn_down"));
   }
   const size_t mx = std::max<size_t>({E, F, HD});
-  M_RC(dev_alloc(m, (void**)&m->h, E * 4));
-  M_RC(dev_alloc(m, (void**)&m->xn, mx * 4));
-  M_RC(dev_alloc(m, (void**)&m->q, HD * 4));
-  M_RC(dev_alloc(m, (void**)&m->k, KD * 4));
-  M_RC(dev_alloc(m, (void**)&m->v, KD * 4));
+  m->batch = 64;
+  if (const char* e = getenv("LLMI_PREFILL_BATCH")) m->batch = uint32_t(std::max(1, atoi(e)));
+  if (m->batch > t_max) m->batch = t_max;
+  const size_t B = m->batch;
+  M_RC(dev_alloc(m, (void**)&m->h, B * E * 4));
+  M_RC(dev_alloc(m, (void**)&m->xn, B * mx * 4));
+  M_RC(dev_alloc(m, (void**)&m->q, B * HD * 4));
+  M_RC(dev_alloc(m, (void**)&m->k, B * KD * 4));
+  M_RC(dev_alloc(m, (void**)&m->v, B * KD * 4));
   M_RC(dev_alloc(m, (void**)&m->q_rot, HD * 4));
-  M_RC(dev_alloc(m, (void**)&m->attn, HD * 4));
-  M_RC(dev_alloc(m, (void**)&m->attn_out, E * 4));
-  M_RC(dev_alloc(m, (void**)&m->gate, F * 4));
-  M_RC(dev_alloc(m, (void**)&m->up, F * 4));
-  M_RC(dev_alloc(m, (void**)&m->ffn_out, E * 4));
+  M_RC(dev_alloc(m, (void**)&m->attn, B * HD * 4));
+  M_RC(dev_alloc(m, (void**)&m->attn_out, B * E * 4));
+  M_RC(dev_alloc(m, (void**)&m->gate, B * F * 4));
+  M_RC(dev_alloc(m, (void**)&m->up, B * F * 4));
+  M_RC(dev_alloc(m, (void**)&m->ffn_out, B * E * 4));
+  M_RC(dev_alloc(m, (void**)&m->qbuf, B * HD * 4));
+  // a batch needs every consumer of a vector to take the same activation kind (true for the uniform and the
+  // Q4_K_M layouts; otherwise prompts go token by token) and attention's fused quantizer to apply
+  for (const LayerW& w : m->layers) {
+    const int kq = llmi_act_kind_for(w.q->type), kg = llmi_act_kind_for(w.gate->type), ko = llmi_act_kind_for(w.o->type);
+    if (llmi_act_kind_for(w.k->type) != kq || llmi_act_kind_for(w.v->type) != kq || llmi_act_kind_for(w.up->type) != kg)
+      m->prefill_ok = false;
+    if (ko == ACT_Q8_K && m->D % 256 != 0) m->prefill_ok = false;
+  }
+  if (m->batch < 2) m->prefill_ok = false;
+  if (const char* e = getenv("LLMI_NO_PREFILL")) m->prefill_ok = m->prefill_ok && !(e[0] == '1');
   M_RC(dev_alloc(m, (void**)&m->logits, size_t(m->V) * 4));
   const size_t kv_elems = size_t(m->L) * t_max * KD;
   M_RC(dev_alloc(m, (void**)&m->kcache, kv_elems * 4));
@@ -456,7 +603,20 @@ int llmi_model_forward(llmi_model_t m, const int32_t* tokens, int n_tokens, int 
   cudaStream_t s = m->stream;
   M_TRY(cudaMemcpyAsync(m->d_toks, tokens, size_t(n_tokens) * 4, cudaMemcpyHostToDevice, s));
   M_TRY(cudaMemcpyAsync(m->d_pos, &pos, 4, cudaMemcpyHostToDevice, s));
-  for (int t = 0; t < n_tokens; ++t) M_RC(run_step(m, m->d_toks + t, t == n_tokens - 1, false));
+  m->prefill_launches = 0;
+  M_TRY(cudaEventRecord(m->ev0, s));
+  if (m->prefill_ok && n_tokens > 1) {
+    for (int t = 0; t < n_tokens; t += int(m->batch)) {
+      const int nb = std::min(int(m->batch), n_tokens - t);
+      M_RC(run_batch(m, m->d_toks + t, uint32_t(nb), t + nb == n_tokens));
+    }
+  } else {
+    for (int t = 0; t < n_tokens; ++t) {
+      M_RC(run_step(m, m->d_toks + t, t == n_tokens - 1, false));
+      m->prefill_launches += m->launches_per_step;
+    }
+  }
+  M_TRY(cudaEventRecord(m->ev1, s));
   M_TRY(cudaMemcpyAsync(m->logits_pinned, m->logits, size_t(m->V) * 4, cudaMemcpyDeviceToHost, s));
   M_TRY(cudaStreamSynchronize(s));
   memcpy(logits_host, m->logits_pinned, size_t(m->V) * 4);
@@ -499,5 +659,12 @@ int llmi_model_last_logits(llmi_model_t m, float* logits_host) {
 }
 
 int llmi_model_launches_per_step(llmi_model_t m) { return m ? m->launches_per_step : 0; }
+
+int llmi_model_last_forward_stats(llmi_model_t m, float* ms_device, int* launches) {
+  if (!m) return llmi_fail(LLMI_ERR_ARG, "llmi_model_last_forward_stats: null model");
+  if (ms_device) M_TRY(cudaEventElapsedTime(ms_device, m->ev0, m->ev1));
+  if (launches) *launches = m->prefill_launches;
+  return LLMI_OK;
+}
 
 }  // extern "C"

@@ -47,6 +47,12 @@ class Model:
         _lib.check(_lib.load().llmi_model_last_logits(self.h, logits.ctypes.data))
         return logits
 
+    def last_forward_stats(self):
+        """(device milliseconds, kernel launches) of the last forward() call."""
+        ms, n = C.c_float(), C.c_int()
+        _lib.check(_lib.load().llmi_model_last_forward_stats(self.h, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
+
     @property
     def launches_per_step(self) -> int:
         return int(_lib.load().llmi_model_launches_per_step(self.h))

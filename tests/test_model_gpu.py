@@ -111,3 +111,33 @@ def test_model_load_errors(gpu_ops):
         Model(g.build())
     with pytest.raises(_lib.LlmiError, match="Invalid GGUF magic number"):
         Model(np.zeros(64, np.uint8))
+
+
+@pytest.mark.parametrize("wt,et", [(synth.Q4_0, synth.F16), ("q4_k_m", synth.Q6_K), (synth.Q8_0, synth.Q8_0)])
+def test_batched_prefill_is_bitwise_the_token_by_token_path(gpu_ops, monkeypatch, wt, et):
+    """A prompt goes through each layer in batches (weights read once per 8 tokens); per token the
+    arithmetic is that of the one-token path, so logits AND the KV cache (probed by decoding on) must be
+    bit-identical, for a batch size that splits the prompt unevenly."""
+    from llm_inference_b200.model import Model
+    dims = synth.GemmaDims("small", 3, 512, 1024, 4, 2, 256, 640)
+    img = synth.build_gemma3_gguf(dims, wt, et, seed=11, embd_std=0.02)
+    prompt = (np.arange(37, dtype=np.int32) * 7 + 3) % dims.vocab
+    outs = {}
+    for mode, env in (("batched", {"LLMI_PREFILL_BATCH": "16"}), ("single", {"LLMI_NO_PREFILL": "1"})):
+        for k in ("LLMI_PREFILL_BATCH", "LLMI_NO_PREFILL"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        m = Model(img, max_positions=64)
+        lg = [m.forward(prompt, 0)]
+        ms, launches = m.last_forward_stats()
+        pos = len(prompt)
+        for _ in range(3):
+            lg.append(m.forward([int(lg[-1].argmax())], pos))
+            pos += 1
+        lg.append(m.forward(prompt[:9], pos))  # a second, short prompt appended to the same cache
+        outs[mode] = (np.stack(lg), launches)
+        m.close()
+    a, b = outs["batched"][0], outs["single"][0]
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert outs["batched"][1] < outs["single"][1] / 4  # 3 batches of launches instead of 37 tokens' worth
