@@ -24,6 +24,9 @@
 //     formulas (summation ORDER differs: that is the documented 1e-5 bound).
 #include <cuda_fp16.h>
 
+#include <algorithm>
+#include <type_traits>
+
 #include "launch.cuh"
 #include "llmi_internal.h"
 
@@ -68,6 +71,7 @@ struct GemvArgs {
   uint32_t row0;  // global index of this handle's first row
   // token-batched launches (prefill): n_tok activation buffers act_stride bytes apart, outputs out_stride floats apart
   uint32_t n_tok, act_stride, out_stride;
+  float* part;  // token-per-lane kernel: chunk partials [chunk][token][8 * n_slabs] of this matrix
 };
 
 // ------------------------------------------------ integer block dot products
@@ -548,7 +552,8 @@ __global__ void __launch_bounds__(W * 32) gemv_slab_tok_kernel(const GemvBatch b
   float* part = reinterpret_cast<float*>(sm_act + size_t(MT) * a.act_stride);
   uint32_t parity = 0;
   pdl_wait();
-  for (uint32_t m0 = 0; m0 < a.n_tok; m0 += MT) {
+  // blockIdx.y strides over the token tiles: small matrices get their parallelism from the tokens
+  for (uint32_t m0 = blockIdx.y * MT; m0 < a.n_tok; m0 += gridDim.y * MT) {
     const uint32_t mt = min(MT, a.n_tok - m0);
     if (threadIdx.x == 0) {
       mbar_expect_tx(&bar, mt * a.act_stride);
@@ -583,6 +588,155 @@ __global__ void __launch_bounds__(W * 32) gemv_slab_tok_kernel(const GemvBatch b
       if (row < a.n_local) a.out[size_t(m0 + m) * a.out_stride + row] = sum;
     }
     __syncthreads();  // the tile and the partials are reused
+  }
+}
+
+// ------------------------------------- token-per-lane kernel (Q4_0 / Q8_0 weights)
+// For batches of >= 16 tokens the roles flip: a lane owns a TOKEN and keeps that
+// token's activation block in registers, the weights of the warp's slab (8 rows)
+// sit in shared memory, unpacked to int8 once per K-chunk, and are read by
+// broadcast — 2 shared-memory wavefronts serve 32 tokens, and the nibble unpack
+// is paid once per 32 tokens.  Per (row, token) the arithmetic is the one of
+// BodyQ4_0 / BodyQ8_0 and the summation order is the canonical one: inside a
+// K-chunk of 16 blocks four chains s[k] take the blocks b with b % 4 == k in
+// order (the four sub-lanes of gemv_slab_kernel), chunk partial = (s0+s1)+(s2+s3)
+// (its two xor shuffles), chunk partials added left to right.  Bit-identical to
+// the one-token kernel (tests/test_model_gpu.py).
+// CTA = W warps = W slabs sharing the activation tile of one group of 32 tokens;
+// grid = (slab groups of all matrices of the batch, token groups).
+constexpr int TL_ACT_ROW = 528;  // 512 int8 of a chunk + 16 pad: lanes 33 x 16 B apart -> conflict-free LDS.128
+constexpr int TL_SC_ROW = 17;    // 16 scale words + 1 pad
+
+template <bool IS_Q8>
+struct TokLane {
+  // stage blocks [b0, b0+nbk) of slab `slab` into wq (int8 [16][8][32]) and wd (f32(f16 d) [16][8])
+  __device__ static void stage_weights(const GemvArgs& a, uint32_t slab, uint32_t b0, uint32_t nbk, uint8_t* wq,
+                                       float* wd, int lane) {
+    if (IS_Q8) {
+      const uint4* src = reinterpret_cast<const uint4*>(a.q) + (size_t(slab) * a.nb + b0) * 16;
+      for (uint32_t i = lane; i < nbk * 16; i += 32) {  // item i = (lb*2 + h)*8 + r
+        const uint32_t lb = i >> 4, hh = (i >> 3) & 1, r = i & 7;
+        *reinterpret_cast<uint4*>(wq + (lb * 8 + r) * 32 + hh * 16) = ldg_stream(src + i);
+      }
+    } else {
+      const uint4* src = reinterpret_cast<const uint4*>(a.q) + (size_t(slab) * a.nb + b0) * 8;
+      for (uint32_t i = lane; i < nbk * 8; i += 32) {  // item i = lb*8 + r: byte j = element j (low nibble) and j+16 (high)
+        const uint4 w = ldg_stream(src + i);
+        uint4 lo, hi;
+        lo.x = w.x & 0x0f0f0f0fu; lo.y = w.y & 0x0f0f0f0fu; lo.z = w.z & 0x0f0f0f0fu; lo.w = w.w & 0x0f0f0f0fu;
+        hi.x = (w.x >> 4) & 0x0f0f0f0fu; hi.y = (w.y >> 4) & 0x0f0f0f0fu;
+        hi.z = (w.z >> 4) & 0x0f0f0f0fu; hi.w = (w.w >> 4) & 0x0f0f0f0fu;
+        *reinterpret_cast<uint4*>(wq + i * 32) = lo;
+        *reinterpret_cast<uint4*>(wq + i * 32 + 16) = hi;
+      }
+    }
+    const uint16_t* dsrc = reinterpret_cast<const uint16_t*>(a.d) + (size_t(slab) * a.nb + b0) * 8;
+    for (uint32_t i = lane; i < nbk * 8; i += 32) wd[i] = h2f(ldg_stream(dsrc + i));
+  }
+  // one block of one row folded into the chain accumulator (BodyQ4_0::compute / BodyQ8_0::compute)
+  // m8 = -8 * (sum of the activation block's quants) for Q4_0 (sum (nib-8)*q = sum nib*q - 8*sum q), 0 for Q8_0
+  __device__ static float fold(const uint4 w0, const uint4 w1, const float dw, const int4 xa, const int4 xb,
+                               const float dx, const int m8, float acc) {
+    int dp = m8;
+    dp = __dp4a(int(w0.x), xa.x, dp);
+    dp = __dp4a(int(w0.y), xa.y, dp);
+    dp = __dp4a(int(w0.z), xa.z, dp);
+    dp = __dp4a(int(w0.w), xa.w, dp);
+    dp = __dp4a(int(w1.x), xb.x, dp);
+    dp = __dp4a(int(w1.y), xb.y, dp);
+    dp = __dp4a(int(w1.z), xb.z, dp);
+    dp = __dp4a(int(w1.w), xb.w, dp);
+    if (IS_Q8) return fmaf(float(dp) * dw, dx, acc);  // (int*dw)*dx, ops.cpp:820
+    return fmaf(dw * dx, float(dp), acc);              // ops.cpp:380-395
+  }
+};
+
+// One CTA = one K-chunk (blockIdx.z) x W slabs x 32 tokens (blockIdx.y): chunk partials are independent of
+// each other, so the K dimension is a grid dimension too and short, wide matrices (ffn_down) still fill the
+// GPU; toklane_reduce_kernel then adds the chunk partials of every (token, row) left to right.
+template <bool IS_Q8, int W>
+__global__ void __launch_bounds__(W * 32) gemm_toklane_kernel(const GemvBatch batch) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int mi = 0;
+  while (mi + 1 < batch.n && blockIdx.x >= batch.cta_end[mi]) ++mi;
+  const GemvArgs& a = batch.a[mi];
+  const uint32_t cta = blockIdx.x - (mi ? batch.cta_end[mi - 1] : 0u);
+  pdl_trigger();
+  const uint32_t j = blockIdx.z, b0 = j * 16;
+  if (b0 >= a.nb) return;  // matrices of one launch may differ in K (never for q/k/v, gate/up)
+  const uint32_t nbk = min(16u, a.nb - b0);
+  uint8_t* act_q = smem;                                                        // [32 tokens][TL_ACT_ROW]
+  uint32_t* act_s = reinterpret_cast<uint32_t*>(smem + 32 * TL_ACT_ROW);        // [32 tokens][TL_SC_ROW]
+  uint8_t* wq = smem + 32 * TL_ACT_ROW + 32 * TL_SC_ROW * 4 + size_t(warp) * (16 * 8 * 32 + 16 * 8 * 4);
+  float* wd = reinterpret_cast<float*>(wq + 16 * 8 * 32);
+  const uint32_t slab = cta * W + warp;
+  const bool have_slab = slab < a.n_slabs;
+  const uint32_t m0 = blockIdx.y * 32, n_here = min(32u, a.n_tok - m0);
+  if (have_slab) TokLane<IS_Q8>::stage_weights(a, slab, b0, nbk, wq, wd, lane);  // independent of the predecessor
+  pdl_wait();
+  // activation tile of the chunk: token-major rows, every thread copies 16-byte pieces (coalesced per token)
+  for (uint32_t p = threadIdx.x; p < n_here * 32; p += W * 32) {
+    const uint32_t tk = p >> 5, piece = p & 31;
+    if (piece < nbk * 2) {
+      const uint4 v = *reinterpret_cast<const uint4*>(a.act + size_t(m0 + tk) * a.act_stride + size_t(b0) * 32 + piece * 16);
+      *reinterpret_cast<uint4*>(act_q + tk * TL_ACT_ROW + piece * 16) = v;
+    }
+  }
+  for (uint32_t p = threadIdx.x; p < n_here * 16; p += W * 32) {
+    const uint32_t tk = p >> 4, lb = p & 15;
+    if (lb < nbk)
+      act_s[tk * TL_SC_ROW + lb] = reinterpret_cast<const uint32_t*>(a.act + size_t(m0 + tk) * a.act_stride + a.n_cols)[b0 + lb];
+  }
+  __syncthreads();
+  if (!have_slab) return;
+  float s[LLMI_SLAB][4];
+#pragma unroll
+  for (int r = 0; r < LLMI_SLAB; ++r)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s[r][k] = 0.0f;
+  for (uint32_t lb4 = 0; lb4 < nbk; lb4 += 4) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t lb = lb4 + k;
+      if (lb < nbk) {
+        const int4 xa = *reinterpret_cast<const int4*>(act_q + lane * TL_ACT_ROW + lb * 32);
+        const int4 xb = *reinterpret_cast<const int4*>(act_q + lane * TL_ACT_ROW + lb * 32 + 16);
+        const uint32_t sw = act_s[lane * TL_SC_ROW + lb];
+        const float dx = h2f(uint16_t(sw & 0xffffu));
+        const int m8 = IS_Q8 ? 0 : -8 * int(int16_t(sw >> 16));
+#pragma unroll
+        for (int r = 0; r < LLMI_SLAB; ++r) {
+          const uint4 w0 = *reinterpret_cast<const uint4*>(wq + (lb * 8 + r) * 32);
+          const uint4 w1 = *reinterpret_cast<const uint4*>(wq + (lb * 8 + r) * 32 + 16);
+          s[r][k] = TokLane<IS_Q8>::fold(w0, w1, wd[lb * 8 + r], xa, xb, dx, m8, s[r][k]);
+        }
+      }
+    }
+  }
+  if (uint32_t(lane) < n_here) {
+    float4* o = reinterpret_cast<float4*>(a.part + (size_t(j) * a.n_tok + m0 + lane) * (a.n_slabs * LLMI_SLAB) +
+                                          size_t(slab) * LLMI_SLAB);
+    o[0] = make_float4((s[0][0] + s[0][1]) + (s[0][2] + s[0][3]), (s[1][0] + s[1][1]) + (s[1][2] + s[1][3]),
+                       (s[2][0] + s[2][1]) + (s[2][2] + s[2][3]), (s[3][0] + s[3][1]) + (s[3][2] + s[3][3]));
+    o[1] = make_float4((s[4][0] + s[4][1]) + (s[4][2] + s[4][3]), (s[5][0] + s[5][1]) + (s[5][2] + s[5][3]),
+                       (s[6][0] + s[6][1]) + (s[6][2] + s[6][3]), (s[7][0] + s[7][1]) + (s[7][2] + s[7][3]));
+  }
+}
+
+// out[token][row] = p[0] + p[1] + ... + p[J-1] (left to right: the canonical order); blockIdx.y = matrix
+__global__ void toklane_reduce_kernel(const GemvBatch batch) {
+  pdl_trigger();
+  pdl_wait();
+  const GemvArgs& a = batch.a[blockIdx.y];
+  const uint32_t rows_p = a.n_slabs * LLMI_SLAB, J = (a.nb + 15) / 16;
+  const uint64_t total = uint64_t(a.n_tok) * a.n_local;
+  for (uint64_t idx = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; idx < total; idx += uint64_t(gridDim.x) * blockDim.x) {
+    const uint32_t m = uint32_t(idx / a.n_local), row = uint32_t(idx % a.n_local);
+    const float* p = a.part + size_t(m) * rows_p + row;
+    float sum = p[0];
+    for (uint32_t j = 1; j < J; ++j) sum += p[size_t(j) * a.n_tok * rows_p];
+    a.out[size_t(m) * a.out_stride + row] = sum;
   }
 }
 
@@ -702,8 +856,63 @@ cudaError_t launch_batch(const GemvArgs* args, int n, cudaStream_t s) {
 constexpr size_t TOK_TILE_BYTES = 64 * 1024;  // activations of one token tile in shared memory
 constexpr int TOK_MAX_TILE = 8;
 
+constexpr size_t tl_smem(int W) { return 32 * TL_ACT_ROW + 32 * TL_SC_ROW * 4 + size_t(W) * (16 * 8 * 32 + 16 * 8 * 4); }
+
+// grow-only scratch for the chunk partials of one token-per-lane launch
+static float* g_part = nullptr;
+static size_t g_part_floats = 0;
+
+template <bool IS_Q8>
+cudaError_t launch_toklane(const GemvArgs* args, int n, cudaStream_t s) {
+  constexpr int W = 8;
+  GemvBatch b;
+  b.n = n;
+  uint32_t ctas = 0, jmax = 0;
+  size_t need = 0;
+  for (int i = 0; i < n; ++i) {
+    const uint32_t J = (args[i].nb + 15) / 16;
+    if (J > jmax) jmax = J;
+    need += size_t(J) * args[i].n_tok * args[i].n_slabs * LLMI_SLAB;
+  }
+  if (need > g_part_floats) {
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return e;
+    if (g_part) cudaFree(g_part);
+    g_part = nullptr;
+    g_part_floats = 0;
+    if ((e = cudaMalloc(&g_part, need * sizeof(float))) != cudaSuccess) return e;
+    g_part_floats = need;
+  }
+  size_t off = 0;
+  uint64_t outs = 0;
+  for (int i = 0; i < n; ++i) {
+    b.a[i] = args[i];
+    b.a[i].part = g_part + off;
+    off += size_t((args[i].nb + 15) / 16) * args[i].n_tok * args[i].n_slabs * LLMI_SLAB;
+    b.S[i] = W;
+    ctas += (args[i].n_slabs + W - 1) / W;
+    b.cta_end[i] = ctas;
+    outs = std::max<uint64_t>(outs, uint64_t(args[i].n_tok) * args[i].n_local);
+  }
+  for (int i = n; i < GEMV_MAX_BATCH; ++i) {
+    b.a[i] = b.a[0];
+    b.S[i] = W;
+    b.cta_end[i] = ctas;
+  }
+  if (ctas == 0) return cudaSuccess;
+  cudaError_t e = llmi_launch(gemm_toklane_kernel<IS_Q8, W>, dim3(ctas, (args[0].n_tok + 31) / 32, jmax), dim3(W * 32),
+                              tl_smem(W), s, b);
+  if (e != cudaSuccess) return e;
+  const unsigned rb = unsigned(std::min<uint64_t>((outs + 255) / 256, uint64_t(g_sm_count) * 8));
+  return llmi_launch(toklane_reduce_kernel, dim3(rb, n), dim3(256), 0, s, b);
+}
+
 template <class B>
 cudaError_t launch_tokens(const GemvArgs* args, int n, cudaStream_t s) {
+  if (args[0].n_tok >= 16) {
+    if (std::is_same<B, BodyQ4_0>::value) return launch_toklane<false>(args, n, s);
+    if (std::is_same<B, BodyQ8_0>::value) return launch_toklane<true>(args, n, s);
+  }
   GemvBatch b;
   b.n = n;
   uint64_t slabs = 0;
@@ -736,10 +945,15 @@ cudaError_t launch_tokens(const GemvArgs* args, int n, cudaStream_t s) {
   }
   if (ctas == 0) return cudaSuccess;
   if (smem > size_t(MAX_DYN_SMEM)) return cudaErrorInvalidValue;
+  // token tiles across grid.y until the grid holds ~8 CTAs per SM (the weights of a tile's CTAs come from L2)
+  const uint32_t tiles = (args[0].n_tok + MT - 1) / MT;
+  uint32_t gy = 1;
+  while (gy < tiles && uint64_t(ctas) * gy < uint64_t(g_sm_count) * 8) gy *= 2;
+  if (gy > tiles) gy = tiles;
   switch (W) {
-    case 4: return llmi_launch(gemv_slab_tok_kernel<B, 4>, dim3(ctas), dim3(128), smem, s, b, MT);
-    case 8: return llmi_launch(gemv_slab_tok_kernel<B, 8>, dim3(ctas), dim3(256), smem, s, b, MT);
-    default: return llmi_launch(gemv_slab_tok_kernel<B, 16>, dim3(ctas), dim3(512), smem, s, b, MT);
+    case 4: return llmi_launch(gemv_slab_tok_kernel<B, 4>, dim3(ctas, gy), dim3(128), smem, s, b, MT);
+    case 8: return llmi_launch(gemv_slab_tok_kernel<B, 8>, dim3(ctas, gy), dim3(256), smem, s, b, MT);
+    default: return llmi_launch(gemv_slab_tok_kernel<B, 16>, dim3(ctas, gy), dim3(512), smem, s, b, MT);
   }
 }
 
@@ -791,6 +1005,11 @@ void llmi_gemv_set_shape(int warps, int slabs_per_cta) {
 }
 
 cudaError_t llmi_gemv_init() {
+  cudaError_t e0;
+  if ((e0 = cudaFuncSetAttribute(gemm_toklane_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 int(tl_smem(8)))) != cudaSuccess) return e0;
+  if ((e0 = cudaFuncSetAttribute(gemm_toklane_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 int(tl_smem(8)))) != cudaSuccess) return e0;
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
@@ -825,6 +1044,7 @@ static GemvArgs make_args(const llmi_weight_s& w, const llmi_act_s& a, float* ou
   g.n_tok = 1;
   g.act_stride = g.act_bytes;
   g.out_stride = 0;
+  g.part = nullptr;
   return g;
 }
 
