@@ -134,6 +134,14 @@ int llmi_mat_vec_mul_dev(llmi_weight_t w, const float* x_dev, llmi_act_t a,
  * never depend on it (canonical summation order). */
 int llmi_set_gemv_shape(int warps, int slabs_per_cta);
 
+/* Token-batched mat-vec (prefill; the M >= 16 entry SURVEY §8b calls llmi_gemm_prefill): x_dev is
+ * [n_tokens][n_cols] fp32, out_dev [n_tokens][n_rows] fp32 (a row-shard handle fills its own rows).  The
+ * reference has no batched matmul — its forward loops the tokens around mat_vec_mul (model.cpp:714-960) —
+ * so the contract is "n_tokens calls of mat_vec_mul": every (token, row) is bit-identical to
+ * llmi_mat_vec_mul_dev, the weights are read once per 8 tokens (any format) or once per K-chunk per 32
+ * tokens (Q4_0 / Q8_0, exact dp4a block dots with the token on the lane). */
+int llmi_gemm_tokens(llmi_weight_t w, const float* x_dev, uint32_t n_tokens, float* out_dev, llmi_stream_t stream);
+
 /* Per-block integer dot products (must be bit-exact with the reference):
  * Q4_0/Q8_0: rows*(K/32) int32; Q4_K: rows*(K/32); Q6_K: rows*(K/128).
  * dots_host is indexed [local_row][block]. */

@@ -53,6 +53,7 @@ SIGNATURES = {
     "llmi_model_forward": (_int, [_vp, _vp, _int, _int, _vp]),
     "llmi_model_decode_greedy": (_int, [_vp, C.c_int32, _int, _int, _vp, C.POINTER(C.c_float)]),
     "llmi_model_last_logits": (_int, [_vp, _vp]),
+    "llmi_gemm_tokens": (_int, [_vp, _vp, _u32, _vp, _vp]),
     "llmi_model_launches_per_step": (_int, [_vp]),
     "llmi_model_last_forward_stats": (_int, [_vp, _vp, _vp]),
     "llmi_dev_alloc": (_int, [_u64, C.POINTER(_vp)]),

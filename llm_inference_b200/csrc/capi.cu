@@ -8,6 +8,7 @@
 #include <tuple>
 #include <vector>
 
+#include "glue.h"
 #include "launch.cuh"
 #include "llmi_internal.h"
 
@@ -32,6 +33,8 @@ struct Context {
   llmi_act_t act = nullptr;
   uint8_t* scratch = nullptr;
   size_t scratch_cap = 0;
+  uint8_t* tok_act = nullptr;  // quantized activations of a token batch (llmi_gemm_tokens)
+  size_t tok_act_cap = 0;
   std::map<std::tuple<const void*, uint32_t, uint64_t, uint64_t>, llmi_weight_t> registry;
 };
 Context g;
@@ -365,6 +368,29 @@ int llmi_gemv_batch(const llmi_weight_t* ws, float* const* outs, int n, llmi_act
 int llmi_mat_vec_mul_dev(llmi_weight_t w, const float* x, llmi_act_t a, float* out, llmi_stream_t s) {
   if (int rc = llmi_act_prepare(w, x, a, s)) return rc;
   return llmi_gemv(w, a, out, s);
+}
+
+// Token-batched mat-vec (prefill), device tier: out[m][rows of w] = W * x[m] for m < n_tokens.  The activations
+// are quantized as the format requires (one kernel over all tokens) into a library-owned buffer, then the
+// token-batched kernels run (gemv.cu).  Bit-identical to n_tokens calls of llmi_mat_vec_mul_dev.
+int llmi_gemm_tokens(llmi_weight_t w, const float* x, uint32_t n_tokens, float* out, llmi_stream_t stream) {
+  LLMI_NEED_INIT();
+  if (!w || !x || !out) return llmi_fail(LLMI_ERR_ARG, "llmi_gemm_tokens: null pointer");
+  if (n_tokens == 0 || w->n_local == 0) return LLMI_OK;
+  const int kind = llmi_act_kind_for(w->type);
+  if (kind == ACT_NONE) return llmi_fail(LLMI_ERR_TYPE, "llmi_gemm_tokens: unsupported tensor type");
+  if (kind == ACT_Q8_K && w->n_cols % 256 != 0)
+    return llmi_fail(LLMI_ERR_SIZE, "mat_vec_mul: n_cols must be a multiple of 256");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);  // NULL: the default stream, like the other device-tier calls
+  const size_t stride = act_bytes(kind, w->n_cols);
+  if (stride * n_tokens > g.tok_act_cap) LLMI_CUDA_TRY(cudaStreamSynchronize(s));
+  if (int rc = ensure_cap((void**)&g.tok_act, &g.tok_act_cap, stride * n_tokens)) return rc;
+  LLMI_CUDA_TRY(llmi_launch_act(x, uint32_t(w->n_cols), kind, g.tok_act, s, n_tokens, uint32_t(stride)));
+  const llmi_weight_s* ws[1] = {w};
+  float* outs[1] = {out};
+  const uint32_t strides[1] = {uint32_t(w->n_rows)};
+  LLMI_CUDA_TRY(llmi_launch_gemv_tokens(ws, outs, strides, 1, kind, w->n_cols, g.tok_act, n_tokens, s));
+  return LLMI_OK;
 }
 
 int llmi_debug_block_dots(llmi_weight_t w, llmi_act_t a, int32_t* dots_host) {

@@ -192,9 +192,11 @@ __global__ void __launch_bounds__(1024) norm_act_kernel(NormArgs a) {
 }
 
 // Generic multi-CTA quantizer of a device vector (after attention).
-__global__ void act_kernel(const float* __restrict__ x, uint32_t n, int kind, uint8_t* buf) {
+__global__ void act_kernel(const float* __restrict__ x, uint32_t n, int kind, uint8_t* buf, uint32_t act_stride) {
   pdl_trigger();
   pdl_wait();
+  x += size_t(blockIdx.y) * n;  // blockIdx.y: vector of a token batch
+  buf += size_t(blockIdx.y) * act_stride;
   const int lane = threadIdx.x & 31;
   const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
   if (kind == ACT_Q8_0) {
@@ -777,10 +779,11 @@ cudaError_t llmi_launch_norm_act(const NormArgs& a, cudaStream_t s) {
   return llmi_launch(norm_act_kernel, dim3(a.n_tok ? a.n_tok : 1), dim3(threads), a.n * sizeof(float), s, a);
 }
 
-cudaError_t llmi_launch_act(const float* x, uint32_t n, int kind, uint8_t* buf, cudaStream_t s) {
+cudaError_t llmi_launch_act(const float* x, uint32_t n, int kind, uint8_t* buf, cudaStream_t s, uint32_t n_tok,
+                            uint32_t act_stride) {
   const uint32_t warps = kind == ACT_Q8_0 ? n / 32 : (kind == ACT_Q8_K ? n / 256 : (n + 31) / 32);
   const uint32_t blocks = (warps + 7) / 8 ? (warps + 7) / 8 : 1;
-  return llmi_launch(act_kernel, dim3(blocks), dim3(256), 0, s, x, n, kind, buf);
+  return llmi_launch(act_kernel, dim3(blocks, n_tok), dim3(256), 0, s, x, n, kind, buf, act_stride);
 }
 
 cudaError_t llmi_launch_rope_table(float2* table, uint32_t t_max, uint32_t D, float base, float scale, cudaStream_t s) {

@@ -54,7 +54,8 @@ struct AttnArgs {
 cudaError_t llmi_launch_embed(const EmbedArgs& a, const int32_t* token, float scale, float* h, cudaStream_t s,
                               uint32_t n_tok = 1);
 cudaError_t llmi_launch_norm_act(const NormArgs& a, cudaStream_t s);
-cudaError_t llmi_launch_act(const float* x, uint32_t n, int kind, uint8_t* buf, cudaStream_t s);
+cudaError_t llmi_launch_act(const float* x, uint32_t n, int kind, uint8_t* buf, cudaStream_t s, uint32_t n_tok = 1,
+                            uint32_t act_stride = 0);
 cudaError_t llmi_launch_rope_table(float2* table, uint32_t t_max, uint32_t D, float base, float scale, cudaStream_t s);
 size_t llmi_attention_smem(uint32_t t_max, uint32_t D);
 cudaError_t llmi_attention_init(uint32_t t_max, uint32_t D);

@@ -186,6 +186,11 @@ def mat_vec_mul_dev(w: DeviceWeight, x: DeviceVector, act: Activation, out: Devi
     _lib.check(_lib.load().llmi_mat_vec_mul_dev(w.h, x.p, act.h, out.p, stream))
 
 
+def gemm_tokens(w: DeviceWeight, xs: DeviceVector, n_tokens: int, out: DeviceVector, stream=None) -> None:
+    """Token-batched mat-vec (prefill): xs = [n_tokens][n_cols], out = [n_tokens][n_rows] (llmi_gemm_tokens)."""
+    _lib.check(_lib.load().llmi_gemm_tokens(w.h, xs.p, n_tokens, out.p, stream))
+
+
 def block_dots(w: DeviceWeight, act: Activation) -> np.ndarray:
     per = {Q4_0: w.n_cols // 32, Q8_0: w.n_cols // 32, Q4_K: w.n_cols // 32, Q6_K: w.n_cols // 128}[w.type]
     out = np.zeros((w.row_end - w.row_begin) * per, np.int32)

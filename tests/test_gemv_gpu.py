@@ -304,3 +304,40 @@ def test_batched_launch_equals_separate_launches(gpu_ops, port):
     act.prepare(w4, dx)
     with pytest.raises(RuntimeError, match="share one format"):
         ops.gemv_batch([w4, w8], act, [ops.DeviceVector(8), ops.DeviceVector(8)])
+
+
+@pytest.mark.parametrize("t", [synth.Q4_0, synth.Q8_0, synth.Q4_K, synth.Q6_K, synth.Q5_0, synth.BF16, synth.F16])
+def test_token_batched_matvec_is_bitwise_n_single_calls(gpu_ops, t):
+    """llmi_gemm_tokens (prefill) == n_tokens x llmi_mat_vec_mul_dev, bit for bit: ragged N, partial last
+    K-chunk, token counts on both sides of the kernel switch (token loop < 16 <= token-per-lane) and of
+    the tile / lane-group sizes, and a row-shard handle."""
+    ops = gpu_ops
+    kq = t in (synth.Q4_K, synth.Q6_K)
+    for k, n in ((512, 40), (1280 if kq else 1184, 203), (2560 if kq else 2592, 77)):
+        w_host = synth.random_blocks(t, n, k, seed=k + n)
+        w = ops.DeviceWeight(w_host, t, k, n)
+        from llm_inference_b200.shard import shard_blocks
+        shard = ops.DeviceWeight(shard_blocks(w_host, synth.row_bytes(t, k), (8, 32)), t, k, n, 8, 32,
+                                 blocks_are_shard=True)
+        act = ops.Activation(k)
+        for m in (1, 5, 16, 37, 70):
+            x = np.random.default_rng(m).standard_normal((m, k)).astype(np.float32)
+            x[0, :32] = 0.0  # an all-zero block
+            xs, out = ops.DeviceVector(m * k, x), ops.DeviceVector(m * n, np.full(m * n, np.nan, np.float32))
+            ops.gemm_tokens(w, xs, m, out)
+            got = out.get().reshape(m, n)
+            one, o1 = ops.DeviceVector(k), ops.DeviceVector(n)
+            for i in range(m):
+                one.set(x[i])
+                ops.mat_vec_mul_dev(w, one, act, o1)
+                assert np.array_equal(got[i].view(np.uint32), o1.get().view(np.uint32)), (t, k, n, m, i)
+            out.set(np.full(m * n, np.nan, np.float32))
+            ops.gemm_tokens(shard, xs, m, out)
+            part = out.get().reshape(m, n)
+            assert np.array_equal(part[:, 8:32].view(np.uint32), got[:, 8:32].view(np.uint32))
+            assert np.isnan(part[:, :8]).all() and np.isnan(part[:, 32:]).all()
+            for v in (xs, out, one, o1):
+                v.close()
+        act.close()
+        w.close()
+        shard.close()
