@@ -446,16 +446,31 @@ struct GemvBatch {
   int n;
 };
 
+#ifdef LLMI_GEMV_TIMING  // dev only (tools/gemv_chain_bench.py): %globaltimer stamps of CTA 0 / thread 0 per launch
+__device__ unsigned long long g_gemv_stamp[256][6];
+__device__ unsigned int g_gemv_launch;
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define GEMV_STAMP(slot, i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_gemv_stamp[(slot) & 255][i] = gtime(); } while (0)
+#else
+#define GEMV_STAMP(slot, i) do { } while (0)
+#endif
+
 // Called by every thread after its first weight loads are in flight: wait for
 // the predecessor grid (PDL), let thread 0 start the bulk copy of the activation
 // vector it produced, wait for the bytes to land.
-__device__ __forceinline__ void stage_activation(const GemvArgs& a, uint8_t* sm_act, uint64_t* bar) {
+__device__ __forceinline__ void stage_activation(const GemvArgs& a, uint8_t* sm_act, uint64_t* bar, unsigned slot = 0) {
   pdl_wait();
+  GEMV_STAMP(slot, 1);
   if (threadIdx.x == 0) {
     mbar_expect_tx(bar, a.act_bytes);
     bulk_g2s(sm_act, a.act, a.act_bytes, bar);
   }
   mbar_wait(bar, 0);
+  GEMV_STAMP(slot, 2);
 }
 
 template <class B, int W>
@@ -470,6 +485,14 @@ __global__ void __launch_bounds__(W * 32) gemv_slab_kernel(const GemvBatch batch
   const uint32_t S = batch.S[mi];
   const uint32_t cta = blockIdx.x - (mi ? batch.cta_end[mi - 1] : 0u);
   pdl_trigger();
+#ifdef LLMI_GEMV_TIMING
+  __shared__ unsigned slot_s;
+  if (blockIdx.x == 0 && threadIdx.x == 0) slot_s = atomicAdd(&g_gemv_launch, 1u);
+#define SLOT (slot_s)
+#else
+#define SLOT 0u
+#endif
+  GEMV_STAMP(SLOT, 0);
   if (threadIdx.x == 0) mbar_init(&bar, 1);
   __syncthreads();
   constexpr int N = B::C;
@@ -485,14 +508,15 @@ __global__ void __launch_bounds__(W * 32) gemv_slab_kernel(const GemvBatch batch
     FragSet<B, N> f;
     load_item<B, N>(f, a, slab0 + sl, j, r, sub);  // weights: independent of the predecessor kernel
     if (!waited) {
-      stage_activation(a, sm_act, &bar);
+      stage_activation(a, sm_act, &bar, SLOT);
       waited = true;
     }
     const float v = compute_item<B, N>(f, a, sm_act, j, sub);
     if (lane < LLMI_SLAB) part[t * LLMI_SLAB + lane] = v;
   }
-  if (!waited) stage_activation(a, sm_act, &bar);  // never exit with the bulk copy into our smem in flight
+  if (!waited) stage_activation(a, sm_act, &bar, SLOT);  // never exit with the bulk copy into our smem in flight
   __syncthreads();
+  GEMV_STAMP(SLOT, 3);
   unsigned long long best = 0;
   for (uint32_t idx = threadIdx.x; idx < n_sl * LLMI_SLAB; idx += W * 32) {
     const uint32_t sl = idx / LLMI_SLAB, rr = idx % LLMI_SLAB;
@@ -520,7 +544,10 @@ __global__ void __launch_bounds__(W * 32) gemv_slab_kernel(const GemvBatch batch
     }
     if (lane == 0 && best) atomicMax(a.argmax_key, best);
   }
+  GEMV_STAMP(SLOT, 4);
+#undef SLOT
 }
+
 
 // ------------------------------------------------------ token-batched (prefill)
 // The same work decomposition for M tokens at once: a warp loads the weights
@@ -1142,3 +1169,15 @@ cudaError_t llmi_launch_block_dots(const llmi_weight_s& w, const llmi_act_s& a, 
   block_dots_kernel<<<unsigned((total + 255) / 256), 256, 0, s>>>(g, w.type, dots_dev);
   return cudaGetLastError();
 }
+
+#ifdef LLMI_GEMV_TIMING
+extern "C" int llmi_debug_gemv_stamps(unsigned long long* out /*[256][6]*/, unsigned* n_launches, int reset) {
+  if (out) cudaMemcpyFromSymbol(out, g_gemv_stamp, sizeof(unsigned long long) * 256 * 6);
+  if (n_launches) cudaMemcpyFromSymbol(n_launches, g_gemv_launch, 4);
+  if (reset) {
+    const unsigned z = 0;
+    cudaMemcpyToSymbol(g_gemv_launch, &z, 4);
+  }
+  return 0;
+}
+#endif
