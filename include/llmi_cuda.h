@@ -133,6 +133,10 @@ int llmi_mat_vec_mul_dev(llmi_weight_t w, const float* x_dev, llmi_act_t a,
  * CTA (4, 8 or 16) and consecutive 8-row slabs per CTA; 0 = heuristic.  Results
  * never depend on it (canonical summation order). */
 int llmi_set_gemv_shape(int warps, int slabs_per_cta);
+/* Tuning knob for benches (A/B): 1 (default) = every mat-vec CTA asks the copy engine to pull its whole weight
+ * range into L2 before it blocks on its predecessor (cp.async.bulk.prefetch.L2); 0 = off.  Also read once from
+ * the environment (LLMI_GEMV_PREFETCH) by llmi_init.  Results never depend on it. */
+int llmi_set_gemv_prefetch(int mode);
 
 /* Token-batched mat-vec (prefill; the M >= 16 entry SURVEY §8b calls llmi_gemm_prefill): x_dev is
  * [n_tokens][n_cols] fp32, out_dev [n_tokens][n_rows] fp32 (a row-shard handle fills its own rows).  The
@@ -169,6 +173,22 @@ typedef struct llmi_model_s* llmi_model_t;
  * Architecture "gemma3" only; anything else returns LLMI_ERR_TYPE (use the
  * ops.h drop-in with the reference's model.cpp for those). */
 int llmi_model_load(const void* gguf_image, uint64_t size, uint32_t max_positions, llmi_model_t* out);
+/* Row-sharded model over `world` GPUs of one node, one process (or host thread) per GPU: rank
+ * `rank` uploads a contiguous, slab-aligned range of the output rows of EVERY matrix — the thread partition of
+ * ops.cpp:439-448 lifted to devices — and keeps activations, norms, attention and the KV cache replicated.  The
+ * vectors the mat-vecs produce are exchanged by the mat-vec kernels themselves: each output row is written,
+ * together with a tag, by one 64-bit store into an exchange buffer on every rank over NVLink peer memory, and
+ * the consuming kernel spins on the tag — no collective call, no extra launch.  A row is computed
+ * start to finish on one device in the canonical order, so logits and tokens are bit-identical to world = 1.
+ * Wiring: every rank calls llmi_model_comm_handle, the host all-gathers the 64-byte handles (torch.distributed,
+ * MPI, ...), every rank calls llmi_model_comm_connect with the world x 64 bytes in rank order.  All ranks must
+ * then make the same forward / decode calls.  world = 1 is llmi_model_load. */
+int llmi_model_load_shard(const void* gguf_image, uint64_t size, uint32_t max_positions, int world, int rank,
+                          llmi_model_t* out);
+int llmi_model_comm_handle(llmi_model_t m, void* handle64);
+int llmi_model_comm_connect(llmi_model_t m, const void* handles);
+/* 1 if a kernel of this rank gave up (after ~4 s) waiting for a peer's rows; results are then invalid. */
+int llmi_model_comm_error(llmi_model_t m);
 int llmi_model_free(llmi_model_t m);
 /* dims[8] = {n_layer, n_embd, n_ff, n_head, n_head_kv, head_dim, vocab, max_positions} */
 int llmi_model_info(llmi_model_t m, uint32_t* dims, uint64_t* weight_bytes);

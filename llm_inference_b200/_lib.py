@@ -43,11 +43,16 @@ SIGNATURES = {
     "llmi_gemv_batch": (_int, [_vp, _vp, _int, _vp, _vp]),
     "llmi_mat_vec_mul_dev": (_int, [_vp, _vp, _vp, _vp, _vp]),
     "llmi_set_gemv_shape": (_int, [_int, _int]),
+    "llmi_set_gemv_prefetch": (_int, [_int]),
     "llmi_debug_block_dots": (_int, [_vp, _vp, _vp]),
     "llmi_host_mat_vec_mul": (_int, [_vp, _vp, _u64, _vp, _u64]),
     "llmi_host_quantize_row_q8_0": (_int, [_vp, _u64, _vp]),
     "llmi_host_quantize_row_q8_k": (_int, [_vp, _u64, _vp]),
     "llmi_model_load": (_int, [_vp, _u64, _u32, C.POINTER(_vp)]),
+    "llmi_model_load_shard": (_int, [_vp, _u64, _u32, _int, _int, C.POINTER(_vp)]),
+    "llmi_model_comm_handle": (_int, [_vp, _vp]),
+    "llmi_model_comm_connect": (_int, [_vp, _vp]),
+    "llmi_model_comm_error": (_int, [_vp]),
     "llmi_model_free": (_int, [_vp]),
     "llmi_model_info": (_int, [_vp, C.POINTER(_u32), C.POINTER(_u64)]),
     "llmi_model_forward": (_int, [_vp, _vp, _int, _int, _vp]),

@@ -72,6 +72,11 @@ struct GemvArgs {
   // token-batched launches (prefill): n_tok activation buffers act_stride bytes apart, outputs out_stride floats apart
   uint32_t n_tok, act_stride, out_stride;
   float* part;  // token-per-lane kernel: chunk partials [chunk][token][8 * n_slabs] of this matrix
+  // bytes per slab of the q / d / x planes (0 = no L2 prefetch of the CTA's weight region)
+  uint32_t pf_q, pf_d, pf_x;
+  // row-sharded model: element offset of this matrix' output vector inside the exchange buffer of every rank
+  // (LL_NONE: plain local store to `out`)
+  uint32_t ll_off;
 };
 
 // ------------------------------------------------ integer block dot products
@@ -444,6 +449,8 @@ struct GemvBatch {
   uint32_t cta_end[GEMV_MAX_BATCH];  // exclusive prefix of CTAs per matrix
   uint32_t S[GEMV_MAX_BATCH];        // slabs per CTA
   int n;
+  LLPeers peers;  // exchange buffers of all ranks (launch.cuh); used by matrices with ll_off != LL_NONE
+  LLTag tag;
 };
 
 #ifdef LLMI_GEMV_TIMING  // dev only (tools/gemv_chain_bench.py): %globaltimer stamps of CTA 0 / thread 0 per launch
@@ -462,6 +469,27 @@ __device__ __forceinline__ unsigned long long gtime() {
 // Called by every thread after its first weight loads are in flight: wait for
 // the predecessor grid (PDL), let thread 0 start the bulk copy of the activation
 // vector it produced, wait for the bytes to land.
+// L2 prefetch of a contiguous, 16-byte-multiple region (cp.async.bulk.prefetch -> UBLKPF): no destination,
+// no completion to wait for.
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
+// A CTA's weights are one contiguous range per plane (slab-major layout).  One
+// thread asks the copy engine to pull the whole range into L2 BEFORE the CTA
+// blocks on its predecessor: weights depend on nothing, so DRAM keeps streaming
+// through the tail of the previous grid, the PDL hand-over and the activation
+// staging, and every load after the first finds its line in L2 or in flight.
+__device__ __forceinline__ void prefetch_cta_weights(const GemvArgs& a, uint32_t slab0, uint32_t n_sl) {
+  if (!a.pf_q) return;
+  for (uint32_t s = 0; s < n_sl; ++s) {
+    const size_t sl = slab0 + s;
+    bulk_prefetch_l2(a.q + sl * a.pf_q, a.pf_q);
+    if (a.pf_d) bulk_prefetch_l2(a.d + sl * a.pf_d, a.pf_d);
+    if (a.pf_x) bulk_prefetch_l2(a.x + sl * a.pf_x, a.pf_x);
+  }
+}
+
 __device__ __forceinline__ void stage_activation(const GemvArgs& a, uint8_t* sm_act, uint64_t* bar, unsigned slot = 0) {
   pdl_wait();
   GEMV_STAMP(slot, 1);
@@ -508,6 +536,7 @@ __global__ void __launch_bounds__(W * 32) gemv_slab_kernel(const GemvBatch batch
     FragSet<B, N> f;
     load_item<B, N>(f, a, slab0 + sl, j, r, sub);  // weights: independent of the predecessor kernel
     if (!waited) {
+      if (threadIdx.x == 32) prefetch_cta_weights(a, slab0, n_sl);
       stage_activation(a, sm_act, &bar, SLOT);
       waited = true;
     }
@@ -518,6 +547,8 @@ __global__ void __launch_bounds__(W * 32) gemv_slab_kernel(const GemvBatch batch
   __syncthreads();
   GEMV_STAMP(SLOT, 3);
   unsigned long long best = 0;
+  const bool push = a.ll_off != LL_NONE;
+  const uint32_t tag = push ? ll_tag(batch.tag) : 0u;  // every thread is past pdl_wait here
   for (uint32_t idx = threadIdx.x; idx < n_sl * LLMI_SLAB; idx += W * 32) {
     const uint32_t sl = idx / LLMI_SLAB, rr = idx % LLMI_SLAB;
     const float* p = part + (size_t)sl * J * LLMI_SLAB + rr;
@@ -533,7 +564,12 @@ __global__ void __launch_bounds__(W * 32) gemv_slab_kernel(const GemvBatch batch
         const unsigned long long k = (uint64_t(u) << 32) | uint32_t(0xffffffffu - (a.row0 + row));
         best = k > best ? k : best;
       }
-      a.out[row] = sum;
+      if (push) {  // the all-gather IS this store: one flagged 64-bit write into every rank's copy of the vector
+        for (uint32_t p = 0; p < batch.peers.n; ++p)
+          ll_store(batch.peers.base[p] + a.ll_off + a.row0 + row, __float_as_uint(sum), tag);
+      } else {
+        a.out[row] = sum;
+      }
     }
   }
   if (a.argmax_key) {  // one atomicMax per warp that saw rows (max is order-independent: deterministic)
@@ -824,6 +860,7 @@ using BF16 = BodyHalf<true>;
 // Benches can pin the CTA shape: g_warps in {0 (heuristic), 4, 8, 16},
 // g_slabs_per_cta in {0 (heuristic), 1..}.  Results never depend on it.
 int g_warps = 0, g_slabs_per_cta = 0;
+int g_prefetch = 1;  // L2 prefetch of each CTA's weight range ahead of the PDL wait (LLMI_GEMV_PREFETCH=0 turns it off)
 
 // (W, S) for one matrix.  Heuristic from tools/gemv_sweep.py
 // (profiles/r01_sweep_v4.jsonl): one slab per CTA and the fewest warps per CTA
@@ -847,9 +884,13 @@ void pick_shape(const GemvArgs& a, uint64_t slabs_in_launch, int& W, uint32_t& S
 }
 
 template <class B>
-cudaError_t launch_batch(const GemvArgs* args, int n, cudaStream_t s) {
+cudaError_t launch_batch(const GemvArgs* args, int n, cudaStream_t s, const GemvLL* ll) {
   GemvBatch b;
   b.n = n;
+  if (ll) {
+    b.peers = ll->peers;
+    b.tag = ll->tag;
+  }
   uint64_t slabs = 0;
   for (int i = 0; i < n; ++i) slabs += args[i].n_slabs;
   int W = 4;
@@ -1026,6 +1067,8 @@ uint32_t llmi_gemv_chunks(const llmi_weight_s& w) {
   return (u + c - 1) / c;
 }
 
+void llmi_gemv_set_prefetch(int mode) { g_prefetch = mode; }
+
 void llmi_gemv_set_shape(int warps, int slabs_per_cta) {
   g_warps = warps;
   g_slabs_per_cta = slabs_per_cta;
@@ -1072,6 +1115,23 @@ static GemvArgs make_args(const llmi_weight_s& w, const llmi_act_s& a, float* ou
   g.act_stride = g.act_bytes;
   g.out_stride = 0;
   g.part = nullptr;
+  g.ll_off = LL_NONE;
+  g.pf_q = g.pf_d = g.pf_x = 0;
+  if (g_prefetch) {
+    uint32_t q = 16, d = 0, x = 0;  // bytes per (unit, row) cell of each plane, as laid out by llmi_plan_planes
+    switch (w.type) {
+      case LLMI_Q4_0: q = 16; d = 2; break;
+      case LLMI_Q8_0: q = 32; d = 2; break;
+      case LLMI_Q5_0: q = 16; d = 2; x = 4; break;
+      case LLMI_Q4_K: q = 128; x = 16; break;
+      case LLMI_Q6_K: q = 192; d = 2; x = 16; break;
+      default: break;
+    }
+    const uint32_t cells = uint32_t(w.nb) * LLMI_SLAB;
+    g.pf_q = cells * q;
+    g.pf_d = cells * d;
+    g.pf_x = cells * x;
+  }
   return g;
 }
 
@@ -1082,7 +1142,7 @@ static float g_argmax_softcap = 0.0f;
 // One launch for up to GEMV_MAX_BATCH matrices of the SAME format consuming the
 // same prepared activation (q/k/v, gate/up): the grid is the union of their CTAs.
 cudaError_t llmi_launch_gemv_batch(const llmi_weight_s* const* ws, float* const* outs, int n, const llmi_act_s& a,
-                                   cudaStream_t s) {
+                                   cudaStream_t s, const GemvLL* ll) {
   if (n < 1 || n > GEMV_MAX_BATCH) return cudaErrorInvalidValue;
   GemvArgs args[GEMV_MAX_BATCH];
   int m = 0;
@@ -1092,18 +1152,19 @@ cudaError_t llmi_launch_gemv_batch(const llmi_weight_s* const* ws, float* const*
     args[m] = make_args(*ws[i], a, outs[i]);
     args[m].argmax_key = g_argmax_key;
     args[m].softcap = g_argmax_softcap;
+    if (ll) args[m].ll_off = ll->off[i];
     if (args[m].act_bytes > (uint32_t)MAX_DYN_SMEM) return cudaErrorInvalidValue;
     ++m;
   }
   if (m == 0) return cudaSuccess;
   switch (ws[0]->type) {
-    case LLMI_Q4_0: return launch_batch<Q4_0>(args, m, s);
-    case LLMI_Q8_0: return launch_batch<Q8_0>(args, m, s);
-    case LLMI_Q5_0: return launch_batch<Q5_0>(args, m, s);
-    case LLMI_Q4_K: return launch_batch<Q4_K>(args, m, s);
-    case LLMI_Q6_K: return launch_batch<Q6_K>(args, m, s);
-    case LLMI_F16: return launch_batch<F16>(args, m, s);
-    case LLMI_BF16: return launch_batch<BF16>(args, m, s);
+    case LLMI_Q4_0: return launch_batch<Q4_0>(args, m, s, ll);
+    case LLMI_Q8_0: return launch_batch<Q8_0>(args, m, s, ll);
+    case LLMI_Q5_0: return launch_batch<Q5_0>(args, m, s, ll);
+    case LLMI_Q4_K: return launch_batch<Q4_K>(args, m, s, ll);
+    case LLMI_Q6_K: return launch_batch<Q6_K>(args, m, s, ll);
+    case LLMI_F16: return launch_batch<F16>(args, m, s, ll);
+    case LLMI_BF16: return launch_batch<BF16>(args, m, s, ll);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -1152,10 +1213,12 @@ cudaError_t llmi_launch_gemv(const llmi_weight_s& w, const llmi_act_s& a, float*
 // ~row, so the maximum is the first index of the largest logit).  The caller
 // zeroes *key before and decodes it after (finish_token_kernel, glue.cu).
 cudaError_t llmi_launch_gemv_argmax(const llmi_weight_s& w, const llmi_act_s& a, float* out,
-                                    unsigned long long* key, float softcap, cudaStream_t s) {
+                                    unsigned long long* key, float softcap, cudaStream_t s, const GemvLL* ll) {
   g_argmax_key = key;
   g_argmax_softcap = softcap;
-  const cudaError_t e = llmi_launch_gemv(w, a, out, s);
+  const llmi_weight_s* ws[1] = {&w};
+  float* outs[1] = {out};
+  const cudaError_t e = llmi_launch_gemv_batch(ws, outs, 1, a, s, ll);
   g_argmax_key = nullptr;
   g_argmax_softcap = 0.0f;
   return e;

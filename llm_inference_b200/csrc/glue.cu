@@ -67,12 +67,24 @@ __device__ float dequant_elem(const EmbedArgs& a, uint32_t row, uint32_t e) {
 }
 
 // embed_tokens + scale_embeddings (model.cpp:240-344): h = dequant(row) * sqrt(float(E))
-__global__ void embed_kernel(EmbedArgs a, const int32_t* __restrict__ token, float scale, float* __restrict__ h) {
+// Row-sharded model (ll.peers.n > 0, one token): the rank that holds the token's row sends it to everybody.
+__global__ void embed_kernel(EmbedArgs a, const int32_t* __restrict__ token, float scale, float* __restrict__ h,
+                             LLCtx ll, uint32_t ll_off) {
   pdl_trigger();
   pdl_wait();
   const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x, m = blockIdx.y;  // m: token of a prefill batch
   if (e >= a.n_cols) return;
-  h[size_t(m) * a.n_cols + e] = dequant_elem(a, uint32_t(token[m]), e) * scale;
+  const uint32_t row = uint32_t(token[m]);
+  if (ll.peers.n == 0) {
+    h[size_t(m) * a.n_cols + e] = dequant_elem(a, row, e) * scale;
+    return;
+  }
+  const uint32_t tag = ll_tag(ll.tag);
+  if (row >= a.row_begin && row < a.row_end) {
+    const float v = dequant_elem(a, row - a.row_begin, e) * scale;
+    for (uint32_t p = 0; p < ll.peers.n; ++p) ll_store(ll.peers.base[p] + ll_off + e, __float_as_uint(v), tag);
+  }
+  h[e] = ll_waitf(ll.peers.base[ll.rank] + ll_off + e, tag, ll.tag.err);
 }
 
 // ----------------------------------------------------------------- reductions
@@ -147,19 +159,21 @@ __global__ void __launch_bounds__(1024) norm_act_kernel(NormArgs a) {
   for (int k = 0; k < NORM_PER; ++k) {  // norm weights are static: fetch them under the predecessor's tail
     const uint32_t i = threadIdx.x + k * blockDim.x;
     const bool ok = i < n;
-    wp[k] = (ok && a.y && a.w_post) ? a.w_post[i] : 0.0f;
+    wp[k] = (ok && (a.y || a.ll_y) && a.w_post) ? a.w_post[i] : 0.0f;
     wn[k] = (ok && a.w) ? a.w[i] : 0.0f;
   }
   pdl_wait();
+  const uint32_t tag = a.ll_y ? ll_tag(a.ll_tag) : 0u;
 #pragma unroll
   for (int k = 0; k < NORM_PER; ++k) {
     const uint32_t i = threadIdx.x + k * blockDim.x;
     const bool ok = i < n;
     hv[k] = ok ? a.h[i] : 0.0f;
-    yv[k] = (ok && a.y) ? a.y[i] : 0.0f;
+    if (a.ll_y) yv[k] = ok ? ll_waitf(a.ll_y + i, tag, a.ll_tag.err) : 0.0f;  // one decode token, grid = 1
+    else yv[k] = (ok && a.y) ? a.y[i] : 0.0f;
   }
   if (a.pos_inc && threadIdx.x == 0 && blockIdx.x == 0) *a.pos_inc += int32_t(gridDim.x);
-  if (a.y) {
+  if (a.y || a.ll_y) {
     float ss = 0.0f;
 #pragma unroll
     for (int k = 0; k < NORM_PER; ++k) ss += __fmul_rn(yv[k], yv[k]);
@@ -172,6 +186,8 @@ __global__ void __launch_bounds__(1024) norm_act_kernel(NormArgs a) {
       hv[k] = __fadd_rn(hv[k], add);
       if (i < n) a.h[i] = hv[k];
     }
+    // every thread read the epoch before block_sum's barriers: safe to open the next step's epoch now
+    if (a.epoch_inc && threadIdx.x == 0) *a.epoch_inc += 1u;
   }
   if (!a.w) return;
   float ss = 0.0f;
@@ -371,7 +387,16 @@ __global__ void __launch_bounds__(1024) attention_kernel(AttnArgs a, uint32_t nb
   } else {
   float q0 = 0.0f, q1 = 0.0f, k0 = 0.0f, k1 = 0.0f, v0 = 0.0f, v1 = 0.0f;
   float2 csn = make_float2(1.0f, 0.0f);
-  if (pair) {
+  if (pair && a.ll_q) {  // row-sharded model: the q/k/v rows of every rank land in the exchange buffer
+    const uint32_t tag = ll_tag(a.ll_tag);
+    q0 = ll_waitf(a.ll_q + h * D + i, tag, a.ll_tag.err);
+    q1 = ll_waitf(a.ll_q + h * D + i + HALF, tag, a.ll_tag.err);
+    k0 = ll_waitf(a.ll_k + hkv * D + i, tag, a.ll_tag.err);
+    k1 = ll_waitf(a.ll_k + hkv * D + i + HALF, tag, a.ll_tag.err);
+    v0 = ll_waitf(a.ll_v + hkv * D + i, tag, a.ll_tag.err);
+    v1 = ll_waitf(a.ll_v + hkv * D + i + HALF, tag, a.ll_tag.err);
+    csn = a.rope_table[size_t(pos) * HALF + i];
+  } else if (pair) {
     q0 = a.q[h * D + i];
     q1 = a.q[h * D + i + HALF];
     k0 = a.k[hkv * D + i];
@@ -700,19 +725,33 @@ __device__ __forceinline__ float geglu(float x, float up) {
   return __fmul_rn(g, up);
 }
 
+// One element pair (gate, up): plain vectors, or the flagged exchange buffers of a row-sharded model.
+struct GegluIn {
+  const float *gate, *up;
+  const uint2 *ll_gate, *ll_up;
+  uint32_t tag;
+  uint32_t* err;
+  __device__ __forceinline__ float operator()(uint32_t e) const {
+    if (ll_gate) return geglu(ll_waitf(ll_gate + e, tag, err), ll_waitf(ll_up + e, tag, err));
+    return geglu(gate[e], up[e]);
+  }
+};
+
 __global__ void geglu_act_kernel(const float* __restrict__ gate, const float* __restrict__ up, uint32_t n, int kind,
-                                 uint8_t* buf, float* hidden_out, uint32_t act_stride) {
+                                 uint8_t* buf, float* hidden_out, uint32_t act_stride, const uint2* ll_gate,
+                                 const uint2* ll_up, LLTag lltag) {
   pdl_trigger();
   pdl_wait();
   gate += size_t(blockIdx.y) * n;  // blockIdx.y: token of a prefill batch
   up += size_t(blockIdx.y) * n;
+  const GegluIn in{gate, up, ll_gate, ll_up, ll_gate ? ll_tag(lltag) : 0u, lltag.err};
   buf += size_t(blockIdx.y) * act_stride;
   if (hidden_out) hidden_out += size_t(blockIdx.y) * n;
   const int lane = threadIdx.x & 31;
   const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
   if (kind == ACT_Q8_0) {
     for (uint32_t b = gw; b < n / 32; b += nw) {
-      const float v = geglu(gate[b * 32 + lane], up[b * 32 + lane]);
+      const float v = in(b * 32 + lane);
       if (hidden_out) hidden_out[b * 32 + lane] = v;
       warp_quantize_q8_0(v, b, n, buf, lane);
     }
@@ -722,7 +761,7 @@ __global__ void geglu_act_kernel(const float* __restrict__ gate, const float* __
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const uint32_t e = sb * 256 + lane * 8 + i;
-        v[i] = geglu(gate[e], up[e]);
+        v[i] = in(e);
         if (hidden_out) hidden_out[e] = v[i];
       }
       warp_quantize_q8_k(v, sb, n, buf, lane);
@@ -730,7 +769,7 @@ __global__ void geglu_act_kernel(const float* __restrict__ gate, const float* __
   } else {
     const uint32_t n_pad = kind == ACT_F16 ? ((n + 7) & ~7u) : ((n + 3) & ~3u);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x) {
-      const float v = i < n ? geglu(gate[i], up[i]) : 0.0f;
+      const float v = i < n ? in(i) : 0.0f;
       if (hidden_out && i < n) hidden_out[i] = v;
       if (kind == ACT_F16) reinterpret_cast<uint16_t*>(buf)[i] = f2h(v);
       else reinterpret_cast<float*>(buf)[i] = v;
@@ -744,11 +783,29 @@ __global__ void geglu_act_kernel(const float* __restrict__ gate, const float* __
 // the logits mat-vec (gemv.cu), which leaves a 64-bit key = ordered value bits
 // << 32 | ~index.  This kernel turns the key into the next token, appends it to
 // the generated list and re-arms the key.
-__global__ void finish_token_kernel(unsigned long long* key, int32_t* cur_tok, int32_t* gen, int32_t* gen_count) {
+// Row-sharded model: *key covers this rank's rows only; the ranks swap keys through the flagged exchange buffer
+// (two words per rank) and every rank takes the maximum — the same token everywhere.
+__global__ void finish_token_kernel(unsigned long long* key, int32_t* cur_tok, int32_t* gen, int32_t* gen_count,
+                                    LLCtx ll, uint32_t ll_off) {
   pdl_trigger();
   pdl_wait();
   if (threadIdx.x == 0) {
-    const int32_t tok = int32_t(0xffffffffu - uint32_t(*key));
+    unsigned long long best = *key;
+    if (ll.peers.n) {
+      const uint32_t tag = ll_tag(ll.tag);
+      for (uint32_t p = 0; p < ll.peers.n; ++p) {
+        ll_store(ll.peers.base[p] + ll_off + 2 * ll.rank, uint32_t(best >> 32), tag);
+        ll_store(ll.peers.base[p] + ll_off + 2 * ll.rank + 1, uint32_t(best), tag);
+      }
+      const uint2* mine = ll.peers.base[ll.rank] + ll_off;
+      best = 0ull;
+      for (uint32_t r = 0; r < ll.peers.n; ++r) {
+        const unsigned long long hi = ll_wait(mine + 2 * r, tag, ll.tag.err), lo = ll_wait(mine + 2 * r + 1, tag, ll.tag.err);
+        const unsigned long long k = (hi << 32) | lo;
+        best = k > best ? k : best;
+      }
+    }
+    const int32_t tok = int32_t(0xffffffffu - uint32_t(best));
     *key = 0ull;
     if (cur_tok) *cur_tok = tok;
     if (gen && gen_count) {
@@ -756,6 +813,16 @@ __global__ void finish_token_kernel(unsigned long long* key, int32_t* cur_tok, i
       *gen_count += 1;
     }
   }
+}
+
+__global__ void ll_unpack_kernel(const uint2* ll, LLTag lltag, float* out, uint32_t n, float softcap) {
+  pdl_trigger();
+  pdl_wait();
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = ll_waitf(ll + i, ll_tag(lltag), lltag.err);
+  if (softcap > 0.0f) v = __fmul_rn(softcap, tanhf(__fdiv_rn(v, softcap)));  // model.cpp:1036-1041
+  out[i] = v;
 }
 
 __global__ void softcap_kernel(float* logits, uint32_t n, float softcap) {
@@ -770,8 +837,10 @@ __global__ void softcap_kernel(float* logits, uint32_t n, float softcap) {
 // ------------------------------------------------------------------ launchers
 
 cudaError_t llmi_launch_embed(const EmbedArgs& a, const int32_t* token, float scale, float* h, cudaStream_t s,
-                              uint32_t n_tok) {
-  return llmi_launch(embed_kernel, dim3((a.n_cols + 255) / 256, n_tok), dim3(256), 0, s, a, token, scale, h);
+                              uint32_t n_tok, const LLCtx* ll, uint32_t ll_off) {
+  if (ll && ll->peers.n && n_tok != 1) return cudaErrorInvalidValue;
+  return llmi_launch(embed_kernel, dim3((a.n_cols + 255) / 256, n_tok), dim3(256), 0, s, a, token, scale, h,
+                     ll ? *ll : LLCtx(), ll_off);
 }
 
 cudaError_t llmi_launch_norm_act(const NormArgs& a, cudaStream_t s) {
@@ -854,16 +923,24 @@ cudaError_t llmi_launch_attention(const AttnArgs& a, cudaStream_t s, uint32_t n_
 }
 
 cudaError_t llmi_launch_geglu_act(const float* gate, const float* up, uint32_t n, int kind, uint8_t* buf,
-                                  float* hidden_out, cudaStream_t s, uint32_t n_tok, uint32_t act_stride) {
+                                  float* hidden_out, cudaStream_t s, uint32_t n_tok, uint32_t act_stride,
+                                  const uint2* ll_gate, const uint2* ll_up, const LLTag* tag) {
   const uint32_t warps = kind == ACT_Q8_0 ? n / 32 : (kind == ACT_Q8_K ? n / 256 : (n + 31) / 32);
   const uint32_t blocks = (warps + 3) / 4 ? (warps + 3) / 4 : 1;
+  if (ll_gate && (n_tok != 1 || !ll_up || !tag)) return cudaErrorInvalidValue;
   return llmi_launch(geglu_act_kernel, dim3(blocks, n_tok), dim3(128), 0, s, gate, up, n, kind, buf, hidden_out,
-                     act_stride);
+                     act_stride, ll_gate, ll_up, tag ? *tag : LLTag());
+}
+
+cudaError_t llmi_launch_ll_unpack(const uint2* ll, const LLTag& tag, float* out, uint32_t n, float softcap,
+                                  cudaStream_t s) {
+  return llmi_launch(ll_unpack_kernel, dim3((n + 255) / 256), dim3(256), 0, s, ll, tag, out, n, softcap);
 }
 
 cudaError_t llmi_launch_finish_token(unsigned long long* key, int32_t* cur_tok, int32_t* gen, int32_t* gen_count,
-                                     cudaStream_t s) {
-  return llmi_launch(finish_token_kernel, dim3(1), dim3(32), 0, s, key, cur_tok, gen, gen_count);
+                                     cudaStream_t s, const LLCtx* ll, uint32_t ll_off) {
+  return llmi_launch(finish_token_kernel, dim3(1), dim3(32), 0, s, key, cur_tok, gen, gen_count, ll ? *ll : LLCtx(),
+                     ll_off);
 }
 
 cudaError_t llmi_launch_softcap(float* logits, uint32_t n, float softcap, cudaStream_t s) {

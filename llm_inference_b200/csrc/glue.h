@@ -10,11 +10,20 @@ struct EmbedArgs {
   uint64_t nb;
   uint32_t n_cols;
   const uint8_t *q, *d, *x;
+  uint32_t row_begin, row_end;  // rows of token_embd this rank holds (a row-sharded model: the owner of the token's row
+                                // pushes it to every rank through the flagged exchange buffer)
 };
 
 inline EmbedArgs make_embed_args(const llmi_weight_s& w) {
-  return EmbedArgs{w.type, w.nb, uint32_t(w.n_cols), w.p_q, w.p_d, w.p_x};
+  return EmbedArgs{w.type, w.nb, uint32_t(w.n_cols), w.p_q, w.p_d, w.p_x, uint32_t(w.row_begin), uint32_t(w.row_end)};
 }
+
+// Row-sharded model: where a glue kernel finds / sends exchanged vectors (launch.cuh).  peers.n == 0: single GPU.
+struct LLCtx {
+  LLPeers peers;
+  LLTag tag;
+  uint32_t rank = 0;
+};
 
 struct NormArgs {
   const float* y = nullptr;       // optional: output of the previous mat-vec (post-norm + residual stage)
@@ -29,6 +38,11 @@ struct NormArgs {
   int32_t* pos_inc = nullptr;     // optional device counter to bump (end of a token step) by the number of tokens
   uint32_t n_tok = 1;             // prefill batch: one CTA per token, vectors n apart, activations act_stride apart
   uint32_t act_stride = 0;
+  // row-sharded model: y arrives through the flagged exchange buffer instead (tag = ll_tag); the last norm of a
+  // token step bumps the exchange epoch
+  const uint2* ll_y = nullptr;
+  LLTag ll_tag;
+  uint32_t* epoch_inc = nullptr;
 };
 
 struct AttnArgs {
@@ -49,10 +63,13 @@ struct AttnArgs {
   // the position of token 0; qbuf [n_tok][H][D] carries the rotated q between the two kernels
   uint32_t* qbuf = nullptr;
   uint32_t act_stride = 0;
+  // row-sharded model: q/k/v arrive through the flagged exchange buffer instead
+  const uint2 *ll_q = nullptr, *ll_k = nullptr, *ll_v = nullptr;
+  LLTag ll_tag;
 };
 
 cudaError_t llmi_launch_embed(const EmbedArgs& a, const int32_t* token, float scale, float* h, cudaStream_t s,
-                              uint32_t n_tok = 1);
+                              uint32_t n_tok = 1, const LLCtx* ll = nullptr, uint32_t ll_off = 0);
 cudaError_t llmi_launch_norm_act(const NormArgs& a, cudaStream_t s);
 cudaError_t llmi_launch_act(const float* x, uint32_t n, int kind, uint8_t* buf, cudaStream_t s, uint32_t n_tok = 1,
                             uint32_t act_stride = 0);
@@ -61,7 +78,14 @@ size_t llmi_attention_smem(uint32_t t_max, uint32_t D);
 cudaError_t llmi_attention_init(uint32_t t_max, uint32_t D);
 cudaError_t llmi_launch_attention(const AttnArgs& a, cudaStream_t s, uint32_t n_tok = 1);
 cudaError_t llmi_launch_geglu_act(const float* gate, const float* up, uint32_t n, int kind, uint8_t* buf,
-                                  float* hidden_out, cudaStream_t s, uint32_t n_tok = 1, uint32_t act_stride = 0);
+                                  float* hidden_out, cudaStream_t s, uint32_t n_tok = 1, uint32_t act_stride = 0,
+                                  const uint2* ll_gate = nullptr, const uint2* ll_up = nullptr,
+                                  const LLTag* tag = nullptr);
+// ll != nullptr: every rank's running key travels to every rank (two flagged words at ll_off + 2*rank) and the
+// token is the maximum over the ranks
 cudaError_t llmi_launch_finish_token(unsigned long long* key, int32_t* cur_tok, int32_t* gen, int32_t* gen_count,
-                                     cudaStream_t s);
+                                     cudaStream_t s, const LLCtx* ll = nullptr, uint32_t ll_off = 0);
+// exchanged vector -> plain floats (+ optional soft-cap): the host-facing logits of a row-sharded model
+cudaError_t llmi_launch_ll_unpack(const uint2* ll, const LLTag& tag, float* out, uint32_t n, float softcap,
+                                  cudaStream_t s);
 cudaError_t llmi_launch_softcap(float* logits, uint32_t n, float softcap, cudaStream_t s);

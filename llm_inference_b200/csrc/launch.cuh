@@ -19,6 +19,8 @@
 #include <cstdint>
 #include <utility>
 
+#include "llmi_internal.h"  // LLTag, LLPeers
+
 extern bool g_llmi_pdl;
 
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
@@ -67,4 +69,55 @@ cudaError_t llmi_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t 
   cfg.attrs = attr;
   cfg.numAttrs = g_llmi_pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+
+// ---------------------------------------------------------------------------
+// Flagged 8-byte exchange between the GPUs of a row-sharded model.
+// A vector that one rank produces and every rank consumes travels as {value bits,
+// tag} pairs: the producing mat-vec writes each of its rows with ONE 64-bit
+// store straight into the consumer's buffer on every peer (NVLink peer memory),
+// and the consuming kernel spins on the element until the tag matches.  A
+// naturally aligned 64-bit access is single-copy atomic, so data and flag
+// arrive together: no fence, no ticket, no collective kernel — the transfer is
+// the mat-vec's own epilogue and its latency is one NVLink store.
+// tag = *epoch * mul + add: `epoch` is a device counter every rank bumps once
+// per token step (the ranks run the same steps), `add` identifies the exchange
+// inside the step, so a buffer reused every layer never shows a stale match.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ll_tag(const LLTag& t) {
+  uint32_t e;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(e) : "l"(t.epoch) : "memory");
+  return e * t.mul + t.add;
+}
+__device__ __forceinline__ void ll_store(uint2* p, uint32_t bits, uint32_t tag) {
+  asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(bits), "r"(tag) : "memory");
+}
+// Spins until element *p carries `tag`; gives up after ~4 s (a peer that never
+// arrives must not hang the GPU) and reports through *err.
+__device__ __forceinline__ uint32_t ll_wait(const uint2* p, uint32_t tag, uint32_t* err) {
+  uint32_t v, f;
+  asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(f) : "l"(p) : "memory");
+  if (f == tag) return v;
+  if (err) {  // an earlier wait already timed out: the run is lost, drain quickly
+    uint32_t dead;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(dead) : "l"(err) : "memory");
+    if (dead) return 0;
+  }
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (uint32_t spins = 1;; ++spins) {
+    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(f) : "l"(p) : "memory");
+    if (f == tag) return v;
+    if ((spins & 1023u) == 0) {
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 4000000000ull) {
+        if (err) *err = 1;
+        return 0;
+      }
+    }
+  }
+}
+__device__ __forceinline__ float ll_waitf(const uint2* p, uint32_t tag, uint32_t* err) {
+  return __uint_as_float(ll_wait(p, tag, err));
 }

@@ -61,6 +61,28 @@ inline size_t act_bytes(int kind, uint64_t n) {
   }
 }
 
+// ---- flagged exchange of a row-sharded model (protocol: launch.cuh) ----------
+constexpr int LLMI_MAX_WORLD = 8;
+constexpr uint32_t LL_NONE = 0xffffffffu;
+
+struct LLTag {
+  const uint32_t* epoch = nullptr;
+  uint32_t mul = 0, add = 0;
+  uint32_t* err = nullptr;  // set to 1 by a consumer that gave up waiting (a peer died): the host checks it
+};
+struct LLPeers {
+  uint2* base[LLMI_MAX_WORLD] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  uint32_t n = 0;  // 0: not sharded
+};
+
+// What a mat-vec launch needs to push its rows to every rank: the ranks' exchange buffers, the tag of this
+// exchange, and per matrix of the batch the element offset of its output vector inside the buffer.
+struct GemvLL {
+  LLPeers peers;
+  LLTag tag;
+  uint32_t off[3] = {LL_NONE, LL_NONE, LL_NONE};
+};
+
 // error plumbing (capi.cu)
 void llmi_set_error(const std::string& msg);
 int llmi_fail(int code, const std::string& msg);
@@ -92,10 +114,11 @@ cudaError_t llmi_launch_gemv_tokens(const llmi_weight_s* const* ws, float* const
                                     int n, int act_kind, uint64_t act_n, const uint8_t* act_base, uint32_t n_tok,
                                     cudaStream_t s);
 cudaError_t llmi_launch_gemv_batch(const llmi_weight_s* const* ws, float* const* outs, int n, const llmi_act_s& a,
-                                   cudaStream_t s);  // same format, same activation, n <= 3
+                                   cudaStream_t s, const GemvLL* ll = nullptr);  // same format, same activation, n <= 3
+void llmi_gemv_set_prefetch(int mode);  // 1 = L2 prefetch of each CTA's weight range ahead of the PDL wait
 uint32_t llmi_gemv_chunks(const llmi_weight_s& w);
 void llmi_gemv_set_shape(int warps, int slabs_per_cta);  // 0 = heuristic  // K-chunks (work items) per slab
 cudaError_t llmi_launch_gemv_argmax(const llmi_weight_s& w, const llmi_act_s& a, float* out, unsigned long long* key,
-                                    float softcap, cudaStream_t s);
+                                    float softcap, cudaStream_t s, const GemvLL* ll = nullptr);
 cudaError_t llmi_launch_block_dots(const llmi_weight_s& w, const llmi_act_s& a, int32_t* dots_dev, cudaStream_t s);
 int llmi_act_kind_for(uint32_t ggml_type);

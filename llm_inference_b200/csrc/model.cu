@@ -65,6 +65,23 @@ struct llmi_model_s {
   uint32_t* qbuf = nullptr;  // [batch][H][D] rotated q between the two prefill attention kernels
   bool prefill_ok = true;
   int prefill_launches = 0;
+  // row-sharded model: every matrix holds the slab-aligned row range of `rank`; the vectors the
+  // mat-vecs produce travel through `comm`, one flagged-exchange buffer per rank with the same layout everywhere
+  // (element offsets off_*), written by the mat-vec epilogues of ALL ranks over peer memory (launch.cuh)
+  int world = 1, rank = 0;
+  uint2* comm = nullptr;
+  size_t comm_elems = 0;
+  LLCtx ll;                       // peers (filled by llmi_model_comm_connect), tag template, rank
+  uint32_t *d_epoch = nullptr, *d_llerr = nullptr;
+  uint32_t off_h = 0, off_q = 0, off_k = 0, off_v = 0, off_ao = 0, off_gate = 0, off_up = 0, off_fo = 0, off_key = 0,
+           off_logits = 0;
+  std::vector<void*> ipc_opened;  // peer mappings to close
+  bool sharded() const { return world > 1; }
+  LLTag tag(uint32_t idx) const {  // idx: 1 + 4*layer + {0 qkv, 1 attn_out, 2 gate/up, 3 ffn_out}; 4L+1 embed, +2 keys, +3 logits
+    LLTag t = ll.tag;
+    t.add = idx;
+    return t;
+  }
 };
 
 namespace {
@@ -100,8 +117,17 @@ int upload_matrix(llmi_model_s* m, const llmi::GgufTensor* t, uint64_t k, uint64
   if (!t) return llmi_fail(LLMI_ERR_ARG, std::string("llmi_model_load: missing tensor ") + name);
   if (t->shape.size() != 2 || t->shape[0] != k || t->shape[1] < n)
     return llmi_fail(LLMI_ERR_SIZE, std::string("llmi_model_load: unexpected shape of ") + name);
-  M_RC(llmi_weight_upload(t->data, t->type, k, n, 0, n, out));
-  m->weight_bytes += llmi_row_bytes(t->type, k) * n;
+  // this rank's rows: contiguous, slab-aligned, as even as possible (shard.row_ranges; the thread partition of
+  // ops.cpp:439-448 lifted to devices)
+  uint64_t rb = 0, re = n;
+  if (m->sharded()) {
+    const uint64_t units = (n + LLMI_SLAB - 1) / LLMI_SLAB, W = uint64_t(m->world), r = uint64_t(m->rank);
+    const uint64_t first = r * (units / W) + std::min(r, units % W), cnt = units / W + (r < units % W ? 1 : 0);
+    rb = std::min(n, first * LLMI_SLAB);
+    re = std::min(n, (first + cnt) * LLMI_SLAB);
+  }
+  M_RC(llmi_weight_upload(t->data, t->type, k, n, rb, re, out));
+  m->weight_bytes += llmi_row_bytes(t->type, k) * (re - rb);
   return LLMI_OK;
 }
 
@@ -143,7 +169,7 @@ int gemv(llmi_model_s* m, llmi_weight_t w, ActSet& set, float* out) {
 // Mat-vecs that consume the same activation vector: matrices of the same format
 // go out as one grid (llmi_launch_gemv_batch), in the order given.
 int gemv_group(llmi_model_s* m, std::initializer_list<llmi_weight_t> ws, std::initializer_list<float*> outs,
-               ActSet& set) {
+               ActSet& set, const GemvLL* ll = nullptr) {
   std::vector<llmi_weight_t> w(ws);
   std::vector<float*> o(outs);
   std::vector<bool> done(w.size(), false);
@@ -151,16 +177,19 @@ int gemv_group(llmi_model_s* m, std::initializer_list<llmi_weight_t> ws, std::in
     if (done[i]) continue;
     const llmi_weight_s* bw[3];
     float* bo[3];
+    GemvLL sub;  // the exchange offsets follow their matrices into the per-format launches
+    if (ll) sub = *ll;
     int n = 0;
     for (size_t j = i; j < w.size() && n < 3; ++j)
       if (!done[j] && w[j]->type == w[i]->type) {
         bw[n] = w[j];
         bo[n] = o[j];
+        if (ll) sub.off[n] = ll->off[j];
         done[j] = true;
         ++n;
       }
     llmi_act_t a = set.a[llmi_act_kind_for(w[i]->type)];
-    M_TRY(llmi_launch_gemv_batch(bw, bo, n, *a, m->stream));
+    M_TRY(llmi_launch_gemv_batch(bw, bo, n, *a, m->stream, ll ? &sub : nullptr));
     m->launches_per_step++;
   }
   return LLMI_OK;
@@ -171,8 +200,23 @@ int run_step(llmi_model_s* m, const int32_t* tok, bool want_logits, bool want_ar
   cudaStream_t s = m->stream;
   m->launches_per_step = 0;
   const uint32_t E = m->E, F = m->F, HD = m->H * m->D;
-  M_TRY(llmi_launch_embed(make_embed_args(*m->embd), tok, std::sqrt(float(E)), m->h, s));  // model.cpp:710-712
+  const bool sh = m->sharded();
+  if (sh && m->ll.peers.n != uint32_t(m->world))
+    return llmi_fail(LLMI_ERR_STATE, "row-sharded model: llmi_model_comm_connect has not been called");
+  LLCtx ll_embed = m->ll;
+  ll_embed.tag = m->tag(4 * m->L + 1);
+  M_TRY(llmi_launch_embed(make_embed_args(*m->embd), tok, std::sqrt(float(E)), m->h, s, 1, sh ? &ll_embed : nullptr,
+                          m->off_h));  // model.cpp:710-712
   m->launches_per_step++;
+  GemvLL gl;  // exchange context of the mat-vec launches of a sharded model
+  if (sh) gl.peers = m->ll.peers;
+  auto push = [&](uint32_t idx, std::initializer_list<uint32_t> offs) -> const GemvLL* {
+    if (!sh) return nullptr;
+    gl.tag = m->tag(idx);
+    int i = 0;
+    for (uint32_t o : offs) gl.off[i++] = o;
+    return &gl;
+  };
   for (uint32_t l = 0; l < m->L; ++l) {
     LayerW& w = m->layers[l];
     const int kq = llmi_act_kind_for(w.q->type);
@@ -185,8 +229,12 @@ int run_step(llmi_model_s* m, const int32_t* tok, bool want_logits, bool want_ar
     }
     M_RC(extra_acts(m, m->act_E, m->xn, E, kq, {w.k, w.v}));
     // model.cpp:754 (Q), 784 (K), 803 (V): one grid per format group
-    M_RC(gemv_group(m, {w.q, w.k, w.v}, {m->q, m->k, m->v}, m->act_E));
+    M_RC(gemv_group(m, {w.q, w.k, w.v}, {m->q, m->k, m->v}, m->act_E, push(1 + 4 * l, {m->off_q, m->off_k, m->off_v})));
     AttnArgs aa;  // q/k norm, RoPE, KV append and attention in one kernel
+    if (sh) {
+      aa.ll_q = m->comm + m->off_q; aa.ll_k = m->comm + m->off_k; aa.ll_v = m->comm + m->off_v;
+      aa.ll_tag = m->tag(1 + 4 * l);
+    }
     aa.q = m->q; aa.k = m->k; aa.v = m->v; aa.wq_norm = w.q_norm; aa.wk_norm = w.k_norm;
     aa.kcache = m->kcache + size_t(l) * m->t_max * m->HK * m->D;
     aa.vcache = m->vcache + size_t(l) * m->t_max * m->HK * m->D;
@@ -207,29 +255,38 @@ int run_step(llmi_model_s* m, const int32_t* tok, bool want_logits, bool want_ar
       M_TRY(llmi_launch_act(m->attn, HD, ko, ko_buf, s));
       m->launches_per_step++;
     }
-    M_RC(gemv(m, w.o, m->act_HD, m->attn_out));  // model.cpp:557
+    M_RC(gemv_group(m, {w.o}, {m->attn_out}, m->act_HD, push(2 + 4 * l, {m->off_ao})));  // model.cpp:557
     {
       const int kg = llmi_act_kind_for(w.gate->type);
       NormArgs na;  // post-attention norm + residual, then ffn_norm (model.cpp:843-858)
       na.y = m->attn_out; na.w_post = w.post_attn_norm; na.h = m->h; na.w = w.ffn_norm; na.n = E; na.eps = m->eps;
+      if (sh) { na.y = nullptr; na.ll_y = m->comm + m->off_ao; na.ll_tag = m->tag(2 + 4 * l); }
       na.xn_out = m->xn; na.act_kind = kg; na.act_buf = get_act(m->act_E, kg, E)->buf;
       M_TRY(llmi_launch_norm_act(na, s));
       m->launches_per_step++;
       M_RC(extra_acts(m, m->act_E, m->xn, E, kg, {w.up}));
     }
-    M_RC(gemv_group(m, {w.gate, w.up}, {m->gate, m->up}, m->act_E));  // model.cpp:875, 877
+    M_RC(gemv_group(m, {w.gate, w.up}, {m->gate, m->up}, m->act_E,
+                    push(3 + 4 * l, {m->off_gate, m->off_up})));  // model.cpp:875, 877
     const int kd = llmi_act_kind_for(w.down->type);
-    M_TRY(llmi_launch_geglu_act(m->gate, m->up, F, kd, get_act(m->act_F, kd, F)->buf, nullptr, s));
+    {
+      const LLTag tg = m->tag(3 + 4 * l);
+      M_TRY(llmi_launch_geglu_act(m->gate, m->up, F, kd, get_act(m->act_F, kd, F)->buf, nullptr, s, 1, 0,
+                                  sh ? m->comm + m->off_gate : nullptr, sh ? m->comm + m->off_up : nullptr,
+                                  sh ? &tg : nullptr));
+    }
     m->launches_per_step++;
-    M_RC(gemv(m, w.down, m->act_F, m->ffn_out));  // model.cpp:909
+    M_RC(gemv_group(m, {w.down}, {m->ffn_out}, m->act_F, push(4 + 4 * l, {m->off_fo})));  // model.cpp:909
     {
       NormArgs na;  // post-ffw norm + residual (model.cpp:915-924), then the next norm
       na.y = m->ffn_out; na.w_post = w.post_ffw_norm; na.h = m->h; na.n = E; na.eps = m->eps; na.xn_out = m->xn;
+      if (sh) { na.y = nullptr; na.ll_y = m->comm + m->off_fo; na.ll_tag = m->tag(4 + 4 * l); }
       if (l + 1 < m->L) {
         const int kn = llmi_act_kind_for(m->layers[l + 1].q->type);
         na.w = m->layers[l + 1].attn_norm; na.act_kind = kn; na.act_buf = get_act(m->act_E, kn, E)->buf;
       } else {
         na.pos_inc = m->d_pos;  // the token is done
+        if (sh) na.epoch_inc = m->d_epoch;
         if (want_logits) {      // final RMSNorm (model.cpp:983-986)
           const int kl = llmi_act_kind_for(m->embd->type);
           na.w = m->out_norm; na.act_kind = kl; na.act_buf = get_act(m->act_E, kl, E)->buf;
@@ -242,9 +299,17 @@ int run_step(llmi_model_s* m, const int32_t* tok, bool want_logits, bool want_ar
   if (want_logits) {
     if (want_argmax) {  // logits mat-vec (model.cpp:1000 / 1027) with the soft-cap + argmax epilogue
       llmi_act_t la = m->act_E.a[llmi_act_kind_for(m->embd->type)];
+      LLCtx ll_key = m->ll;
+      ll_key.tag = m->tag(4 * m->L + 2);
+      // sharded: every rank keeps the logits of its own rows only and the ranks swap their argmax keys
       M_TRY(llmi_launch_gemv_argmax(*m->embd, *la, m->logits, m->d_key, m->final_softcap, s));
-      M_TRY(llmi_launch_finish_token(m->d_key, m->d_tok, m->d_gen, m->d_gen_count, s));
+      M_TRY(llmi_launch_finish_token(m->d_key, m->d_tok, m->d_gen, m->d_gen_count, s, sh ? &ll_key : nullptr,
+                                     m->off_key));
       m->launches_per_step += 2;
+    } else if (sh) {  // host-facing logits: rows of every rank through the exchange buffer, then plain (+ soft-cap)
+      M_RC(gemv_group(m, {m->embd}, {m->logits}, m->act_E, push(4 * m->L + 3, {m->off_logits})));
+      M_TRY(llmi_launch_ll_unpack(m->comm + m->off_logits, m->tag(4 * m->L + 3), m->logits, m->V, m->final_softcap, s));
+      m->launches_per_step++;
     } else {
       M_RC(gemv(m, m->embd, m->act_E, m->logits));
       if (m->final_softcap > 0.0f) {  // model.cpp:1036-1041
@@ -387,7 +452,9 @@ double kv_f(const llmi::GgufImage& g, const std::string& key, double dflt, bool*
   return (v->type == 6 || v->type == 12) ? v->f : double(v->u);
 }
 
-int load_impl(llmi_model_s* m, const uint8_t* image, uint64_t size, uint32_t t_max) {
+int load_impl(llmi_model_s* m, const uint8_t* image, uint64_t size, uint32_t t_max, int world, int rank) {
+  m->world = world;
+  m->rank = rank;
   llmi::GgufImage g(image, size);
   const llmi::GgufValue* arch = g.find("general.architecture");
   if (!arch) return llmi_fail(LLMI_ERR_ARG, "Failed to find metadata key: general.architecture");
@@ -485,6 +552,28 @@ int load_impl(llmi_model_s* m, const uint8_t* image, uint64_t size, uint32_t t_m
   }
   if (m->batch < 2) m->prefill_ok = false;
   if (const char* e = getenv("LLMI_NO_PREFILL")) m->prefill_ok = m->prefill_ok && !(e[0] == '1');
+  if (m->sharded()) {
+    m->prefill_ok = false;  // prompts of a sharded model go token by token through the exchange path
+    // one exchange buffer, same layout on every rank (element = {value bits, tag})
+    uint32_t off = 0;
+    auto take = [&](uint32_t n) { const uint32_t o = off; off += (n + 1u) & ~1u; return o; };
+    m->off_h = take(E); m->off_q = take(HD); m->off_k = take(KD); m->off_v = take(KD); m->off_ao = take(E);
+    m->off_gate = take(F); m->off_up = take(F); m->off_fo = take(E); m->off_key = take(2 * LLMI_MAX_WORLD);
+    m->off_logits = take(m->V);
+    m->comm_elems = off;
+    M_TRY(cudaMalloc((void**)&m->comm, size_t(off) * sizeof(uint2)));  // not in `owned`: exported through CUDA IPC
+    M_TRY(cudaMemset(m->comm, 0, size_t(off) * sizeof(uint2)));
+    M_RC(dev_alloc(m, (void**)&m->d_epoch, 16));
+    M_RC(dev_alloc(m, (void**)&m->d_llerr, 16));
+    const uint32_t one = 1;
+    M_TRY(cudaMemcpy(m->d_epoch, &one, 4, cudaMemcpyHostToDevice));
+    M_TRY(cudaMemset(m->d_llerr, 0, 16));
+    m->ll.rank = uint32_t(rank);
+    m->ll.tag.epoch = m->d_epoch;
+    m->ll.tag.mul = 4 * m->L + 4;
+    m->ll.tag.err = m->d_llerr;
+    M_TRY(cudaDeviceSynchronize());
+  }
   M_RC(dev_alloc(m, (void**)&m->logits, size_t(m->V) * 4));
   const size_t kv_elems = size_t(m->L) * t_max * KD;
   M_RC(dev_alloc(m, (void**)&m->kcache, kv_elems * 4));
@@ -545,13 +634,20 @@ int ensure_decode_graph(llmi_model_s* m) {
 extern "C" {
 
 int llmi_model_load(const void* gguf_image, uint64_t size, uint32_t max_positions, llmi_model_t* out) {
+  return llmi_model_load_shard(gguf_image, size, max_positions, 1, 0, out);
+}
+
+int llmi_model_load_shard(const void* gguf_image, uint64_t size, uint32_t max_positions, int world, int rank,
+                          llmi_model_t* out) {
   if (!gguf_image || !out) return llmi_fail(LLMI_ERR_ARG, "llmi_model_load: null pointer");
   if (llmi_sm_count() == 0) return llmi_fail(LLMI_ERR_STATE, "llmi_init() has not been called");
+  if (world < 1 || world > LLMI_MAX_WORLD || rank < 0 || rank >= world)
+    return llmi_fail(LLMI_ERR_ARG, "llmi_model_load_shard: need 1 <= world <= 8 and 0 <= rank < world");
   if (max_positions == 0) max_positions = 4096;
   std::unique_ptr<llmi_model_s> m(new llmi_model_s());
   int rc;
   try {
-    rc = load_impl(m.get(), static_cast<const uint8_t*>(gguf_image), size, max_positions);
+    rc = load_impl(m.get(), static_cast<const uint8_t*>(gguf_image), size, max_positions, world, rank);
   } catch (const std::exception& e) {
     rc = llmi_fail(LLMI_ERR_ARG, e.what());
   }
@@ -573,12 +669,56 @@ int llmi_model_free(llmi_model_t m) {
   for (ActSet* s : {&m->act_E, &m->act_HD, &m->act_F})
     for (llmi_act_t a : s->a) llmi_act_free(a);
   for (void* p : m->owned) cudaFree(p);
+  for (void* p : m->ipc_opened) cudaIpcCloseMemHandle(p);
+  if (m->comm) cudaFree(m->comm);
   if (m->logits_pinned) cudaFreeHost(m->logits_pinned);
   if (m->ev0) cudaEventDestroy(m->ev0);
   if (m->ev1) cudaEventDestroy(m->ev1);
   if (m->stream) cudaStreamDestroy(m->stream);
   delete m;
   return LLMI_OK;
+}
+
+// ---- row-sharded model: wiring the ranks' exchange buffers together ------------------------------------------
+// One process per GPU: every rank exports its buffer as a CUDA IPC handle (64 bytes), the host plumbing
+// (torch.distributed, MPI, a pipe ...) all-gathers the handles, and every rank maps its peers' buffers.  After
+// that the ranks never call a collective again: the mat-vec epilogues store into the mapped buffers.
+int llmi_model_comm_handle(llmi_model_t m, void* handle64) {
+  if (!m || !handle64) return llmi_fail(LLMI_ERR_ARG, "llmi_model_comm_handle: null pointer");
+  if (!m->sharded()) return llmi_fail(LLMI_ERR_STATE, "llmi_model_comm_handle: the model is not sharded");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+  cudaIpcMemHandle_t h;
+  M_TRY(cudaIpcGetMemHandle(&h, m->comm));
+  memcpy(handle64, &h, sizeof(h));
+  return LLMI_OK;
+}
+
+int llmi_model_comm_connect(llmi_model_t m, const void* handles /* world x 64 bytes, rank order */) {
+  if (!m || !handles) return llmi_fail(LLMI_ERR_ARG, "llmi_model_comm_connect: null pointer");
+  if (!m->sharded()) return llmi_fail(LLMI_ERR_STATE, "llmi_model_comm_connect: the model is not sharded");
+  if (m->ll.peers.n) return llmi_fail(LLMI_ERR_STATE, "llmi_model_comm_connect: already connected");
+  for (int r = 0; r < m->world; ++r) {
+    if (r == m->rank) {
+      m->ll.peers.base[r] = m->comm;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, static_cast<const uint8_t*>(handles) + size_t(r) * sizeof(h), sizeof(h));
+    void* p = nullptr;
+    M_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    m->ipc_opened.push_back(p);
+    m->ll.peers.base[r] = static_cast<uint2*>(p);
+  }
+  m->ll.peers.n = uint32_t(m->world);
+  return LLMI_OK;
+}
+
+// 1 when a kernel gave up waiting for a peer's rows (the peer died or the ranks ran different steps).
+int llmi_model_comm_error(llmi_model_t m) {
+  if (!m || !m->sharded()) return 0;
+  uint32_t e = 0;
+  if (cudaMemcpy(&e, m->d_llerr, 4, cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
+  return int(e);
 }
 
 int llmi_model_info(llmi_model_t m, uint32_t* dims /*[8]: L,E,F,H,HK,D,V,t_max*/, uint64_t* weight_bytes) {
@@ -652,6 +792,9 @@ int llmi_model_decode_greedy(llmi_model_t m, int32_t first_token, int pos, int n
 // Logits of the last executed step (device -> host), e.g. after decode_greedy.
 int llmi_model_last_logits(llmi_model_t m, float* logits_host) {
   if (!m || !logits_host) return llmi_fail(LLMI_ERR_ARG, "llmi_model_last_logits: null pointer");
+  if (m->sharded())
+    return llmi_fail(LLMI_ERR_STATE, "llmi_model_last_logits: a sharded greedy step keeps only this rank's rows (the "
+                                     "ranks swap argmax keys); call llmi_model_forward for full logits");
   M_TRY(cudaMemcpyAsync(m->logits_pinned, m->logits, size_t(m->V) * 4, cudaMemcpyDeviceToHost, m->stream));
   M_TRY(cudaStreamSynchronize(m->stream));
   memcpy(logits_host, m->logits_pinned, size_t(m->V) * 4);

@@ -12,20 +12,49 @@ from . import _lib, ops
 
 
 class Model:
-    def __init__(self, gguf_image, max_positions: int = 4096, device: int = 0) -> None:
+    """``world > 1``: this process holds rank ``rank``'s row shard of every matrix; call
+    :meth:`connect` (after every rank has constructed its Model) before the first forward / decode.  All ranks
+    must then make the same calls; logits and tokens are bit-identical to the single-GPU model."""
+
+    def __init__(self, gguf_image, max_positions: int = 4096, device: int = 0, world: int = 1, rank: int = 0) -> None:
         ops.init_ops(1, device)
         L = _lib.load()
         img = np.ascontiguousarray(np.frombuffer(gguf_image, np.uint8) if isinstance(gguf_image, (bytes, bytearray))
                                    else gguf_image, np.uint8)
         h = C.c_void_p()
-        _lib.check(L.llmi_model_load(img.ctypes.data, img.size, max_positions, C.byref(h)))
+        _lib.check(L.llmi_model_load_shard(img.ctypes.data, img.size, max_positions, world, rank, C.byref(h)))
         self.h = h
+        self.world, self.rank = world, rank
         dims = (C.c_uint32 * 8)()
         wb = C.c_uint64()
         _lib.check(L.llmi_model_info(h, dims, C.byref(wb)))
         (self.n_layer, self.n_embd, self.n_ff, self.n_head, self.n_head_kv, self.head_dim, self.vocab,
          self.max_positions) = (int(v) for v in dims)
         self.weight_bytes = int(wb.value)
+
+    def comm_handle(self) -> bytes:
+        """This rank's exchange buffer as a CUDA IPC handle (64 bytes)."""
+        buf = (C.c_uint8 * 64)()
+        _lib.check(_lib.load().llmi_model_comm_handle(self.h, buf))
+        return bytes(buf)
+
+    def connect(self, group=None) -> None:
+        """Maps the peers' exchange buffers.  The 64-byte handles are all-gathered through ``torch.distributed``
+        (any backend — this is the only collective a sharded model ever calls); afterwards the mat-vec kernels
+        write their rows straight into the peers' buffers."""
+        if self.world == 1:
+            return
+        import torch.distributed as dist
+
+        handles = [None] * self.world
+        dist.all_gather_object(handles, self.comm_handle(), group=group)
+        blob = b"".join(handles)
+        _lib.check(_lib.load().llmi_model_comm_connect(self.h, blob))
+        dist.barrier(group=group)
+
+    @property
+    def comm_error(self) -> bool:
+        return bool(_lib.load().llmi_model_comm_error(self.h))
 
     def forward(self, tokens, pos: int) -> np.ndarray:
         """Model::forward(tokens, pos): logits of the last token (model.cpp:706-1048)."""
