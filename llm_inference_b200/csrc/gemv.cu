@@ -803,6 +803,8 @@ __global__ void toklane_reduce_kernel(const GemvBatch batch) {
   }
 }
 
+#include "umma_prefill.cuh"
+
 // --------------------------------------------------------------- debug dump
 // One thread per (local row, block): recomputes the integer block dot with the
 // same device functions and planes as the GEMV.
@@ -860,7 +862,7 @@ using BF16 = BodyHalf<true>;
 // Benches can pin the CTA shape: g_warps in {0 (heuristic), 4, 8, 16},
 // g_slabs_per_cta in {0 (heuristic), 1..}.  Results never depend on it.
 int g_warps = 0, g_slabs_per_cta = 0;
-int g_prefetch = 1;  // L2 prefetch of each CTA's weight range ahead of the PDL wait (LLMI_GEMV_PREFETCH=0 turns it off)
+int g_prefetch = 0;  // L2 prefetch of each CTA's weight range ahead of the PDL wait: measured slower on the large matrices (profiles/r01_notes.md); LLMI_GEMV_PREFETCH=1 turns it on
 
 // (W, S) for one matrix.  Heuristic from tools/gemv_sweep.py
 // (profiles/r01_sweep_v4.jsonl): one slab per CTA and the fewest warps per CTA
@@ -975,8 +977,89 @@ cudaError_t launch_toklane(const GemvArgs* args, int n, cudaStream_t s) {
   return llmi_launch(toklane_reduce_kernel, dim3(rb, n), dim3(256), 0, s, b);
 }
 
+// grow-only scratch of one tensor-core prefill launch: activations in UMMA operand order + fp32 scales
+static uint4* g_bq = nullptr;
+static float* g_bd = nullptr;
+static size_t g_bq_items = 0, g_bd_floats = 0;
+bool g_umma = true;  // LLMI_NO_UMMA=1: token batches stay on the dp4a token-per-lane kernel (A/B)
+
+// Token batches of >= 32 tokens, Q4_0 / Q8_0 weights: exact int8 tensor-core path (umma_prefill.cuh).
+template <bool IS_Q8>
+cudaError_t launch_umma(const GemvArgs* args, int n, cudaStream_t s) {
+  GemvBatch b;
+  b.n = n;
+  const uint32_t n_tok = args[0].n_tok, nb0 = args[0].nb;
+  for (int i = 1; i < n; ++i)
+    if (args[i].nb != nb0) return cudaErrorInvalidValue;  // one activation -> one K
+  const uint32_t tiles_n = (n_tok + umma::TN - 1) / umma::TN, J = (nb0 + 15) / 16;
+  size_t need = 0;
+  for (int i = 0; i < n; ++i) need += size_t(J) * n_tok * args[i].n_slabs * LLMI_SLAB;
+  const size_t bq_items = size_t(tiles_n) * nb0 * 64, bd_floats = size_t(tiles_n) * nb0 * umma::TN;
+  if (need > g_part_floats || bq_items > g_bq_items || bd_floats > g_bd_floats) {
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return e;
+    if (need > g_part_floats) {
+      if (g_part) cudaFree(g_part);
+      g_part = nullptr;
+      g_part_floats = 0;
+      if ((e = cudaMalloc(&g_part, need * sizeof(float))) != cudaSuccess) return e;
+      g_part_floats = need;
+    }
+    if (bq_items > g_bq_items) {
+      if (g_bq) cudaFree(g_bq);
+      g_bq = nullptr;
+      g_bq_items = 0;
+      if ((e = cudaMalloc(&g_bq, bq_items * sizeof(uint4))) != cudaSuccess) return e;
+      g_bq_items = bq_items;
+    }
+    if (bd_floats > g_bd_floats) {
+      if (g_bd) cudaFree(g_bd);
+      g_bd = nullptr;
+      g_bd_floats = 0;
+      if ((e = cudaMalloc(&g_bd, bd_floats * sizeof(float))) != cudaSuccess) return e;
+      g_bd_floats = bd_floats;
+    }
+  }
+  size_t off = 0;
+  uint32_t ctas = 0;
+  uint64_t outs = 0;
+  for (int i = 0; i < n; ++i) {
+    b.a[i] = args[i];
+    b.a[i].part = g_part + off;
+    off += size_t(J) * n_tok * args[i].n_slabs * LLMI_SLAB;
+    b.S[i] = umma::TM / LLMI_SLAB;
+    ctas += (args[i].n_slabs + umma::TM / LLMI_SLAB - 1) / (umma::TM / LLMI_SLAB);
+    b.cta_end[i] = ctas;
+    outs = std::max<uint64_t>(outs, uint64_t(n_tok) * args[i].n_local);
+  }
+  for (int i = n; i < GEMV_MAX_BATCH; ++i) {
+    b.a[i] = b.a[0];
+    b.S[i] = umma::TM / LLMI_SLAB;
+    b.cta_end[i] = ctas;
+  }
+  if (ctas == 0) return cudaSuccess;
+  const unsigned pb = unsigned(std::min<uint64_t>((bq_items + 255) / 256, uint64_t(g_sm_count) * 8));
+  cudaError_t e = llmi_launch(umma_pack_act_kernel, dim3(pb), dim3(256), 0, s, args[0].act, args[0].act_stride,
+                              args[0].n_cols, nb0, n_tok, g_bq, g_bd);
+  if (e != cudaSuccess) return e;
+  // K-chunk groups across grid.z until the grid holds ~2 CTAs per SM (one CTA per SM is resident)
+  uint32_t gz = 1;
+  while (gz < J && uint64_t(ctas) * tiles_n * gz < uint64_t(g_sm_count) * 2) ++gz;
+  const uint32_t nj = (J + gz - 1) / gz;
+  gz = (J + nj - 1) / nj;
+  e = llmi_launch(gemm_umma_kernel<IS_Q8>, dim3(ctas, tiles_n, gz), dim3(umma::WARPS * 32), umma::SMEM_BYTES, s, b,
+                  (const uint4*)g_bq, (const float*)g_bd, nj);
+  if (e != cudaSuccess) return e;
+  const unsigned rb = unsigned(std::min<uint64_t>((outs + 255) / 256, uint64_t(g_sm_count) * 8));
+  return llmi_launch(toklane_reduce_kernel, dim3(rb, n), dim3(256), 0, s, b);
+}
+
 template <class B>
 cudaError_t launch_tokens(const GemvArgs* args, int n, cudaStream_t s) {
+  if (g_umma && args[0].n_tok >= 32) {
+    if (std::is_same<B, BodyQ4_0>::value) return launch_umma<false>(args, n, s);
+    if (std::is_same<B, BodyQ8_0>::value) return launch_umma<true>(args, n, s);
+  }
   if (args[0].n_tok >= 16) {
     if (std::is_same<B, BodyQ4_0>::value) return launch_toklane<false>(args, n, s);
     if (std::is_same<B, BodyQ8_0>::value) return launch_toklane<true>(args, n, s);
@@ -1076,6 +1159,11 @@ void llmi_gemv_set_shape(int warps, int slabs_per_cta) {
 
 cudaError_t llmi_gemv_init() {
   cudaError_t e0;
+  if (const char* e = getenv("LLMI_NO_UMMA")) g_umma = !(e[0] == '1');
+  if ((e0 = cudaFuncSetAttribute(gemm_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 int(umma::SMEM_BYTES))) != cudaSuccess) return e0;
+  if ((e0 = cudaFuncSetAttribute(gemm_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 int(umma::SMEM_BYTES))) != cudaSuccess) return e0;
   if ((e0 = cudaFuncSetAttribute(gemm_toklane_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  int(tl_smem(8)))) != cudaSuccess) return e0;
   if ((e0 = cudaFuncSetAttribute(gemm_toklane_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -123,7 +123,9 @@ def test_batched_prefill_is_bitwise_the_token_by_token_path(gpu_ops, monkeypatch
     img = synth.build_gemma3_gguf(dims, wt, et, seed=11, embd_std=0.02)
     prompt = (np.arange(37, dtype=np.int32) * 7 + 3) % dims.vocab
     outs = {}
-    for mode, env in (("batched", {"LLMI_PREFILL_BATCH": "16"}), ("single", {"LLMI_NO_PREFILL": "1"})):
+    # batch 16: token-per-lane dp4a kernel; batch 36: the tcgen05 int8 kernel (>= 32 tokens) on a ragged token tile
+    for mode, env in (("batched", {"LLMI_PREFILL_BATCH": "16"}), ("umma", {"LLMI_PREFILL_BATCH": "36"}),
+                      ("single", {"LLMI_NO_PREFILL": "1"})):
         for k in ("LLMI_PREFILL_BATCH", "LLMI_NO_PREFILL"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
@@ -140,4 +142,5 @@ def test_batched_prefill_is_bitwise_the_token_by_token_path(gpu_ops, monkeypatch
         m.close()
     a, b = outs["batched"][0], outs["single"][0]
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert np.array_equal(outs["umma"][0].view(np.uint32), b.view(np.uint32))
     assert outs["batched"][1] < outs["single"][1] / 4  # 3 batches of launches instead of 37 tokens' worth
