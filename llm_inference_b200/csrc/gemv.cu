@@ -22,6 +22,7 @@
 //   * integer block dots are __dp4a, bit-exact with the reference's per-block
 //     sums; the fp32 scale product and accumulation follow the reference's
 //     formulas (summation ORDER differs: that is the documented 1e-5 bound).
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_fp16.h>
 
 #include <algorithm>
@@ -982,6 +983,35 @@ static uint4* g_bq = nullptr;
 static float* g_bd = nullptr;
 static size_t g_bq_items = 0, g_bd_floats = 0;
 bool g_umma = true;  // LLMI_NO_UMMA=1: token batches stay on the dp4a token-per-lane kernel (A/B)
+// Below this many tokens the dp4a token-per-lane kernel is at least as fast (measured, profiles/r01_notes.md: a CTA
+// of the tensor-core kernel has ~3 us of fixed cost); LLMI_UMMA_MIN_TOKENS overrides (>= 32: one token tile).
+uint32_t g_umma_min_tokens = 128;
+
+// The quant plane of a matrix as a 2-D tensor for TMA: [slab][the slab's K run] in 8-byte elements; box = 16 slabs x
+// one stage (8 blocks).  The encoder lives in the driver library: fetched once through the runtime, no -lcuda.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static cudaError_t make_plane_map(CUtensorMap* tm, const GemvArgs& a, bool is_q8) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr);
+    if (e != cudaSuccess) return e;
+    if (!p || qr != cudaDriverEntryPointSuccess) return cudaErrorNotSupported;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  const cuuint64_t per_blk = is_q8 ? 32 : 16;  // 8-byte elements per (slab, block): 8 rows x 32 / 16 bytes
+  const cuuint64_t dims[2] = {cuuint64_t(a.nb) * per_blk, cuuint64_t(a.n_slabs)};
+  const cuuint64_t strides[1] = {cuuint64_t(a.nb) * per_blk * 8};
+  const cuuint32_t box[2] = {cuuint32_t(umma::SB * per_blk), cuuint32_t(umma::TM / LLMI_SLAB)};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<uint8_t*>(a.q), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
 
 // Token batches of >= 32 tokens, Q4_0 / Q8_0 weights: exact int8 tensor-core path (umma_prefill.cuh).
 template <bool IS_Q8>
@@ -1047,8 +1077,11 @@ cudaError_t launch_umma(const GemvArgs* args, int n, cudaStream_t s) {
   while (gz < J && uint64_t(ctas) * tiles_n * gz < uint64_t(g_sm_count) * 2) ++gz;
   const uint32_t nj = (J + gz - 1) / gz;
   gz = (J + nj - 1) / nj;
-  e = llmi_launch(gemm_umma_kernel<IS_Q8>, dim3(ctas, tiles_n, gz), dim3(umma::WARPS * 32), umma::SMEM_BYTES, s, b,
-                  (const uint4*)g_bq, (const float*)g_bd, nj);
+  alignas(64) CUtensorMap tms[GEMV_MAX_BATCH];
+  for (int i = 0; i < GEMV_MAX_BATCH; ++i)
+    if ((e = make_plane_map(&tms[i], b.a[i], IS_Q8)) != cudaSuccess) return e;
+  e = llmi_launch(gemm_umma_kernel<IS_Q8>, dim3(ctas, tiles_n, gz), dim3(umma::WARPS * 32), umma::Cfg<IS_Q8>::SMEM_BYTES, s, b,
+                  (const uint4*)g_bq, (const float*)g_bd, nj, tms[0], tms[1], tms[2]);
   if (e != cudaSuccess) return e;
   const unsigned rb = unsigned(std::min<uint64_t>((outs + 255) / 256, uint64_t(g_sm_count) * 8));
   return llmi_launch(toklane_reduce_kernel, dim3(rb, n), dim3(256), 0, s, b);
@@ -1056,7 +1089,7 @@ cudaError_t launch_umma(const GemvArgs* args, int n, cudaStream_t s) {
 
 template <class B>
 cudaError_t launch_tokens(const GemvArgs* args, int n, cudaStream_t s) {
-  if (g_umma && args[0].n_tok >= 32) {
+  if (g_umma && args[0].n_tok >= g_umma_min_tokens) {
     if (std::is_same<B, BodyQ4_0>::value) return launch_umma<false>(args, n, s);
     if (std::is_same<B, BodyQ8_0>::value) return launch_umma<true>(args, n, s);
   }
@@ -1157,13 +1190,21 @@ void llmi_gemv_set_shape(int warps, int slabs_per_cta) {
   g_slabs_per_cta = slabs_per_cta;
 }
 
+// Bench / test knobs of the token-batched path, re-read by every llmi_model_load.
+void llmi_gemv_read_env() {
+  const char* e = getenv("LLMI_NO_UMMA");
+  g_umma = !(e && e[0] == '1');
+  e = getenv("LLMI_UMMA_MIN_TOKENS");
+  g_umma_min_tokens = e ? uint32_t(std::max(32, atoi(e))) : 128u;
+}
+
 cudaError_t llmi_gemv_init() {
   cudaError_t e0;
-  if (const char* e = getenv("LLMI_NO_UMMA")) g_umma = !(e[0] == '1');
+  llmi_gemv_read_env();
   if ((e0 = cudaFuncSetAttribute(gemm_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 int(umma::SMEM_BYTES))) != cudaSuccess) return e0;
+                                 int(umma::Cfg<false>::SMEM_BYTES))) != cudaSuccess) return e0;
   if ((e0 = cudaFuncSetAttribute(gemm_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 int(umma::SMEM_BYTES))) != cudaSuccess) return e0;
+                                 int(umma::Cfg<true>::SMEM_BYTES))) != cudaSuccess) return e0;
   if ((e0 = cudaFuncSetAttribute(gemm_toklane_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  int(tl_smem(8)))) != cudaSuccess) return e0;
   if ((e0 = cudaFuncSetAttribute(gemm_toklane_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1320,6 +1361,12 @@ cudaError_t llmi_launch_block_dots(const llmi_weight_s& w, const llmi_act_s& a, 
   block_dots_kernel<<<unsigned((total + 255) / 256), 256, 0, s>>>(g, w.type, dots_dev);
   return cudaGetLastError();
 }
+
+#ifdef LLMI_UMMA_TIMING
+extern "C" int llmi_debug_umma_stamps(long long* out /*[6][160]*/) {
+  return int(cudaMemcpyFromSymbol(out, g_umma_stamp, sizeof(long long) * 6 * 160));
+}
+#endif
 
 #ifdef LLMI_GEMV_TIMING
 extern "C" int llmi_debug_gemv_stamps(unsigned long long* out /*[256][6]*/, unsigned* n_launches, int reset) {

@@ -526,7 +526,7 @@ int load_impl(llmi_model_s* m, const uint8_t* image, uint64_t size, uint32_t t_m
     M_RC(upload_matrix(m, T("ffn_down"), F, E, &w.down, "ffn_down"));
   }
   const size_t mx = std::max<size_t>({E, F, HD});
-  m->batch = 64;
+  m->batch = 256;  // >= 128 tokens per batch go through the tensor-core mat-vec (gemv.cu launch_tokens)
   if (const char* e = getenv("LLMI_PREFILL_BATCH")) m->batch = uint32_t(std::max(1, atoi(e)));
   if (m->batch > t_max) m->batch = t_max;
   const size_t B = m->batch;
@@ -644,6 +644,7 @@ int llmi_model_load_shard(const void* gguf_image, uint64_t size, uint32_t max_po
   if (world < 1 || world > LLMI_MAX_WORLD || rank < 0 || rank >= world)
     return llmi_fail(LLMI_ERR_ARG, "llmi_model_load_shard: need 1 <= world <= 8 and 0 <= rank < world");
   if (max_positions == 0) max_positions = 4096;
+  llmi_gemv_read_env();
   std::unique_ptr<llmi_model_s> m(new llmi_model_s());
   int rc;
   try {

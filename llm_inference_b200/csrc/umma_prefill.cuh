@@ -27,11 +27,21 @@ namespace umma {
 
 constexpr int TM = 128, TN = 32;          // tile: weight rows x tokens
 constexpr int SB = 8;                     // quant blocks per shared-memory stage
-constexpr int NSTAGE = 3, NTMEM = 4;      // smem ring depth, TMEM ring depth (x TN columns)
-constexpr int WARPS = 12, EPI_WARP0 = 4;
+constexpr int NTMEM = 8;                  // TMEM ring depth (x TN columns) = blocks per stage: ring slot = block in stage
+constexpr int NDS = 8;                    // ring of activation-scale stages (1 KB each), deeper than the operand ring
+static_assert(NTMEM == SB, "the TMEM slot of a block is its index in the stage (static barrier addresses)");
+constexpr int WARPS = 12, EPI_WARP0 = 4;   // 8 epilogue warps: 4 TMEM lane quarters x 2 groups of EC token columns
+constexpr int EC = 16;                    // token columns per epilogue thread (measured: 8 warps x 16 columns beat 16 x 8)
 constexpr uint32_t A_BYTES = TM * SB * 32, B_BYTES = TN * SB * 32, D_BYTES = TN * SB * 4, P_BYTES = TM * SB * 16;
-constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES + D_BYTES + P_BYTES;  // 58368, a multiple of 1024
-constexpr size_t SMEM_BYTES = size_t(NSTAGE) * STAGE_BYTES + 1024;
+// The operand ring is what hides the refill latency (18 bulk copies per stage, ~3 us from issue to landed): a stage
+// is released by the MMA commit alone — the scales the epilogue still needs live in their own, deeper ring — and
+// the ring is as deep as shared memory allows: 5 stages of A+B for Q8_0, 3 of A+B+packed nibbles for Q4_0.
+template <bool IS_Q8>
+struct Cfg {
+  static constexpr int NSTAGE = IS_Q8 ? 5 : 3;
+  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES + (IS_Q8 ? 0u : P_BYTES);
+  static constexpr size_t SMEM_BYTES = size_t(NSTAGE) * STAGE_BYTES + size_t(NDS) * D_BYTES + 1024;
+};
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -48,7 +58,7 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
   return uint64_t((addr & 0x3ffffu) >> 4) | (uint64_t(lbo >> 4) << 16) | (uint64_t(sbo >> 4) << 32) | (1ull << 46);
 }
-// D[tmem] = A[smem] * B[smem]^T, int8 x int8 -> int32, M128 N32 K32, overwrite (no accumulate)
+// D[tmem] += A[smem] * B[smem]^T, int8 x int8 -> int32, M128 N32 K32 (D is pre-armed, see the epilogue)
 __device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
   asm volatile(
       "{\n"
@@ -56,23 +66,62 @@ __device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_
       "setp.ne.b32 p, %4, 0;\n"
       "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n"
       "}\n" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(0u), "r"(0u)
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(1u), "r"(0u)
       : "memory");
 }
 // cute::UMMA::InstrDescriptor: c_format S32 (2) @4, a/b format INT8 (1) @7/@10, K-major both, N>>3 @17, M>>4 @24
 constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | (uint32_t(TN >> 3) << 17) | (uint32_t(TM >> 4) << 24);
 
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&v)[16]) {
+// 2-D tiled TMA load (coordinates in elements of the tensor map: c0 innermost), completion on the mbarrier
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, uint32_t c0, uint32_t c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, int (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+// the registers of the pending load are operands, so nothing that reads them can move above the wait
+__device__ __forceinline__ void tmem_wait_ld(int (&v)[8]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, int (&v)[16]) {  // 16-column overload
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-      "tcgen05.wait::ld.sync.aligned;\n"
       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
         "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr)
       : "memory");
 }
-// exact int -> float for |x| < 2^22 on the full-rate pipes (I2F is a quarter-rate conversion)
-__device__ __forceinline__ float int_to_float(int x) { return __int_as_float(0x4B400000 + x) - 12582912.0f; }
+__device__ __forceinline__ void tmem_wait_ld(int (&v)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                 "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+               :
+               : "memory");
+}
+constexpr uint32_t MAGIC = 0x4B400000u;  // bits of 12582912.0f = 1.5 * 2^23: bits(MAGIC + x) = 12582912 + x for |x| < 2^22
+// this thread's row, 8 columns <- MAGIC (mg: eight registers holding MAGIC, kept live by the caller — the store
+// wants a register vector and re-materializing it costs eight moves per block)
+__device__ __forceinline__ void tmem_arm8(uint32_t taddr, const uint32_t (&mg)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr), "r"(mg[0]),
+               "r"(mg[1]), "r"(mg[2]), "r"(mg[3]), "r"(mg[4]), "r"(mg[5]), "r"(mg[6]), "r"(mg[7])
+               : "memory");
+}
+// this thread's row, EC columns <- MAGIC
+__device__ __forceinline__ void tmem_arm(uint32_t taddr, const uint32_t (&mg)[8]) {
+#pragma unroll
+  for (int c = 0; c < EC; c += 8) tmem_arm8(taddr + c, mg);
+}
 
 }  // namespace umma
 
@@ -100,13 +149,28 @@ __global__ void umma_pack_act_kernel(const uint8_t* __restrict__ act, uint32_t a
   }
 }
 
+#ifdef LLMI_UMMA_TIMING  // dev only (tools/umma_timeline.py): clock64 stamps of CTA (0,0,0), one row per role
+__device__ long long g_umma_stamp[6][160];
+#define UMMA_STAMP(role, idx)                                                                                   \
+  do {                                                                                                          \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (idx) < 160) g_umma_stamp[role][idx] = clock64(); \
+  } while (0)
+#else
+#define UMMA_STAMP(role, idx) do { } while (0)
+#endif
+
 // grid = (row tiles of all matrices of the batch, token tiles, K-chunk groups of `nj` chunks)
 template <bool IS_Q8>
 __global__ void __launch_bounds__(umma::WARPS * 32, 1)
-gemm_umma_kernel(const GemvBatch batch, const uint4* __restrict__ bq, const float* __restrict__ bd, uint32_t nj) {
+gemm_umma_kernel(const GemvBatch batch, const uint4* __restrict__ bq, const float* __restrict__ bd, uint32_t nj,
+                 const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
+                 const __grid_constant__ CUtensorMap tm2) {
   using namespace umma;
+  constexpr int NSTAGE = Cfg<IS_Q8>::NSTAGE;
+  constexpr uint32_t STAGE_BYTES = Cfg<IS_Q8>::STAGE_BYTES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full[NSTAGE], pk_full[NSTAGE], empty[NSTAGE], tfull[NTMEM], tempty[NTMEM];
+  __shared__ __align__(8) uint64_t full[NSTAGE], pk_full[NSTAGE], empty[NSTAGE], dfull[NDS], dempty[NDS], tfull[NTMEM],
+      tempty[NTMEM];
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int mi = 0;
@@ -120,17 +184,21 @@ gemm_umma_kernel(const GemvBatch batch, const uint4* __restrict__ bq, const floa
   const uint32_t b_begin = j0 * 16, b_end = active ? min(nb, j1 * 16) : b_begin;
   const uint32_t n_blk = b_end - b_begin, n_st = (n_blk + SB - 1) / SB;
   const uint32_t slab0 = tile_m * (TM / 8), n_sl = min(uint32_t(TM / 8), a.n_slabs - slab0);
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   auto stA = [&](uint32_t s) { return smem + size_t(s) * STAGE_BYTES; };                      // [slab 16][blk 8][h 2][r 8][16]
   auto stB = [&](uint32_t s) { return smem + size_t(s) * STAGE_BYTES + A_BYTES; };            // [blk 8][n/8 4][h 2][n%8 8][16]
-  auto stD = [&](uint32_t s) { return reinterpret_cast<float*>(smem + size_t(s) * STAGE_BYTES + A_BYTES + B_BYTES); };  // [blk 8][32]
-  auto stP = [&](uint32_t s) { return smem + size_t(s) * STAGE_BYTES + A_BYTES + B_BYTES + D_BYTES; };  // [slab 16][blk 8][r 8][16] nibbles
+  auto stP = [&](uint32_t s) { return smem + size_t(s) * STAGE_BYTES + A_BYTES + B_BYTES; };  // [slab 16][blk 8][r 8][16] nibbles
+  auto stD = [&](uint32_t d) { return reinterpret_cast<float*>(smem + size_t(NSTAGE) * STAGE_BYTES + size_t(d) * D_BYTES); };  // [blk 8][32]
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(&full[s], IS_Q8 ? 1 : 1 + 64);   // producer's expect_tx (+ the 64 unpack threads)
       mbar_init(&pk_full[s], 1);
-      mbar_init(&empty[s], 1 + (WARPS - EPI_WARP0));  // MMA commit + the epilogue warps (done with the scales)
+      mbar_init(&empty[s], 1);                    // MMA commit: the stage's operands have been read
+    }
+    for (int d = 0; d < NDS; ++d) {
+      mbar_init(&dfull[d], 1);
+      mbar_init(&dempty[d], WARPS - EPI_WARP0);  // the epilogue warps are done with the stage's scales
     }
     for (int t = 0; t < NTMEM; ++t) {
       mbar_init(&tfull[t], 1);
@@ -151,42 +219,68 @@ gemm_umma_kernel(const GemvBatch batch, const uint4* __restrict__ bq, const floa
 
   if (warp == 0) {
     // ------------------------------------------------------------------ producer
+    // One TMA tensor copy per stage for the weights: the quant plane is a 2-D tensor [slab][K run] and the stage is
+    // the box 16 slabs x (8 blocks' bytes), which lands as [slab][blk][...] — the operand layout.  (16 separate
+    // bulk copies of 2 KB ran at ~6 B/clk per SM: the copy engine works through them one after the other; the
+    // clock64 timeline of tools/umma_timeline.py showed a stage landing every ~7000 cycles whatever else changed.)
     if (lane == 0) {
+      const CUtensorMap* tm = mi == 0 ? &tm0 : (mi == 1 ? &tm1 : &tm2);
       for (uint32_t st = 0; st < n_st; ++st) {
         const uint32_t s = st % NSTAGE, ph = (st / NSTAGE) & 1;
+        const uint32_t ds = st % NDS;
         if (st >= NSTAGE) mbar_wait(&empty[s], ph ^ 1);
+        if (st >= NDS) mbar_wait(&dempty[ds], ((st / NDS) & 1) ^ 1);
+        UMMA_STAMP(0, st);
         const uint32_t b0 = b_begin + st * SB, nbs = min(uint32_t(SB), b_end - b0);
-        const uint32_t w_run = nbs * (IS_Q8 ? 256u : 128u);  // bytes of one slab's blocks [b0, b0+nbs): contiguous
         const uint32_t tb = (tile_n * nb + b0);
+        // the box is always whole (rows / blocks past the end arrive as zeros and are never used)
         if (IS_Q8) {
-          mbar_expect_tx(&full[s], n_sl * w_run + nbs * (1024u + 128u));
-          for (uint32_t sl = 0; sl < n_sl; ++sl)
-            bulk_g2s(stA(s) + sl * (SB * 256), a.q + (size_t(slab0 + sl) * nb + b0) * 256, w_run, &full[s]);
+          mbar_expect_tx(&full[s], A_BYTES + nbs * 1024u);
+          tma_load_2d(stA(s), tm, b0 * 32, slab0, &full[s]);
         } else {
-          mbar_expect_tx(&pk_full[s], n_sl * w_run);
-          for (uint32_t sl = 0; sl < n_sl; ++sl)
-            bulk_g2s(stP(s) + sl * (SB * 128), a.q + (size_t(slab0 + sl) * nb + b0) * 128, w_run, &pk_full[s]);
-          mbar_expect_tx(&full[s], nbs * (1024u + 128u));
+          mbar_expect_tx(&pk_full[s], P_BYTES);
+          tma_load_2d(stP(s), tm, b0 * 16, slab0, &pk_full[s]);
+          mbar_expect_tx(&full[s], nbs * 1024u);
         }
         bulk_g2s(stB(s), bq + size_t(tb) * 64, nbs * 1024u, &full[s]);
-        bulk_g2s(stD(s), bd + size_t(tb) * TN, nbs * 128u, &full[s]);
+        mbar_expect_tx(&dfull[ds], nbs * 128u);
+        bulk_g2s(stD(ds), bd + size_t(tb) * TN, nbs * 128u, &dfull[ds]);
       }
     }
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer
-    for (uint32_t i = 0; i < n_blk; ++i) {
-      const uint32_t st = i / SB, ib = i % SB, s = st % NSTAGE, t = i % NTMEM;
-      if (ib == 0) mbar_wait(&full[s], (st / NSTAGE) & 1);
-      if (i >= NTMEM) mbar_wait(&tempty[t], ((i / NTMEM) & 1) ^ 1);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint64_t ad = smem_desc(smem_u32(stA(s)) + ib * 256, 128, SB * 256);
-        const uint64_t bdsc = smem_desc(smem_u32(stB(s)) + ib * 1024, 128, 256);
-        mma_i8(tmem_base + t * TN, ad, bdsc, IDESC);
-        tc_commit(&tfull[t]);
-        if (ib == SB - 1 || i == n_blk - 1) tc_commit(&empty[s]);
+    // ONE thread runs this loop (tcgen05.mma / tcgen05.commit are single-thread instructions): the loop is a
+    // serial chain of uniform-datapath instructions, so it is kept to a wait, a descriptor add, the MMA and a
+    // commit per block — with the whole warp looping, electing and re-converging it was the kernel's bound
+    // (~580 cycles per block in the ncu source view, profiles/r01_notes.md).
+    if (lane == 0) {
+      const uint64_t a_hi = (uint64_t((SB * 256) >> 4) << 32) | (uint64_t(128 >> 4) << 16) | (1ull << 46);
+      const uint64_t b_hi = (uint64_t(256 >> 4) << 32) | (uint64_t(128 >> 4) << 16) | (1ull << 46);
+      const uint32_t a_lo0 = (smem_u32(stA(0)) & 0x3ffffu) >> 4, b_lo0 = (smem_u32(stB(0)) & 0x3ffffu) >> 4;
+      uint32_t s = 0, sph = 0;
+      for (uint32_t st = 0; st < n_st; ++st) {
+        mbar_wait(&full[s], sph);
+        UMMA_STAMP(1, st);
+        tc_fence_after();
+        const uint32_t nbs = min(uint32_t(SB), n_blk - st * SB);
+        const uint64_t ad0 = a_hi | uint64_t(a_lo0 + s * (STAGE_BYTES >> 4));
+        const uint64_t bd0 = b_hi | uint64_t(b_lo0 + s * (STAGE_BYTES >> 4));
+#pragma unroll
+        for (int ib = 0; ib < SB; ++ib) {
+          if (uint32_t(ib) < nbs) {
+            mbar_wait(&tempty[ib], st & 1);  // armed (completion 0 = the initial arming) and drained
+            tc_fence_after();
+            mma_i8(tmem_base + ib * TN, ad0 + uint64_t(ib * (256 >> 4)), bd0 + uint64_t(ib * (1024 >> 4)), IDESC);
+            tc_commit(&tfull[ib]);
+            UMMA_STAMP(2, st * SB + ib);
+          }
+        }
+        tc_commit(&empty[s]);  // arrives when the stage's MMAs have read their operands
+        if (++s == NSTAGE) {
+          s = 0;
+          sph ^= 1;
+        }
       }
-      __syncwarp();
     }
   } else if (warp < EPI_WARP0) {
     // ------------------------------------------- Q4_0: nibbles -> signed int8 core matrices
@@ -220,53 +314,95 @@ gemm_umma_kernel(const GemvBatch batch, const uint4* __restrict__ bq, const floa
     }
   } else {
     // ------------------------------------------------------------------ epilogue
-    const uint32_t q = warp & 3, g = (warp - EPI_WARP0) >> 2;  // TMEM lane quarter, column group of 16 tokens
+    // Every TMEM stage is kept "armed" with the integer 0x4B400000 in every cell and the MMA ACCUMULATES onto it:
+    // the bits of cell + dot are the float 12582912 + dot, so float(dot) is one FADD (exact for |dot| < 2^22)
+    // instead of an integer add + FADD or a quarter-rate I2F.  The thread that read a cell re-arms it.
+    const uint32_t q = warp & 3, g = (warp - EPI_WARP0) >> 2;  // TMEM lane quarter, group of EC token columns
     const uint32_t row = tile_m * TM + q * 32 + lane, rows_p = a.n_slabs * LLMI_SLAB;
     const bool row_ok = row < rows_p;
     const uint16_t* dsrc = reinterpret_cast<const uint16_t*>(a.d) + (size_t(row >> 3) * nb) * 8 + (row & 7);
-    const uint32_t tok0 = tile_n * TN + g * 16;
-    float acc[4][16];
+    const uint32_t tok0 = tile_n * TN + g * EC;
+    const uint32_t tcol = tmem_base + ((q * 32u) << 16) + g * EC;
+    uint32_t mg[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) asm volatile("mov.u32 %0, %1;" : "=r"(mg[k]) : "r"(MAGIC));  // opaque: stays in registers
+#pragma unroll
+    for (int t = 0; t < NTMEM; ++t) tmem_arm(tcol + t * TN, mg);
+    tmem_wait_st();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0)
+      for (int t = 0; t < NTMEM; ++t) mbar_arrive(&tempty[t]);
+    float acc[4][EC];
 #pragma unroll
     for (int c = 0; c < 4; ++c)
 #pragma unroll
-      for (int k = 0; k < 16; ++k) acc[c][k] = 0.0f;
+      for (int k = 0; k < EC; ++k) acc[c][k] = 0.0f;
+    uint16_t dwn[SB];  // this row's block scales, fetched one stage ahead (global, read-only path)
+#pragma unroll
+    for (int ib = 0; ib < SB; ++ib) dwn[ib] = (row_ok && b_begin + ib < b_end) ? ldg_stream(dsrc + size_t(b_begin + ib) * 8) : uint16_t(0);
+    int va[EC], vb[EC];  // block dots of the even / odd block in flight
+    if (n_blk) {
+      mbar_wait(&tfull[0], 0);
+      tc_fence_after();
+      tmem_ld8_issue(tcol, va);
+    }
     for (uint32_t st = 0; st < n_st; ++st) {
-      const uint32_t s = st % NSTAGE, b0 = b_begin + st * SB;
+      const uint32_t ds = st % NDS, b0 = b_begin + st * SB;
       float dw[SB];
 #pragma unroll
-      for (int ib = 0; ib < SB; ++ib)  // this row's block scales of the stage (global, read-only path)
-        dw[ib] = (row_ok && b0 + ib < b_end) ? h2f(ldg_stream(dsrc + size_t(b0 + ib) * 8)) : 0.0f;
-      mbar_wait(&full[s], (st / NSTAGE) & 1);  // the stage's activation scales are in shared memory
-      const float* dxs = stD(s) + g * 16;
+      for (int ib = 0; ib < SB; ++ib) dw[ib] = h2f(dwn[ib]);
+#pragma unroll
+      for (int ib = 0; ib < SB; ++ib) {
+        const uint32_t bn = b0 + SB + ib;
+        dwn[ib] = (row_ok && bn < b_end) ? ldg_stream(dsrc + size_t(bn) * 8) : uint16_t(0);
+      }
+      mbar_wait(&dfull[ds], (st / NDS) & 1);
+      const uint32_t dxs = smem_u32(stD(ds)) + g * (EC * 4);
 #pragma unroll
       for (int ib = 0; ib < SB; ++ib) {
         const uint32_t i = st * SB + ib;
         if (i < n_blk) {
-          const uint32_t t = i % NTMEM;
-          mbar_wait(&tfull[t], (i / NTMEM) & 1);
-          tc_fence_after();
-          int v[16];
-          tmem_ld16(tmem_base + ((q * 32u) << 16) + t * TN + g * 16, v);
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[t]);
-          float dx[16];
+          int(&v)[EC] = (ib & 1) ? vb : va;
+          int(&vn)[EC] = (ib & 1) ? va : vb;
+          const int t = ib, tn = (ib + 1) % NTMEM;  // TMEM slots of this block and the next
+          tmem_wait_ld(v);  // v = block i
+          if (warp == EPI_WARP0 && lane == 0) UMMA_STAMP(3, i);
+          if (i + 1 < n_blk) {  // next block's dots fly while this block is folded
+            mbar_wait(&tfull[tn], (ib + 1 == SB ? st + 1 : st) & 1);
+            tc_fence_after();
+            if (warp == EPI_WARP0 && lane == 0) UMMA_STAMP(4, i);
+            tmem_ld8_issue(tcol + tn * TN, vn);
+          }
+          // release the PREVIOUS block's slot now: its re-arming store was issued an iteration ago, so the wait is
+          // free — waiting right after the store put the tensor-memory store latency into every warp's per-block
+          // chain (each warp walks every block, so that chain, not the instruction count, set the pace)
+          if (i > 0) {
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[(ib + NTMEM - 1) % NTMEM]);
+          }
+          tmem_arm(tcol + t * TN, mg);
+          float dx[EC];
 #pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4) {
-            const float4 d4 = *reinterpret_cast<const float4*>(dxs + ib * TN + k4 * 4);
-            dx[k4 * 4] = d4.x; dx[k4 * 4 + 1] = d4.y; dx[k4 * 4 + 2] = d4.z; dx[k4 * 4 + 3] = d4.w;
+          for (int k4 = 0; k4 < EC / 4; ++k4) {
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(dx[k4 * 4]), "=f"(dx[k4 * 4 + 1]), "=f"(dx[k4 * 4 + 2]), "=f"(dx[k4 * 4 + 3])
+                         : "r"(dxs + ib * (TN * 4) + k4 * 16));
           }
 #pragma unroll
-          for (int k = 0; k < 16; ++k) {
-            const float fd = int_to_float(v[k]);
+          for (int k = 0; k < EC; ++k) {
+            const float fd = __int_as_float(v[k]) - 12582912.0f;
             if (IS_Q8) acc[ib & 3][k] = fmaf(__fmul_rn(fd, dw[ib]), dx[k], acc[ib & 3][k]);  // (int*dw)*dx, ops.cpp:820
             else acc[ib & 3][k] = fmaf(__fmul_rn(dw[ib], dx[k]), fd, acc[ib & 3][k]);         // ops.cpp:380-395
           }
+          if (warp == EPI_WARP0 && lane == 0) UMMA_STAMP(5, i);
           const uint32_t b = b0 + ib;
           if ((b & 15) == 15 || b == nb - 1) {  // end of a K-chunk: (s0+s1)+(s2+s3) -> part[chunk][token][row]
             const uint32_t j = b >> 4;
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
+            for (int k = 0; k < EC; ++k) {
               const float p = (acc[0][k] + acc[1][k]) + (acc[2][k] + acc[3][k]);
               if (row_ok && tok0 + k < a.n_tok) a.part[(size_t(j) * a.n_tok + tok0 + k) * rows_p + row] = p;
               acc[0][k] = acc[1][k] = acc[2][k] = acc[3][k] = 0.0f;
@@ -275,8 +411,9 @@ gemm_umma_kernel(const GemvBatch batch, const uint4* __restrict__ bq, const floa
         }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[s]);  // done with the stage's scales
+      if (lane == 0) mbar_arrive(&dempty[ds]);  // done with the stage's scales
     }
+    tmem_wait_st();  // the last re-arming store (nobody consumes it) must have landed before the dealloc
   }
   // ------------------------------------------------------------------ teardown
   tc_fence_before();

@@ -309,8 +309,8 @@ def test_batched_launch_equals_separate_launches(gpu_ops, port):
 @pytest.mark.parametrize("t", [synth.Q4_0, synth.Q8_0, synth.Q4_K, synth.Q6_K, synth.Q5_0, synth.BF16, synth.F16])
 def test_token_batched_matvec_is_bitwise_n_single_calls(gpu_ops, t):
     """llmi_gemm_tokens (prefill) == n_tokens x llmi_mat_vec_mul_dev, bit for bit: ragged N, partial last
-    K-chunk, token counts on both sides of the kernel switch (token loop < 16 <= token-per-lane) and of
-    the tile / lane-group sizes, and a row-shard handle."""
+    K-chunk, token counts on both sides of the kernel switches (token loop < 16 <= token-per-lane dp4a < 128 <=
+    tcgen05 int8 for Q4_0 / Q8_0) and of the tile / lane-group sizes, and a row-shard handle."""
     ops = gpu_ops
     kq = t in (synth.Q4_K, synth.Q6_K)
     for k, n in ((512, 40), (1280 if kq else 1184, 203), (2560 if kq else 2592, 77)):
@@ -320,7 +320,7 @@ def test_token_batched_matvec_is_bitwise_n_single_calls(gpu_ops, t):
         shard = ops.DeviceWeight(shard_blocks(w_host, synth.row_bytes(t, k), (8, 32)), t, k, n, 8, 32,
                                  blocks_are_shard=True)
         act = ops.Activation(k)
-        for m in (1, 5, 16, 37, 70):
+        for m in (1, 5, 16, 37, 70) + ((131,) if t in (synth.Q4_0, synth.Q8_0) else ()):
             x = np.random.default_rng(m).standard_normal((m, k)).astype(np.float32)
             x[0, :32] = 0.0  # an all-zero block
             xs, out = ops.DeviceVector(m * k, x), ops.DeviceVector(m * n, np.full(m * n, np.nan, np.float32))

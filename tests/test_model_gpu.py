@@ -124,9 +124,9 @@ def test_batched_prefill_is_bitwise_the_token_by_token_path(gpu_ops, monkeypatch
     prompt = (np.arange(37, dtype=np.int32) * 7 + 3) % dims.vocab
     outs = {}
     # batch 16: token-per-lane dp4a kernel; batch 36: the tcgen05 int8 kernel (>= 32 tokens) on a ragged token tile
-    for mode, env in (("batched", {"LLMI_PREFILL_BATCH": "16"}), ("umma", {"LLMI_PREFILL_BATCH": "36"}),
+    for mode, env in (("batched", {"LLMI_PREFILL_BATCH": "16"}), ("umma", {"LLMI_PREFILL_BATCH": "36", "LLMI_UMMA_MIN_TOKENS": "32"}),
                       ("single", {"LLMI_NO_PREFILL": "1"})):
-        for k in ("LLMI_PREFILL_BATCH", "LLMI_NO_PREFILL"):
+        for k in ("LLMI_PREFILL_BATCH", "LLMI_NO_PREFILL", "LLMI_UMMA_MIN_TOKENS"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)

@@ -18,6 +18,8 @@ ops.init_ops(1, 0)
 toks = [int(v) for v in sys.argv[1:]] or [64, 256]
 cases = [(synth.Q4_0, 1152, 6912), (synth.Q4_0, 6912, 1152), (synth.Q4_0, 5376, 21504), (synth.Q4_0, 21504, 5376),
          (synth.Q8_0, 3840, 15360)]
+if os.environ.get("CASE"):  # one case only (ncu captures)
+    cases = [cases[int(os.environ["CASE"])]]
 for t, k, n in cases:
     w = ops.DeviceWeight(synth.random_blocks(t, n, k, seed=1), t, k, n)
     for m in toks:
