@@ -133,10 +133,6 @@ int llmi_mat_vec_mul_dev(llmi_weight_t w, const float* x_dev, llmi_act_t a,
  * CTA (4, 8 or 16) and consecutive 8-row slabs per CTA; 0 = heuristic.  Results
  * never depend on it (canonical summation order). */
 int llmi_set_gemv_shape(int warps, int slabs_per_cta);
-/* Tuning knob for benches (A/B): 1 = every mat-vec CTA asks the copy engine to pull its whole weight
- * range into L2 before it blocks on its predecessor (cp.async.bulk.prefetch.L2); 0 (default: measured faster) = off.  Also read once from
- * the environment (LLMI_GEMV_PREFETCH) by llmi_init.  Results never depend on it. */
-int llmi_set_gemv_prefetch(int mode);
 
 /* Token-batched mat-vec (prefill; the M >= 16 entry SURVEY §8b calls llmi_gemm_prefill): x_dev is
  * [n_tokens][n_cols] fp32, out_dev [n_tokens][n_rows] fp32 (a row-shard handle fills its own rows).  The

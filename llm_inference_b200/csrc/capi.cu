@@ -114,7 +114,6 @@ int llmi_init(int device) {
   }
   g.sm_count = prop.multiProcessorCount;
   if (const char* e = getenv("LLMI_NO_PDL")) g_llmi_pdl = !(e[0] == '1');
-  if (const char* e = getenv("LLMI_GEMV_PREFETCH")) llmi_gemv_set_prefetch(e[0] != '0');
   LLMI_CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
   LLMI_CUDA_TRY(llmi_gemv_init());
   g.device = device;
@@ -337,12 +336,6 @@ int llmi_set_gemv_shape(int warps, int slabs_per_cta) {
   if ((warps != 0 && warps != 4 && warps != 8 && warps != 16) || slabs_per_cta < 0 || slabs_per_cta > 64)
     return llmi_fail(LLMI_ERR_ARG, "llmi_set_gemv_shape: warps in {0,4,8,16}, slabs_per_cta in [0,64]");
   llmi_gemv_set_shape(warps, slabs_per_cta);
-  return LLMI_OK;
-}
-
-int llmi_set_gemv_prefetch(int mode) {
-  if (mode < 0 || mode > 1) return llmi_fail(LLMI_ERR_ARG, "llmi_set_gemv_prefetch: mode in {0,1}");
-  llmi_gemv_set_prefetch(mode);
   return LLMI_OK;
 }
 

@@ -73,8 +73,6 @@ struct GemvArgs {
   // token-batched launches (prefill): n_tok activation buffers act_stride bytes apart, outputs out_stride floats apart
   uint32_t n_tok, act_stride, out_stride;
   float* part;  // token-per-lane kernel: chunk partials [chunk][token][8 * n_slabs] of this matrix
-  // bytes per slab of the q / d / x planes (0 = no L2 prefetch of the CTA's weight region)
-  uint32_t pf_q, pf_d, pf_x;
   // row-sharded model: element offset of this matrix' output vector inside the exchange buffer of every rank
   // (LL_NONE: plain local store to `out`)
   uint32_t ll_off;
@@ -470,27 +468,6 @@ __device__ __forceinline__ unsigned long long gtime() {
 // Called by every thread after its first weight loads are in flight: wait for
 // the predecessor grid (PDL), let thread 0 start the bulk copy of the activation
 // vector it produced, wait for the bytes to land.
-// L2 prefetch of a contiguous, 16-byte-multiple region (cp.async.bulk.prefetch -> UBLKPF): no destination,
-// no completion to wait for.
-__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-}
-
-// A CTA's weights are one contiguous range per plane (slab-major layout).  One
-// thread asks the copy engine to pull the whole range into L2 BEFORE the CTA
-// blocks on its predecessor: weights depend on nothing, so DRAM keeps streaming
-// through the tail of the previous grid, the PDL hand-over and the activation
-// staging, and every load after the first finds its line in L2 or in flight.
-__device__ __forceinline__ void prefetch_cta_weights(const GemvArgs& a, uint32_t slab0, uint32_t n_sl) {
-  if (!a.pf_q) return;
-  for (uint32_t s = 0; s < n_sl; ++s) {
-    const size_t sl = slab0 + s;
-    bulk_prefetch_l2(a.q + sl * a.pf_q, a.pf_q);
-    if (a.pf_d) bulk_prefetch_l2(a.d + sl * a.pf_d, a.pf_d);
-    if (a.pf_x) bulk_prefetch_l2(a.x + sl * a.pf_x, a.pf_x);
-  }
-}
-
 __device__ __forceinline__ void stage_activation(const GemvArgs& a, uint8_t* sm_act, uint64_t* bar, unsigned slot = 0) {
   pdl_wait();
   GEMV_STAMP(slot, 1);
@@ -502,7 +479,9 @@ __device__ __forceinline__ void stage_activation(const GemvArgs& a, uint8_t* sm_
   GEMV_STAMP(slot, 2);
 }
 
-template <class B, int W>
+// PUSH: row-sharded model — the rows go, flagged, into every rank's exchange buffer instead of `out` (its own
+// instantiation: the peer table and the tag would cost the single-GPU kernel registers, i.e. resident warps).
+template <class B, int W, bool PUSH>
 __global__ void __launch_bounds__(W * 32) gemv_slab_kernel(const GemvBatch batch) {
   extern __shared__ __align__(128) uint8_t sm_act[];  // [act_bytes][S * chunks * 8 floats]
   __shared__ __align__(8) uint64_t bar;
@@ -537,7 +516,6 @@ __global__ void __launch_bounds__(W * 32) gemv_slab_kernel(const GemvBatch batch
     FragSet<B, N> f;
     load_item<B, N>(f, a, slab0 + sl, j, r, sub);  // weights: independent of the predecessor kernel
     if (!waited) {
-      if (threadIdx.x == 32) prefetch_cta_weights(a, slab0, n_sl);
       stage_activation(a, sm_act, &bar, SLOT);
       waited = true;
     }
@@ -548,8 +526,7 @@ __global__ void __launch_bounds__(W * 32) gemv_slab_kernel(const GemvBatch batch
   __syncthreads();
   GEMV_STAMP(SLOT, 3);
   unsigned long long best = 0;
-  const bool push = a.ll_off != LL_NONE;
-  const uint32_t tag = push ? ll_tag(batch.tag) : 0u;  // every thread is past pdl_wait here
+  const uint32_t tag = PUSH ? ll_tag(batch.tag) : 0u;  // every thread is past pdl_wait here
   for (uint32_t idx = threadIdx.x; idx < n_sl * LLMI_SLAB; idx += W * 32) {
     const uint32_t sl = idx / LLMI_SLAB, rr = idx % LLMI_SLAB;
     const float* p = part + (size_t)sl * J * LLMI_SLAB + rr;
@@ -565,7 +542,7 @@ __global__ void __launch_bounds__(W * 32) gemv_slab_kernel(const GemvBatch batch
         const unsigned long long k = (uint64_t(u) << 32) | uint32_t(0xffffffffu - (a.row0 + row));
         best = k > best ? k : best;
       }
-      if (push) {  // the all-gather IS this store: one flagged 64-bit write into every rank's copy of the vector
+      if (PUSH) {  // the all-gather IS this store: one flagged 64-bit write into every rank's copy of the vector
         for (uint32_t p = 0; p < batch.peers.n; ++p)
           ll_store(batch.peers.base[p] + a.ll_off + a.row0 + row, __float_as_uint(sum), tag);
       } else {
@@ -863,7 +840,6 @@ using BF16 = BodyHalf<true>;
 // Benches can pin the CTA shape: g_warps in {0 (heuristic), 4, 8, 16},
 // g_slabs_per_cta in {0 (heuristic), 1..}.  Results never depend on it.
 int g_warps = 0, g_slabs_per_cta = 0;
-int g_prefetch = 0;  // L2 prefetch of each CTA's weight range ahead of the PDL wait: measured slower on the large matrices (profiles/r01_notes.md); LLMI_GEMV_PREFETCH=1 turns it on
 
 // (W, S) for one matrix.  Heuristic from tools/gemv_sweep.py
 // (profiles/r01_sweep_v4.jsonl): one slab per CTA and the fewest warps per CTA
@@ -917,10 +893,19 @@ cudaError_t launch_batch(const GemvArgs* args, int n, cudaStream_t s, const Gemv
     b.cta_end[i] = ctas;
   }
   if (ctas == 0) return cudaSuccess;
+  if (ll) {  // every matrix of a sharded launch pushes (model.cu passes an offset per matrix)
+    for (int i = 0; i < n; ++i)
+      if (b.a[i].ll_off == LL_NONE) return cudaErrorInvalidValue;
+    switch (W) {
+      case 4: return llmi_launch(gemv_slab_kernel<B, 4, true>, dim3(ctas), dim3(128), smem, s, b);
+      case 8: return llmi_launch(gemv_slab_kernel<B, 8, true>, dim3(ctas), dim3(256), smem, s, b);
+      default: return llmi_launch(gemv_slab_kernel<B, 16, true>, dim3(ctas), dim3(512), smem, s, b);
+    }
+  }
   switch (W) {
-    case 4: return llmi_launch(gemv_slab_kernel<B, 4>, dim3(ctas), dim3(128), smem, s, b);
-    case 8: return llmi_launch(gemv_slab_kernel<B, 8>, dim3(ctas), dim3(256), smem, s, b);
-    default: return llmi_launch(gemv_slab_kernel<B, 16>, dim3(ctas), dim3(512), smem, s, b);
+    case 4: return llmi_launch(gemv_slab_kernel<B, 4, false>, dim3(ctas), dim3(128), smem, s, b);
+    case 8: return llmi_launch(gemv_slab_kernel<B, 8, false>, dim3(ctas), dim3(256), smem, s, b);
+    default: return llmi_launch(gemv_slab_kernel<B, 16, false>, dim3(ctas), dim3(512), smem, s, b);
   }
 }
 
@@ -1144,11 +1129,17 @@ cudaError_t launch_tokens(const GemvArgs* args, int n, cudaStream_t s) {
 template <class B>
 cudaError_t optin() {
   cudaError_t e;
-  if ((e = cudaFuncSetAttribute(gemv_slab_kernel<B, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  if ((e = cudaFuncSetAttribute(gemv_slab_kernel<B, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 MAX_DYN_SMEM)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(gemv_slab_kernel<B, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  if ((e = cudaFuncSetAttribute(gemv_slab_kernel<B, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 MAX_DYN_SMEM)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(gemv_slab_kernel<B, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  if ((e = cudaFuncSetAttribute(gemv_slab_kernel<B, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                MAX_DYN_SMEM)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(gemv_slab_kernel<B, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                MAX_DYN_SMEM)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(gemv_slab_kernel<B, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                MAX_DYN_SMEM)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(gemv_slab_kernel<B, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 MAX_DYN_SMEM)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(gemv_slab_tok_kernel<B, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 MAX_DYN_SMEM)) != cudaSuccess) return e;
@@ -1182,8 +1173,6 @@ uint32_t llmi_gemv_chunks(const llmi_weight_s& w) {
   const uint32_t u = units_of(w), c = chunk_units_of(w.type);
   return (u + c - 1) / c;
 }
-
-void llmi_gemv_set_prefetch(int mode) { g_prefetch = mode; }
 
 void llmi_gemv_set_shape(int warps, int slabs_per_cta) {
   g_warps = warps;
@@ -1245,22 +1234,6 @@ static GemvArgs make_args(const llmi_weight_s& w, const llmi_act_s& a, float* ou
   g.out_stride = 0;
   g.part = nullptr;
   g.ll_off = LL_NONE;
-  g.pf_q = g.pf_d = g.pf_x = 0;
-  if (g_prefetch) {
-    uint32_t q = 16, d = 0, x = 0;  // bytes per (unit, row) cell of each plane, as laid out by llmi_plan_planes
-    switch (w.type) {
-      case LLMI_Q4_0: q = 16; d = 2; break;
-      case LLMI_Q8_0: q = 32; d = 2; break;
-      case LLMI_Q5_0: q = 16; d = 2; x = 4; break;
-      case LLMI_Q4_K: q = 128; x = 16; break;
-      case LLMI_Q6_K: q = 192; d = 2; x = 16; break;
-      default: break;
-    }
-    const uint32_t cells = uint32_t(w.nb) * LLMI_SLAB;
-    g.pf_q = cells * q;
-    g.pf_d = cells * d;
-    g.pf_x = cells * x;
-  }
   return g;
 }
 

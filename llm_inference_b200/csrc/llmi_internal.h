@@ -116,7 +116,6 @@ cudaError_t llmi_launch_gemv_tokens(const llmi_weight_s* const* ws, float* const
                                     cudaStream_t s);
 cudaError_t llmi_launch_gemv_batch(const llmi_weight_s* const* ws, float* const* outs, int n, const llmi_act_s& a,
                                    cudaStream_t s, const GemvLL* ll = nullptr);  // same format, same activation, n <= 3
-void llmi_gemv_set_prefetch(int mode);  // 1 = L2 prefetch of each CTA's weight range ahead of the PDL wait
 uint32_t llmi_gemv_chunks(const llmi_weight_s& w);
 void llmi_gemv_set_shape(int warps, int slabs_per_cta);  // 0 = heuristic  // K-chunks (work items) per slab
 cudaError_t llmi_launch_gemv_argmax(const llmi_weight_s& w, const llmi_act_s& a, float* out, unsigned long long* key,

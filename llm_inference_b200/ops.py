@@ -198,11 +198,6 @@ def block_dots(w: DeviceWeight, act: Activation) -> np.ndarray:
     return out
 
 
-def set_gemv_prefetch(mode: int = 1) -> None:
-    """Bench knob: L2 prefetch of each mat-vec CTA's weight range (1, default) or not (0)."""
-    _lib.check(_lib.load().llmi_set_gemv_prefetch(mode))
-
-
 def set_gemv_shape(warps: int = 0, slabs_per_cta: int = 0) -> None:
     """Pin the mat-vec CTA shape (benches); 0 = heuristic.  Results never change."""
     _lib.check(_lib.load().llmi_set_gemv_shape(warps, slabs_per_cta))
@@ -311,6 +306,6 @@ def registry_clear() -> None:
 __all__ = [
     "init_ops", "mat_vec_mul", "mat_vec_mul_q4_0", "mat_vec_mul_q4_k", "mat_vec_mul_q6_k", "mat_vec_mul_q8_0",
     "mat_vec_mul_q5_0", "mat_vec_mul_bf16", "mat_vec_mul_fp16", "quantize_row_q8_0", "quantize_row_q8_k",
-    "DeviceWeight", "DeviceVector", "TorchVector", "Activation", "gemv", "gemv_batch", "mat_vec_mul_dev", "block_dots", "set_gemv_shape", "set_gemv_prefetch",
+    "DeviceWeight", "DeviceVector", "TorchVector", "Activation", "gemv", "gemv_batch", "mat_vec_mul_dev", "block_dots", "set_gemv_shape",
     "device_sync", "registry_clear", "row_bytes",
 ]

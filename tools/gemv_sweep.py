@@ -69,7 +69,6 @@ def main():
     ap.add_argument("--shapes", default="0x0", help="comma list of WxS, 0x0 = heuristic")
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--with-quant", action="store_true")
-    ap.add_argument("--prefetch", default="1", help="comma list of L2-prefetch modes to A/B (0,1)")
     a = ap.parse_args()
     ops.init_ops(1, 0)
     peak = peak_gbs()
@@ -87,15 +86,13 @@ def main():
                  (Q4_0, 5376, 4096), (F16, 1152, 262144), (Q8_0, 3840, 15360), (Q4_K, 2560, 10240), (Q6_K, 10240, 2560)]
     for t, k, n in cases:
         for shape in a.shapes.split(","):
-            for pf in (int(v) for v in a.prefetch.split(",")):
-                W, S = (int(v) for v in shape.split("x"))
-                ops.set_gemv_prefetch(pf)
-                us, copies = time_case(t, k, n, (W, S), with_quant=a.with_quant)
-                b = synth.algorithmic_bytes(t, n, k)
-                gbs = b / us * 1e-3
-                print(json.dumps({"fmt": synth.TYPE_NAMES[t], "K": k, "N": n, "shape": shape, "pf": pf,
-                                  "us": round(us, 3), "alg_MB": round(b / 1e6, 3), "GBps": round(gbs, 1),
-                                  "frac_of_measured_peak": round(gbs / peak, 4), "copies": copies}), flush=True)
+            W, S = (int(v) for v in shape.split("x"))
+            us, copies = time_case(t, k, n, (W, S), with_quant=a.with_quant)
+            b = synth.algorithmic_bytes(t, n, k)
+            gbs = b / us * 1e-3
+            print(json.dumps({"fmt": synth.TYPE_NAMES[t], "K": k, "N": n, "shape": shape, "us": round(us, 3),
+                              "alg_MB": round(b / 1e6, 3), "GBps": round(gbs, 1),
+                              "frac_of_measured_peak": round(gbs / peak, 4), "copies": copies}), flush=True)
 
 
 if __name__ == "__main__":
