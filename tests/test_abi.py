@@ -30,6 +30,9 @@ def test_sass_is_sm_100a_with_bulk_copy_and_dp4a():
     assert "UBLKCP" in out.stdout, "activation staging must be a bulk async (TMA) copy"
     assert "IDP.4A" in out.stdout, "block dots must be dp4a"
     assert "LDG.E.NA.128" in out.stdout or "LDG.E.128" in out.stdout
+    # the prefill kernel is on the 5th-generation tensor cores: int8 UMMA, tensor-memory loads, TMA tensor copy
+    for mnemonic in ("UTCIMMA", "LDTM", "UTCBAR", "UTMALDG"):
+        assert mnemonic in out.stdout, f"{mnemonic} missing: the tcgen05 prefill kernel did not compile for sm_100a"
 
 
 def test_row_bytes_matches_reference_block_sizes():
