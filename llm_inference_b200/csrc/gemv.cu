@@ -1336,8 +1336,8 @@ cudaError_t llmi_launch_block_dots(const llmi_weight_s& w, const llmi_act_s& a, 
 }
 
 #ifdef LLMI_UMMA_TIMING
-extern "C" int llmi_debug_umma_stamps(long long* out /*[6][160]*/) {
-  return int(cudaMemcpyFromSymbol(out, g_umma_stamp, sizeof(long long) * 6 * 160));
+extern "C" int llmi_debug_umma_stamps(long long* out /*[10][160]*/) {
+  return int(cudaMemcpyFromSymbol(out, g_umma_stamp, sizeof(long long) * 10 * 160));
 }
 #endif
 

@@ -150,7 +150,7 @@ __global__ void umma_pack_act_kernel(const uint8_t* __restrict__ act, uint32_t a
 }
 
 #ifdef LLMI_UMMA_TIMING  // dev only (tools/umma_timeline.py): clock64 stamps of CTA (0,0,0), one row per role
-__device__ long long g_umma_stamp[6][160];
+__device__ long long g_umma_stamp[10][160];
 #define UMMA_STAMP(role, idx)                                                                                   \
   do {                                                                                                          \
     if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (idx) < 160) g_umma_stamp[role][idx] = clock64(); \
@@ -357,38 +357,48 @@ gemm_umma_kernel(const GemvBatch batch, const uint4* __restrict__ bq, const floa
     for (int c = 0; c < 4; ++c)
 #pragma unroll
       for (int k = 0; k < EC; ++k) acc[c][k] = 0.0f;
-    uint16_t dwn[SB];  // this row's block scales, fetched one stage ahead (global, read-only path)
+    // The loop body is ONE group of four blocks (one block per chain), not unrolled further: the fully unrolled
+    // stage (8 blocks, each with its own copy of the chunk-end stores) was ~5000 instructions = 80 KB of straight-line
+    // code that no instruction cache level kept, and the whole epilogue ran at ~5 cycles per instruction
+    // (profiles/r01_notes.md).  Per group: this row's four block scales were fetched one group ahead.
+    uint16_t dwn[4];
 #pragma unroll
-    for (int ib = 0; ib < SB; ++ib) dwn[ib] = (row_ok && b_begin + ib < b_end) ? ldg_stream(dsrc + size_t(b_begin + ib) * 8) : uint16_t(0);
+    for (int k = 0; k < 4; ++k) dwn[k] = (row_ok && b_begin + k < b_end) ? ldg_stream(dsrc + size_t(b_begin + k) * 8) : uint16_t(0);
     int va[EC], vb[EC];  // block dots of the even / odd block in flight
     if (n_blk) {
       mbar_wait(&tfull[0], 0);
       tc_fence_after();
       tmem_ld8_issue(tcol, va);
     }
-    for (uint32_t st = 0; st < n_st; ++st) {
-      const uint32_t ds = st % NDS, b0 = b_begin + st * SB;
-      float dw[SB];
+    const uint32_t n_grp = (n_blk + 3) / 4;
+#pragma unroll 1
+    for (uint32_t gi = 0; gi < n_grp; ++gi) {
+      const uint32_t st = gi >> 1, half = gi & 1, ds = st % NDS, bg = b_begin + gi * 4;  // bg: first block of the group
+      float dw[4];
 #pragma unroll
-      for (int ib = 0; ib < SB; ++ib) dw[ib] = h2f(dwn[ib]);
+      for (int k = 0; k < 4; ++k) dw[k] = h2f(dwn[k]);
 #pragma unroll
-      for (int ib = 0; ib < SB; ++ib) {
-        const uint32_t bn = b0 + SB + ib;
-        dwn[ib] = (row_ok && bn < b_end) ? ldg_stream(dsrc + size_t(bn) * 8) : uint16_t(0);
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t bn = bg + 4 + k;
+        dwn[k] = (row_ok && bn < b_end) ? ldg_stream(dsrc + size_t(bn) * 8) : uint16_t(0);
       }
-      mbar_wait(&dfull[ds], (st / NDS) & 1);
-      const uint32_t dxs = smem_u32(stD(ds)) + g * (EC * 4);
+      if (half == 0) {
+        if (warp == EPI_WARP0 && lane == 0) UMMA_STAMP(8, st);
+        mbar_wait(&dfull[ds], (st / NDS) & 1);
+        if (warp == EPI_WARP0 && lane == 0) UMMA_STAMP(9, st);
+      }
+      const uint32_t dxs = smem_u32(stD(ds)) + g * (EC * 4) + half * (4 * TN * 4);
 #pragma unroll
-      for (int ib = 0; ib < SB; ++ib) {
-        const uint32_t i = st * SB + ib;
+      for (int k4b = 0; k4b < 4; ++k4b) {  // block of the group = chain index
+        const uint32_t i = gi * 4 + k4b;
         if (i < n_blk) {
-          int(&v)[EC] = (ib & 1) ? vb : va;
-          int(&vn)[EC] = (ib & 1) ? va : vb;
-          const int t = ib, tn = (ib + 1) % NTMEM;  // TMEM slots of this block and the next
+          int(&v)[EC] = (k4b & 1) ? vb : va;
+          int(&vn)[EC] = (k4b & 1) ? va : vb;
+          const uint32_t t = half * 4 + k4b, tn = (t + 1) % NTMEM;  // TMEM slots of this block and the next
           tmem_wait_ld(v);  // v = block i
           if (warp == EPI_WARP0 && lane == 0) UMMA_STAMP(3, i);
           if (i + 1 < n_blk) {  // next block's dots fly while this block is folded
-            mbar_wait(&tfull[tn], (ib + 1 == SB ? st + 1 : st) & 1);
+            mbar_wait(&tfull[tn], (tn == 0 ? st + 1 : st) & 1);
             tc_fence_after();
             if (warp == EPI_WARP0 && lane == 0) UMMA_STAMP(4, i);
             tmem_ld8_issue(tcol + tn * TN, vn);
@@ -400,7 +410,7 @@ gemm_umma_kernel(const GemvBatch batch, const uint4* __restrict__ bq, const floa
             tmem_wait_st();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[(ib + NTMEM - 1) % NTMEM]);
+            if (lane == 0) mbar_arrive(&tempty[(t + NTMEM - 1) % NTMEM]);
           }
           tmem_arm(tcol + t * TN, mg);
           float dx[EC];
@@ -408,29 +418,33 @@ gemm_umma_kernel(const GemvBatch batch, const uint4* __restrict__ bq, const floa
           for (int k4 = 0; k4 < EC / 4; ++k4) {
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                          : "=f"(dx[k4 * 4]), "=f"(dx[k4 * 4 + 1]), "=f"(dx[k4 * 4 + 2]), "=f"(dx[k4 * 4 + 3])
-                         : "r"(dxs + ib * (TN * 4) + k4 * 16));
+                         : "r"(dxs + k4b * (TN * 4) + k4 * 16));
           }
 #pragma unroll
           for (int k = 0; k < EC; ++k) {
             const float fd = __int_as_float(v[k]) - 12582912.0f;
-            if (IS_Q8) acc[ib & 3][k] = fmaf(__fmul_rn(fd, dw[ib]), dx[k], acc[ib & 3][k]);  // (int*dw)*dx, ops.cpp:820
-            else acc[ib & 3][k] = fmaf(__fmul_rn(dw[ib], dx[k]), fd, acc[ib & 3][k]);         // ops.cpp:380-395
+            if (IS_Q8) acc[k4b][k] = fmaf(__fmul_rn(fd, dw[k4b]), dx[k], acc[k4b][k]);  // (int*dw)*dx, ops.cpp:820
+            else acc[k4b][k] = fmaf(__fmul_rn(dw[k4b], dx[k]), fd, acc[k4b][k]);         // ops.cpp:380-395
           }
           if (warp == EPI_WARP0 && lane == 0) UMMA_STAMP(5, i);
-          const uint32_t b = b0 + ib;
-          if ((b & 15) == 15 || b == nb - 1) {  // end of a K-chunk: (s0+s1)+(s2+s3) -> part[chunk][token][row]
-            const uint32_t j = b >> 4;
-#pragma unroll
-            for (int k = 0; k < EC; ++k) {
-              const float p = (acc[0][k] + acc[1][k]) + (acc[2][k] + acc[3][k]);
-              if (row_ok && tok0 + k < a.n_tok) a.part[(size_t(j) * a.n_tok + tok0 + k) * rows_p + row] = p;
-              acc[0][k] = acc[1][k] = acc[2][k] = acc[3][k] = 0.0f;
-            }
-          }
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&dempty[ds]);  // done with the stage's scales
+      // K-chunks are 16 blocks and groups 4, so a chunk ends with a group: the one holding block 15 (mod 16) or the
+      // last block of the row.  (s0+s1)+(s2+s3) -> part[chunk][token][row]
+      const uint32_t b_last = min(bg + 3, b_end - 1);
+      if ((b_last & 15) == 15 || b_last == nb - 1) {
+        const uint32_t j = b_last >> 4;
+#pragma unroll
+        for (int k = 0; k < EC; ++k) {
+          const float p = (acc[0][k] + acc[1][k]) + (acc[2][k] + acc[3][k]);
+          if (row_ok && tok0 + k < a.n_tok) a.part[(size_t(j) * a.n_tok + tok0 + k) * rows_p + row] = p;
+          acc[0][k] = acc[1][k] = acc[2][k] = acc[3][k] = 0.0f;
+        }
+      }
+      if (half == 1 || gi == n_grp - 1) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&dempty[ds]);  // done with the stage's scales
+      }
     }
     tmem_wait_st();  // the last re-arming store (nobody consumes it) must have landed before the dealloc
   }

@@ -26,15 +26,15 @@ o = ops.DeviceVector(m * n)
 for _ in range(3):
     ops.gemm_tokens(w, x, m, o)
 torch.cuda.synchronize()
-st = np.zeros((6, 160), np.int64)
+st = np.zeros((10, 160), np.int64)
 L.llmi_debug_umma_stamps.argtypes = [C.c_void_p]
 L.llmi_debug_umma_stamps(st.ctypes.data)
 t0 = st[0, 0]
 names = ["producer issues stage", "MMA sees stage full", "MMA issued block", "epi: dots landed", "epi: next tfull seen",
-         "epi: block folded"]
+         "epi: block folded", "epi: block done (+stores)", "epi: stage top", "epi: scales requested", "epi: dfull seen"]
 for r, nm in enumerate(names):
     row = st[r] - t0
-    cnt = 20 if r < 2 else 48
+    cnt = 12 if r in (0, 1, 7, 8, 9) else 40
     print(f"{nm:24s}", " ".join(str(int(v)) for v in row[:cnt]))
 for r in (2, 3, 5):
     d = np.diff(st[r, 8:120])
