@@ -181,6 +181,11 @@ int llmi_model_load(const void* gguf_image, uint64_t size, uint32_t max_position
  * then make the same forward / decode calls.  world = 1 is llmi_model_load. */
 int llmi_model_load_shard(const void* gguf_image, uint64_t size, uint32_t max_positions, int world, int rank,
                           llmi_model_t* out);
+/* The row range [*row_begin, *row_end) of an n_rows matrix that rank `rank` of `world` holds: contiguous,
+ * aligned to the 8-row slab of the device layout, as even as possible (trailing ranks may be empty when the
+ * matrix has fewer slabs than ranks).  Pure host arithmetic (no device needed); llmi_model_load_shard uses it
+ * for every matrix, a host that shards handles itself passes the result to llmi_weight_upload. */
+int llmi_shard_range(uint64_t n_rows, int world, int rank, uint64_t* row_begin, uint64_t* row_end);
 int llmi_model_comm_handle(llmi_model_t m, void* handle64);
 int llmi_model_comm_connect(llmi_model_t m, const void* handles);
 /* 1 if a kernel of this rank gave up (after ~4 s) waiting for a peer's rows; results are then invalid. */

@@ -49,6 +49,7 @@ SIGNATURES = {
     "llmi_host_quantize_row_q8_k": (_int, [_vp, _u64, _vp]),
     "llmi_model_load": (_int, [_vp, _u64, _u32, C.POINTER(_vp)]),
     "llmi_model_load_shard": (_int, [_vp, _u64, _u32, _int, _int, C.POINTER(_vp)]),
+    "llmi_shard_range": (_int, [_u64, _int, _int, C.POINTER(_u64), C.POINTER(_u64)]),
     "llmi_model_comm_handle": (_int, [_vp, _vp]),
     "llmi_model_comm_connect": (_int, [_vp, _vp]),
     "llmi_model_comm_error": (_int, [_vp]),

@@ -120,12 +120,7 @@ int upload_matrix(llmi_model_s* m, const llmi::GgufTensor* t, uint64_t k, uint64
   // this rank's rows: contiguous, slab-aligned, as even as possible (shard.row_ranges; the thread partition of
   // ops.cpp:439-448 lifted to devices)
   uint64_t rb = 0, re = n;
-  if (m->sharded()) {
-    const uint64_t units = (n + LLMI_SLAB - 1) / LLMI_SLAB, W = uint64_t(m->world), r = uint64_t(m->rank);
-    const uint64_t first = r * (units / W) + std::min(r, units % W), cnt = units / W + (r < units % W ? 1 : 0);
-    rb = std::min(n, first * LLMI_SLAB);
-    re = std::min(n, (first + cnt) * LLMI_SLAB);
-  }
+  M_RC(llmi_shard_range(n, m->world, m->rank, &rb, &re));
   M_RC(llmi_weight_upload(t->data, t->type, k, n, rb, re, out));
   m->weight_bytes += llmi_row_bytes(t->type, k) * (re - rb);
   return LLMI_OK;
@@ -632,6 +627,16 @@ int ensure_decode_graph(llmi_model_s* m) {
 }  // namespace
 
 extern "C" {
+
+int llmi_shard_range(uint64_t n_rows, int world, int rank, uint64_t* row_begin, uint64_t* row_end) {
+  if (!row_begin || !row_end) return llmi_fail(LLMI_ERR_ARG, "llmi_shard_range: null pointer");
+  if (world < 1 || rank < 0 || rank >= world) return llmi_fail(LLMI_ERR_ARG, "llmi_shard_range: need 0 <= rank < world");
+  const uint64_t units = (n_rows + LLMI_SLAB - 1) / LLMI_SLAB, W = uint64_t(world), r = uint64_t(rank);
+  const uint64_t first = r * (units / W) + std::min(r, units % W), cnt = units / W + (r < units % W ? 1 : 0);
+  *row_begin = std::min(n_rows, first * LLMI_SLAB);
+  *row_end = std::min(n_rows, (first + cnt) * LLMI_SLAB);
+  return LLMI_OK;
+}
 
 int llmi_model_load(const void* gguf_image, uint64_t size, uint32_t max_positions, llmi_model_t* out) {
   return llmi_model_load_shard(gguf_image, size, max_positions, 1, 0, out);

@@ -76,3 +76,21 @@ def test_sharded_matvec_allgather_equals_unsharded(world):
         p.join(timeout=180)
         assert p.exitcode == 0
     assert q.get(timeout=5) == 1
+
+
+def test_c_abi_shard_range_is_the_python_partition():
+    """llmi_shard_range (what llmi_model_load_shard applies to every matrix) == shard.row_ranges: contiguous,
+    slab-aligned, covering, as even as possible — for ragged row counts and more ranks than slabs."""
+    import ctypes as C
+
+    from llm_inference_b200 import _lib
+    L = _lib.load()
+    for n in (0, 1, 7, 8, 9, 40, 203, 256, 520, 1152, 6912, 262144, 262208):
+        for world in (1, 2, 3, 4, 5, 8):
+            want = shard.row_ranges(n, world) if n else [(0, 0)] * world
+            for rank in range(world):
+                b, e = C.c_uint64(), C.c_uint64()
+                assert L.llmi_shard_range(n, world, rank, C.byref(b), C.byref(e)) == 0
+                assert (b.value, e.value) == want[rank], (n, world, rank)
+    b, e = C.c_uint64(), C.c_uint64()
+    assert L.llmi_shard_range(8, 2, 2, C.byref(b), C.byref(e)) != 0  # rank out of range
