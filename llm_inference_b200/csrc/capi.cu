@@ -131,6 +131,7 @@ int llmi_shutdown(void) {
   if (g.x_dev) cudaFree(g.x_dev);
   if (g.o_dev) cudaFree(g.o_dev);
   if (g.scratch) cudaFree(g.scratch);
+  llmi_gemv_shutdown();
   if (g.stream) cudaStreamDestroy(g.stream);
   g = Context();
   return LLMI_OK;

@@ -1179,6 +1179,17 @@ void llmi_gemv_set_shape(int warps, int slabs_per_cta) {
   g_slabs_per_cta = slabs_per_cta;
 }
 
+// llmi_shutdown: the grow-only scratch of the token-batched launches (chunk partials, packed activations).
+void llmi_gemv_shutdown() {
+  if (g_part) cudaFree(g_part);
+  if (g_bq) cudaFree(g_bq);
+  if (g_bd) cudaFree(g_bd);
+  g_part = nullptr;
+  g_bq = nullptr;
+  g_bd = nullptr;
+  g_part_floats = g_bq_items = g_bd_floats = 0;
+}
+
 // Bench / test knobs of the token-batched path, re-read by every llmi_model_load.
 void llmi_gemv_read_env() {
   const char* e = getenv("LLMI_NO_UMMA");

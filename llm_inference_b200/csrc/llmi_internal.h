@@ -107,6 +107,7 @@ cudaError_t llmi_launch_export_q8_0(const uint8_t* buf, uint64_t n, uint8_t* out
 cudaError_t llmi_launch_export_q8_k(const uint8_t* buf, uint64_t n, uint8_t* out292, cudaStream_t s);
 
 // gemv.cu
+void llmi_gemv_shutdown();  // frees the scratch of the token-batched launches
 void llmi_gemv_read_env();  // LLMI_NO_UMMA, LLMI_UMMA_MIN_TOKENS
 cudaError_t llmi_gemv_init();  // opt-in dynamic shared memory for every instantiation
 cudaError_t llmi_launch_gemv(const llmi_weight_s& w, const llmi_act_s& a, float* out, cudaStream_t s);
