@@ -74,6 +74,8 @@ class Port:
         for n in ("q4_0", "q8_0", "q4_k", "q6_k"):
             getattr(L, f"orc_gemv_{n}").argtypes = [_f32p, _u8p, _f32p, C.c_size_t, C.c_size_t, _i32p]
         L.orc_gemv_q5_0.argtypes = [_f32p, _u8p, _f32p, C.c_size_t, C.c_size_t]
+        L.orc_gemv_q4_0_canonical.argtypes = [_f32p, _u8p, _f32p, C.c_size_t, C.c_size_t]
+        L.orc_gemv_q8_0_canonical.argtypes = [_f32p, _u8p, _f32p, C.c_size_t, C.c_size_t]
         L.orc_gemv_bf16.argtypes = [_f32p, _u16p, _f32p, C.c_size_t, C.c_size_t]
         L.orc_gemv_f16.argtypes = [_f32p, _u16p, _f32p, C.c_size_t, C.c_size_t]
         L.orc_mat_vec_mul.restype = C.c_int
@@ -129,6 +131,16 @@ class Port:
             self.L.orc_gemv_f16(_p(o, _f32p), _p(w.view(np.uint16), _u16p), _p(x, _f32p), n_rows, n_cols)
         else:
             raise RuntimeError(f"mat_vec_mul: unsupported tensor type {ggml_type}")
+        return o
+
+    def mat_vec_mul_canonical(self, ggml_type: int, w: np.ndarray, x: np.ndarray, n_rows: int, n_cols: int) -> np.ndarray:
+        """Q4_0 / Q8_0 mat-vec with the reference's per-block terms summed in the DEVICE's canonical order: what
+        every GPU kernel of the path must reproduce bit for bit."""
+        w = np.ascontiguousarray(w).view(np.uint8).ravel()
+        x = np.ascontiguousarray(x, np.float32)
+        o = np.zeros(n_rows, np.float32)
+        fn = {2: self.L.orc_gemv_q4_0_canonical, 8: self.L.orc_gemv_q8_0_canonical}[ggml_type]
+        fn(_p(o, _f32p), _p(w, _u8p), _p(x, _f32p), n_rows, n_cols)
         return o
 
     def dequantize_row(self, ggml_type: int, row: np.ndarray, n_cols: int) -> np.ndarray:

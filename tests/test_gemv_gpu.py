@@ -341,3 +341,28 @@ def test_token_batched_matvec_is_bitwise_n_single_calls(gpu_ops, t):
         act.close()
         w.close()
         shard.close()
+
+
+@pytest.mark.parametrize("t", [Q4_0, Q8_0])
+def test_every_kernel_is_bitwise_the_canonical_order_oracle(gpu_ops, port, t):
+    """The CPU restatement of the device's summation order (oracle/qgemv_oracle.c, orc_gemv_*_canonical: the
+    reference's per-block terms, chunks of 16 blocks, four chains, (s0+s1)+(s2+s3), chunks left to right) against
+    all three GPU kernels of the path — one-token dp4a, token-per-lane dp4a (37 tokens), tcgen05 int8 (131 tokens) —
+    BIT FOR BIT, on ragged shapes with a partial last chunk."""
+    ops = gpu_ops
+    for k, n in ((1184, 203), (2592, 77), (512, 40)):
+        w_host = _weights(t, n, k, seed=3 * k + n)
+        w = ops.DeviceWeight(w_host, t, k, n)
+        act = ops.Activation(k)
+        for m in (1, 37, 131):
+            x = np.random.default_rng(m + k).standard_normal((m, k)).astype(np.float32)
+            want = np.stack([port.mat_vec_mul_canonical(t, w_host, x[i], n, k) for i in range(m)])
+            if m == 1:
+                dx, do = ops.DeviceVector(k, x[0]), ops.DeviceVector(n)
+                ops.mat_vec_mul_dev(w, dx, act, do)
+                got = do.get().reshape(1, n)
+            else:
+                xs, out = ops.DeviceVector(m * k, x), ops.DeviceVector(m * n)
+                ops.gemm_tokens(w, xs, m, out)
+                got = out.get().reshape(m, n)
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (t, k, n, m)

@@ -182,3 +182,20 @@ def test_block_dots_are_consistent(port):
     dw = w.reshape(n, k // 32, 18)[:, :, :2].copy().view(np.float16).astype(np.float64).reshape(n, -1)
     exact = (dots.reshape(n, -1) * dw * dx).sum(axis=1)
     assert np.abs(o - exact).max() <= 1e-5 * np.abs(exact).max()
+
+
+@pytest.mark.parametrize("t,k,n", [(synth.Q4_0, 1152, 64), (synth.Q4_0, 1184, 33), (synth.Q8_0, 2592, 17),
+                                   (synth.Q4_0, 96, 8), (synth.Q8_0, 32, 8), (synth.Q4_0, 5376, 24)])
+def test_canonical_order_restatement_is_within_the_bound_of_the_reference_order(port, t, k, n):
+    """The device's summation order restated on the CPU (orc_gemv_*_canonical: chunks of 16 blocks, four chains,
+    (s0+s1)+(s2+s3), chunks left to right — what the GPU kernels are checked against BIT FOR BIT in
+    tests/test_gemv_gpu.py) uses the reference's per-block terms, so it differs from the reference-order port only
+    by fp32 summation order: <= 1e-5 of max|o| (north_star's bar), and exactly equal when a row is one block."""
+    w = synth.random_blocks(t, n, k, seed=k + n)
+    x = np.random.default_rng(k).standard_normal(k).astype(np.float32)
+    ref_order = port.mat_vec_mul(t, w, x, n, k)
+    canonical = port.mat_vec_mul_canonical(t, w, x, n, k)
+    scale = float(np.abs(ref_order).max())
+    assert float(np.abs(canonical - ref_order).max()) <= 1e-5 * scale
+    if k == 32 and t == synth.Q8_0:  # one block: (dot*dw)*dx, a single rounding sequence either way
+        assert np.array_equal(canonical.view(np.uint32), ref_order.view(np.uint32))
