@@ -76,6 +76,10 @@ class Port:
         L.orc_gemv_q5_0.argtypes = [_f32p, _u8p, _f32p, C.c_size_t, C.c_size_t]
         L.orc_gemv_q4_0_canonical.argtypes = [_f32p, _u8p, _f32p, C.c_size_t, C.c_size_t]
         L.orc_gemv_q8_0_canonical.argtypes = [_f32p, _u8p, _f32p, C.c_size_t, C.c_size_t]
+        for n in ("q4_k", "q6_k", "q5_0"):
+            getattr(L, f"orc_gemv_{n}_canonical").argtypes = [_f32p, _u8p, _f32p, C.c_size_t, C.c_size_t]
+        for n in ("f16", "bf16"):
+            getattr(L, f"orc_gemv_{n}_canonical").argtypes = [_f32p, _u16p, _f32p, C.c_size_t, C.c_size_t]
         L.orc_gemv_bf16.argtypes = [_f32p, _u16p, _f32p, C.c_size_t, C.c_size_t]
         L.orc_gemv_f16.argtypes = [_f32p, _u16p, _f32p, C.c_size_t, C.c_size_t]
         L.orc_mat_vec_mul.restype = C.c_int
@@ -134,13 +138,17 @@ class Port:
         return o
 
     def mat_vec_mul_canonical(self, ggml_type: int, w: np.ndarray, x: np.ndarray, n_rows: int, n_cols: int) -> np.ndarray:
-        """Q4_0 / Q8_0 mat-vec with the reference's per-block terms summed in the DEVICE's canonical order: what
-        every GPU kernel of the path must reproduce bit for bit."""
+        """Mat-vec with the reference's per-block terms summed in the DEVICE's canonical order: what every GPU
+        kernel of the path must reproduce bit for bit (all seven formats)."""
         w = np.ascontiguousarray(w).view(np.uint8).ravel()
         x = np.ascontiguousarray(x, np.float32)
         o = np.zeros(n_rows, np.float32)
-        fn = {2: self.L.orc_gemv_q4_0_canonical, 8: self.L.orc_gemv_q8_0_canonical}[ggml_type]
-        fn(_p(o, _f32p), _p(w, _u8p), _p(x, _f32p), n_rows, n_cols)
+        name = {2: "q4_0", 8: "q8_0", 12: "q4_k", 14: "q6_k", 6: "q5_0", 1: "f16", 30: "bf16"}[ggml_type]
+        fn = getattr(self.L, f"orc_gemv_{name}_canonical")
+        if ggml_type in (1, 30):
+            fn(_p(o, _f32p), _p(w.view(np.uint16), _u16p), _p(x, _f32p), n_rows, n_cols)
+        else:
+            fn(_p(o, _f32p), _p(w, _u8p), _p(x, _f32p), n_rows, n_cols)
         return o
 
     def dequantize_row(self, ggml_type: int, row: np.ndarray, n_cols: int) -> np.ndarray:

@@ -54,6 +54,11 @@ void orc_gemv_f16(float* o, const uint16_t* w, const float* x, size_t n_rows,
  * (s0+s1)+(s2+s3), chunks left to right): GPU outputs must equal these bit for bit. */
 void orc_gemv_q4_0_canonical(float* o, const uint8_t* w, const float* x, size_t n_rows, size_t n_cols);
 void orc_gemv_q8_0_canonical(float* o, const uint8_t* w, const float* x, size_t n_rows, size_t n_cols);
+void orc_gemv_q4_k_canonical(float* o, const uint8_t* w, const float* x, size_t n_rows, size_t n_cols);
+void orc_gemv_q6_k_canonical(float* o, const uint8_t* w, const float* x, size_t n_rows, size_t n_cols);
+void orc_gemv_q5_0_canonical(float* o, const uint8_t* w, const float* x, size_t n_rows, size_t n_cols);
+void orc_gemv_f16_canonical(float* o, const uint16_t* w, const float* x, size_t n_rows, size_t n_cols);
+void orc_gemv_bf16_canonical(float* o, const uint16_t* w, const float* x, size_t n_rows, size_t n_cols);
 
 /* dispatcher: 0 ok, 1 unsupported type (the reference throws, ops.cpp:952-955) */
 int orc_mat_vec_mul(uint32_t ggml_type, float* o, const uint8_t* w,

@@ -343,18 +343,19 @@ def test_token_batched_matvec_is_bitwise_n_single_calls(gpu_ops, t):
         shard.close()
 
 
-@pytest.mark.parametrize("t", [Q4_0, Q8_0])
+@pytest.mark.parametrize("t", [Q4_0, Q8_0, Q4_K, Q6_K, Q5_0, F16, BF16])
 def test_every_kernel_is_bitwise_the_canonical_order_oracle(gpu_ops, port, t):
     """The CPU restatement of the device's summation order (oracle/qgemv_oracle.c, orc_gemv_*_canonical: the
-    reference's per-block terms, chunks of 16 blocks, four chains, (s0+s1)+(s2+s3), chunks left to right) against
-    all three GPU kernels of the path — one-token dp4a, token-per-lane dp4a (37 tokens), tcgen05 int8 (131 tokens) —
-    BIT FOR BIT, on ragged shapes with a partial last chunk."""
+    reference's per-block terms; K-chunks, four sub-lane chains per chunk, (s0+s1)+(s2+s3), chunks left to right)
+    against every GPU kernel of the path — one-token, token loop (5 tokens), token-per-lane dp4a (37), tcgen05 int8
+    (131; Q4_0 / Q8_0) — BIT FOR BIT, on ragged shapes with a partial last chunk."""
     ops = gpu_ops
-    for k, n in ((1184, 203), (2592, 77), (512, 40)):
+    kq = t in (Q4_K, Q6_K)
+    for k, n in ((1280 if kq else 1184, 203), (2560 if kq else 2592, 77), (512, 40)):
         w_host = _weights(t, n, k, seed=3 * k + n)
         w = ops.DeviceWeight(w_host, t, k, n)
         act = ops.Activation(k)
-        for m in (1, 37, 131):
+        for m in (1, 5, 37) + ((131,) if t in (Q4_0, Q8_0) else ()):
             x = np.random.default_rng(m + k).standard_normal((m, k)).astype(np.float32)
             want = np.stack([port.mat_vec_mul_canonical(t, w_host, x[i], n, k) for i in range(m)])
             if m == 1:

@@ -185,7 +185,9 @@ def test_block_dots_are_consistent(port):
 
 
 @pytest.mark.parametrize("t,k,n", [(synth.Q4_0, 1152, 64), (synth.Q4_0, 1184, 33), (synth.Q8_0, 2592, 17),
-                                   (synth.Q4_0, 96, 8), (synth.Q8_0, 32, 8), (synth.Q4_0, 5376, 24)])
+                                   (synth.Q4_0, 96, 8), (synth.Q8_0, 32, 8), (synth.Q4_0, 5376, 24),
+                                   (synth.Q4_K, 1280, 19), (synth.Q6_K, 2560, 19), (synth.Q5_0, 1184, 19),
+                                   (synth.F16, 1160, 19), (synth.BF16, 1152, 19)])
 def test_canonical_order_restatement_is_within_the_bound_of_the_reference_order(port, t, k, n):
     """The device's summation order restated on the CPU (orc_gemv_*_canonical: chunks of 16 blocks, four chains,
     (s0+s1)+(s2+s3), chunks left to right — what the GPU kernels are checked against BIT FOR BIT in
