@@ -1074,7 +1074,7 @@ cudaError_t launch_umma(const GemvArgs* args, int n, cudaStream_t s) {
 
 template <class B>
 cudaError_t launch_tokens(const GemvArgs* args, int n, cudaStream_t s) {
-  if (g_umma && args[0].n_tok >= g_umma_min_tokens) {
+  if (g_umma && args[0].n_tok >= g_umma_min_tokens && args[0].nb >= uint32_t(umma::SB)) {  // K >= one stage (256)
     if (std::is_same<B, BodyQ4_0>::value) return launch_umma<false>(args, n, s);
     if (std::is_same<B, BodyQ8_0>::value) return launch_umma<true>(args, n, s);
   }
