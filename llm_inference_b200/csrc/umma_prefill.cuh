@@ -7,20 +7,23 @@
 // GEMM cannot reproduce that; an int8 MMA with K = 32 can: one tcgen05.mma per quant block gives the int32
 // block dots of a 128-row x 32-token tile in tensor memory, bit-identical to the dp4a dots, and the fp32 part
 // (float(dot), dw*dx, fma into the chain of the canonical summation order) is the epilogue.  Results are
-// bit-identical to the one-token kernel; the tensor pipe is ~25 % busy by construction (the per-block fp32
-// epilogue on the CUDA cores is the bound — 4 ops per output per block vs ~14 for the dp4a kernel).
+// bit-identical to the one-token kernel.  The per-block fp32 epilogue on the CUDA cores is the bound by
+// construction: 3 ops per output per block (vs ~14 for the dp4a kernel), i.e. the tensor pipe can be ~15 % busy at
+// best; measured 2.4 % (DESIGN.md 4.6 says why and what is next).
 //
 // CTA = 128 weight rows (16 slabs) x 32 tokens x a range of K-chunks, 12 warps, warp-specialized:
-//   warp 0      producer: bulk async copies (UBLKCP) of the stage's weights (one contiguous run per slab: the
-//               Q8_0 slab layout IS the UMMA K-major core-matrix layout, 8 rows x 16 bytes), of the token tile's
-//               activation quants (pre-packed into core-matrix order by umma_pack_act_kernel) and fp32 scales
-//   warp 1      tensor-memory allocation; one lane issues tcgen05.mma (M128 N32 K32, no accumulate) per block
-//               into a ring of 4 TMEM stages and commits to mbarriers
+//   warp 0      producer: ONE 2-D TMA tensor copy per stage for the weights (quant plane = tensor [slab][K run], box =
+//               16 slabs x 8 blocks; the Q8_0 slab layout IS the UMMA K-major core-matrix layout, 8 rows x 16 bytes),
+//               one bulk copy each for the token tile's activation quants (pre-packed into core-matrix order by
+//               umma_pack_act_kernel) and fp32 scales; its idle lanes prefetch the weight lines 8 stages ahead into L2
+//   warp 1      tensor-memory allocation; one thread issues tcgen05.mma (M128 N32 K32, accumulating onto the "armed"
+//               cells, see the epilogue) per block into a ring of 8 TMEM slots and commits to mbarriers
 //   warps 2-3   Q4_0 only: unpack the nibbles of a stage to signed int8 core matrices (generic -> async proxy fence)
 //   warps 4-11  epilogue: tcgen05.ld the block dots (thread = row, 16 token columns), four chain accumulators
 //               per (row, token) = the four sub-lanes of gemv_slab_kernel, chunk partial (s0+s1)+(s2+s3) stored
 //               to part[chunk][token][row]; toklane_reduce_kernel adds the chunk partials left to right.
-// Shared-memory ring: 3 stages of 8 blocks (A 32 KB int8 + B 8 KB + scales 1 KB, + 16 KB packed nibbles for Q4_0).
+// Shared memory: 5 (Q8_0) / 3 (Q4_0) operand stages of 8 blocks (A 32 KB int8 + B 8 KB, + 16 KB packed nibbles for
+// Q4_0) released by the MMA commit alone, and a deeper ring of 8 scale stages (1 KB) the epilogue releases.
 #pragma once
 
 namespace umma {
