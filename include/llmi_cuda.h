@@ -138,8 +138,10 @@ int llmi_set_gemv_shape(int warps, int slabs_per_cta);
  * [n_tokens][n_cols] fp32, out_dev [n_tokens][n_rows] fp32 (a row-shard handle fills its own rows).  The
  * reference has no batched matmul — its forward loops the tokens around mat_vec_mul (model.cpp:714-960) —
  * so the contract is "n_tokens calls of mat_vec_mul": every (token, row) is bit-identical to
- * llmi_mat_vec_mul_dev, the weights are read once per 8 tokens (any format) or once per K-chunk per 32
- * tokens (Q4_0 / Q8_0, exact dp4a block dots with the token on the lane). */
+ * llmi_mat_vec_mul_dev.  Three kernels by token count: a token loop around the one-token decomposition (any
+ * format; weights read once per 8 tokens), from 16 tokens a dp4a kernel with the token on the lane (Q4_0 / Q8_0),
+ * from 128 tokens the exact int8 tensor-core kernel (Q4_0 / Q8_0; tcgen05.mma kind::i8, one MMA per quant block,
+ * the per-block fp32 scale-and-accumulate as its epilogue). */
 int llmi_gemm_tokens(llmi_weight_t w, const float* x_dev, uint32_t n_tokens, float* out_dev, llmi_stream_t stream);
 
 /* Per-block integer dot products (must be bit-exact with the reference):
@@ -195,7 +197,7 @@ int llmi_model_free(llmi_model_t m);
 int llmi_model_info(llmi_model_t m, uint32_t* dims, uint64_t* weight_bytes);
 /* Model::forward(tokens, pos) (model.h:91, model.cpp:706-1048): host token ids
  * in, host logits of the last token out; activations and KV stay on the device.
- * A prompt (n_tokens > 1) goes through each layer in batches of up to 64 tokens
+ * A prompt (n_tokens > 1) goes through each layer in batches of up to 256 tokens
  * (env LLMI_PREFILL_BATCH) — the reference's layer-major loop with the tokens
  * inside — with bit-identical results to feeding the tokens one by one
  * (LLMI_NO_PREFILL=1 forces that).  Synchronous. */

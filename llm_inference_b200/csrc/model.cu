@@ -355,8 +355,8 @@ int gemv_tokens_group(llmi_model_s* m, std::initializer_list<llmi_weight_t> ws, 
 // n_tok <= batch prompt tokens through all layers together (the loop nest of the reference's forward is
 // layer-major with the tokens inside, model.cpp:714-960).  Per token the arithmetic is the one run_step
 // does — same kernels with a token index — so the KV cache and the logits are bit-identical to feeding the
-// tokens one by one; what changes is that every weight matrix is read once per 8 tokens instead of once per
-// token and a layer costs 9 launches per batch instead of 8 per token.  Requires prefill_ok (every
+// tokens one by one; what changes is that every weight matrix is read once per token tile (8 to 32 tokens,
+// gemv.cu launch_tokens) instead of once per token and a layer costs ~9 launches per batch instead of 8 per token.  Requires prefill_ok (every
 // consumer of a vector takes the same activation kind).  Logits (of the last token) only if want_logits.
 int run_batch(llmi_model_s* m, const int32_t* toks, uint32_t n_tok, bool want_logits) {
   cudaStream_t s = m->stream;

@@ -115,7 +115,7 @@ def test_model_load_errors(gpu_ops):
 
 @pytest.mark.parametrize("wt,et", [(synth.Q4_0, synth.F16), ("q4_k_m", synth.Q6_K), (synth.Q8_0, synth.Q8_0)])
 def test_batched_prefill_is_bitwise_the_token_by_token_path(gpu_ops, monkeypatch, wt, et):
-    """A prompt goes through each layer in batches (weights read once per 8 tokens); per token the
+    """A prompt goes through each layer in batches (weights read once per token tile); per token the
     arithmetic is that of the one-token path, so logits AND the KV cache (probed by decoding on) must be
     bit-identical, for a batch size that splits the prompt unevenly."""
     from llm_inference_b200.model import Model
