@@ -190,8 +190,12 @@ int llmi_model_load_shard(const void* gguf_image, uint64_t size, uint32_t max_po
 int llmi_shard_range(uint64_t n_rows, int world, int rank, uint64_t* row_begin, uint64_t* row_end);
 int llmi_model_comm_handle(llmi_model_t m, void* handle64);
 int llmi_model_comm_connect(llmi_model_t m, const void* handles);
-/* 1 if a kernel of this rank gave up (after ~4 s) waiting for a peer's rows; results are then invalid. */
+/* 1 if a kernel of this rank gave up (after ~4 s) waiting for exchanged rows (a peer died, stalled, or ran other
+ * steps).  The flag is sticky: llmi_model_forward / llmi_model_decode_greedy return LLMI_ERR_STATE while it is set. */
 int llmi_model_comm_error(llmi_model_t m);
+/* Clears the flag (and the argmax scratch) after the host has dealt with the failure; every rank calls it, with all
+ * ranks' streams drained, before the next step. */
+int llmi_model_comm_reset(llmi_model_t m);
 int llmi_model_free(llmi_model_t m);
 /* dims[8] = {n_layer, n_embd, n_ff, n_head, n_head_kv, head_dim, vocab, max_positions} */
 int llmi_model_info(llmi_model_t m, uint32_t* dims, uint64_t* weight_bytes);

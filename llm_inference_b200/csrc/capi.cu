@@ -10,6 +10,7 @@
 
 #include "glue.h"
 #include "launch.cuh"
+#include "mega.h"
 #include "llmi_internal.h"
 
 // Programmatic dependent launch for every kernel of the library (launch.cuh);
@@ -116,6 +117,7 @@ int llmi_init(int device) {
   if (const char* e = getenv("LLMI_NO_PDL")) g_llmi_pdl = !(e[0] == '1');
   LLMI_CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
   LLMI_CUDA_TRY(llmi_gemv_init());
+  LLMI_CUDA_TRY(llmi_mega_init());
   g.device = device;
   g.ready = true;
   return LLMI_OK;

@@ -32,6 +32,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
+__device__ __forceinline__ void mbar_inval(uint64_t* bar) {
+  asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -85,6 +88,7 @@ cudaError_t llmi_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t 
 // inside the step, so a buffer reused every layer never shows a stale match.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t ll_tag(const LLTag& t) {
+  if (!t.epoch) return t.add;  // tag given by value (persistent decode kernel: the host counts the steps)
   uint32_t e;
   asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(e) : "l"(t.epoch) : "memory");
   return e * t.mul + t.add;
@@ -93,11 +97,10 @@ __device__ __forceinline__ void ll_store(uint2* p, uint32_t bits, uint32_t tag) 
   asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(bits), "r"(tag) : "memory");
 }
 // Spins until element *p carries `tag`; gives up after ~4 s (a peer that never
-// arrives must not hang the GPU) and reports through *err.
-__device__ __forceinline__ uint32_t ll_wait(const uint2* p, uint32_t tag, uint32_t* err) {
+// arrives must not hang the GPU) and reports through *err.  The spin is out of line: it is the slow path, and the
+// persistent decode kernel has dozens of wait sites whose code must stay small (instruction cache).
+static __device__ __noinline__ uint32_t ll_wait_slow(const uint2* p, uint32_t tag, uint32_t* err) {
   uint32_t v, f;
-  asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(f) : "l"(p) : "memory");
-  if (f == tag) return v;
   if (err) {  // an earlier wait already timed out: the run is lost, drain quickly
     uint32_t dead;
     asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(dead) : "l"(err) : "memory");
@@ -106,7 +109,7 @@ __device__ __forceinline__ uint32_t ll_wait(const uint2* p, uint32_t tag, uint32
   unsigned long long t0;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
   for (uint32_t spins = 1;; ++spins) {
-    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(f) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(f) : "l"(p) : "memory");
     if (f == tag) return v;
     if ((spins & 1023u) == 0) {
       unsigned long long t1;
@@ -116,7 +119,32 @@ __device__ __forceinline__ uint32_t ll_wait(const uint2* p, uint32_t tag, uint32
         return 0;
       }
     }
+    __nanosleep(32);  // thousands of threads may be polling the same L2 lines: leave room for the producer's store
   }
+}
+// (the reader always polls its OWN GPU's buffer: a gpu-scope strong load, served by L2, is enough — also for words a
+// peer wrote over NVLink, which land in this GPU's L2 — and, unlike ld.volatile, several of them pipeline)
+__device__ __forceinline__ uint32_t ll_wait(const uint2* p, uint32_t tag, uint32_t* err) {
+  uint32_t v, f;
+  asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(f) : "l"(p) : "memory");
+  if (f == tag) return v;
+  return ll_wait_slow(p, tag, err);
+}
+// N flagged words at once: every load is issued before the first tag is examined (one L2 round trip when the data
+// is there); stragglers take the spinning wait.
+template <int N>
+__device__ __forceinline__ void ll_wait_many(const uint2* const (&p)[N], const bool (&ok)[N], uint32_t tag, uint32_t* err,
+                                             uint32_t (&v)[N]) {
+  uint32_t f[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    v[k] = 0;
+    f[k] = tag;
+    if (ok[k]) asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(v[k]), "=r"(f[k]) : "l"(p[k]) : "memory");
+  }
+#pragma unroll
+  for (int k = 0; k < N; ++k)
+    if (f[k] != tag) v[k] = ll_wait_slow(p[k], tag, err);
 }
 __device__ __forceinline__ float ll_waitf(const uint2* p, uint32_t tag, uint32_t* err) {
   return __uint_as_float(ll_wait(p, tag, err));

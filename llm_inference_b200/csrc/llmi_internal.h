@@ -34,6 +34,26 @@ struct llmi_weight_s {
 // kinds of prepared activation
 enum : int { ACT_NONE = 0, ACT_Q8_0 = 1, ACT_Q8_K = 2, ACT_F16 = 3, ACT_F32 = 4 };
 
+// One bit per supported weight format / per activation kind: kernels that are compiled for a subset of the formats
+// (mega_impl.cuh) carry a mask of these as a template parameter.
+#ifdef __CUDACC__
+#define LLMI_HD __host__ __device__
+#else
+#define LLMI_HD
+#endif
+LLMI_HD constexpr uint32_t llmi_type_bit(uint32_t ggml_type) {
+  return ggml_type == LLMI_Q4_0 ? 1u : ggml_type == LLMI_Q8_0 ? 2u : ggml_type == LLMI_Q5_0 ? 4u : ggml_type == LLMI_Q4_K ? 8u
+       : ggml_type == LLMI_Q6_K ? 16u : ggml_type == LLMI_F16 ? 32u : ggml_type == LLMI_BF16 ? 64u : 0x80000000u;
+}
+constexpr uint32_t LLMI_ALL_TYPES = 0x7fu;
+// activation kinds the formats of a type mask consume (bit = 1 << kind)
+LLMI_HD constexpr uint32_t llmi_kind_mask(uint32_t type_mask) {
+  return ((type_mask & (llmi_type_bit(LLMI_Q4_0) | llmi_type_bit(LLMI_Q8_0))) ? (1u << ACT_Q8_0) : 0u) |
+         ((type_mask & (llmi_type_bit(LLMI_Q4_K) | llmi_type_bit(LLMI_Q6_K))) ? (1u << ACT_Q8_K) : 0u) |
+         ((type_mask & llmi_type_bit(LLMI_F16)) ? (1u << ACT_F16) : 0u) |
+         ((type_mask & (llmi_type_bit(LLMI_Q5_0) | llmi_type_bit(LLMI_BF16))) ? (1u << ACT_F32) : 0u);
+}
+
 // Device layout of a prepared activation (one contiguous, 16-byte-multiple
 // buffer so a single bulk async copy stages it into shared memory):
 //   ACT_Q8_0: [K int8 quants][K/32 x {f16 d, int16 sum-of-quants}]
@@ -81,6 +101,30 @@ struct GemvLL {
   LLPeers peers;
   LLTag tag;
   uint32_t off[3] = {LL_NONE, LL_NONE, LL_NONE};
+};
+
+// One weight matrix (or row shard) as the mat-vec kernels see it (gemv_bodies.cuh); filled by gemv.cu per launch
+// and by model.cu once per matrix for the persistent decode kernel (mega.cu).
+struct GemvArgs {
+  const uint8_t* q;
+  const uint8_t* d;
+  const uint8_t* x;
+  const uint8_t* act;
+  uint32_t act_bytes;
+  float* out;  // already offset to this handle's first row
+  uint32_t n_local, n_slabs, nb, n_cols;
+  uint32_t units;   // K-units per slab row (4 blocks of 32 / one super-block / 4 chunks of 8)
+  uint32_t chunks;  // K-chunks (work items) per slab = ceil(units / Body::C)
+  // optional fused epilogue of the logits mat-vec: soft-cap + running argmax key
+  unsigned long long* argmax_key;
+  float softcap;
+  uint32_t row0;  // global index of this handle's first row
+  // token-batched launches (prefill): n_tok activation buffers act_stride bytes apart, outputs out_stride floats apart
+  uint32_t n_tok, act_stride, out_stride;
+  float* part;  // token-per-lane kernel: chunk partials [chunk][token][8 * n_slabs] of this matrix
+  // row-sharded model: element offset of this matrix' output vector inside the exchange buffer of every rank
+  // (LL_NONE: plain local store to `out`)
+  uint32_t ll_off;
 };
 
 // error plumbing (capi.cu)

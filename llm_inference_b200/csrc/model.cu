@@ -18,6 +18,7 @@
 
 #include "glue.h"
 #include "gguf_reader.h"
+#include "mega.h"
 
 namespace {
 
@@ -76,6 +77,20 @@ struct llmi_model_s {
   uint32_t off_h = 0, off_q = 0, off_k = 0, off_v = 0, off_ao = 0, off_gate = 0, off_up = 0, off_fo = 0, off_key = 0,
            off_logits = 0;
   std::vector<void*> ipc_opened;  // peer mappings to close
+  // persistent decode kernel (mega.cu): one cooperative launch per decode call.  Its exchange
+  // region follows the per-launch path's inside `comm` (one allocation, one IPC handle).
+  bool use_mega = false;
+  MegaArgs mega;             // everything but the step-control fields
+  std::vector<uint32_t> mega_off;  // MegaOffsets (element offsets of the per-layer vectors, two copies each)
+  MegaPhase* d_prog = nullptr;
+  MegaAttn* d_mattn = nullptr;
+  uint32_t* d_done = nullptr;
+  uint32_t mega_epoch = 1;   // steps run so far + 1 (every rank runs the same steps)
+  uint32_t mega_tok_uses = 0;  // greedy steps run so far
+  uint32_t mega_ctas = 0;
+  size_t mega_smem = 0;
+  int mega_variant = -1;     // the kernel instantiation for this model's formats and head size (mega.cu)
+  int mega_launches = 0;     // kernel launches of the last decode / forward call
   bool sharded() const { return world > 1; }
   LLTag tag(uint32_t idx) const {  // idx: 1 + 4*layer + {0 qkv, 1 attn_out, 2 gate/up, 3 ffn_out}; 4L+1 embed, +2 keys, +3 logits
     LLTag t = ll.tag;
@@ -440,6 +455,273 @@ int run_batch(llmi_model_s* m, const int32_t* toks, uint32_t n_tok, bool want_lo
   return LLMI_OK;
 }
 
+
+// ---- persistent decode kernel: plan + descriptors (mega.h) ----------------------------------------------------
+struct MegaOffsets {
+  uint32_t q[2], k[2], v[2], attn[2], ao[2], hid[2], fo[2];
+};
+
+uint32_t slab_bytes(uint32_t type, uint64_t nb, int plane) {  // bytes of one slab of a plane (repack.cu llmi_plan_planes)
+  uint32_t q = 0, d = 0, x = 0;
+  switch (type) {
+    case LLMI_Q4_0: q = 16; d = 2; break;
+    case LLMI_Q8_0: q = 32; d = 2; break;
+    case LLMI_Q5_0: q = 16; d = 2; x = 4; break;
+    case LLMI_Q4_K: q = 128; x = 16; break;
+    case LLMI_Q6_K: q = 192; d = 2; x = 16; break;
+    case LLMI_F16:
+    case LLMI_BF16: q = 16; break;
+    default: break;
+  }
+  return uint32_t(nb) * LLMI_SLAB * (plane == 0 ? q : (plane == 1 ? d : x));
+}
+
+// Decides whether this model runs on the persistent kernel and reserves its region of the exchange buffer
+// (element offsets from `off` on).  Conditions: what norm_act_kernel supports (E <= 6144), one activation kind per
+// consumer group, gate and up of one format, shared memory for the activations + the attention scratch.
+int mega_plan(llmi_model_s* m, uint32_t& off) {
+  const uint32_t E = m->E, F = m->F, HD = m->H * m->D, KD = m->HK * m->D;
+  MegaArgs& a = m->mega;
+  a = MegaArgs();
+  // LLMI_DECODE = mega | legacy.  Default: the per-launch path; the persistent kernel is bit-identical but (round 2
+  // measurements, profiles/r02_notes.md) not yet faster on one GPU
+  m->use_mega = false;
+  if (const char* e = getenv("LLMI_DECODE")) m->use_mega = std::string(e) == "mega";
+  if (E > 6144 || llmi_mega_max_ctas() == 0) m->use_mega = false;
+  for (const LayerW& w : m->layers) {
+    const int kq = llmi_act_kind_for(w.q->type);
+    if (llmi_act_kind_for(w.k->type) != kq || llmi_act_kind_for(w.v->type) != kq) m->use_mega = false;
+    if (w.gate->type != w.up->type) m->use_mega = false;
+    if (w.gate->n_slabs != w.up->n_slabs) m->use_mega = false;
+  }
+  if (!m->use_mega) return LLMI_OK;
+  auto take = [&](uint32_t n) { const uint32_t o = off; off += (n + 1u) & ~1u; return o; };
+  a.off_h = take(E);
+  a.off_key = take(2 * LLMI_MAX_WORLD);
+  a.off_tok = take(2);
+  a.off_logits = m->sharded() ? take(m->V) : 0;
+  off = (off + MEGA_CNT_STRIDE - 1) / MEGA_CNT_STRIDE * MEGA_CNT_STRIDE;  // counters on their own 128-byte lines
+  a.off_cnt = take(MEGA_CNT_SLOTS * MEGA_CNT_STRIDE);
+  // per-layer vectors twice (layer parity): a CTA that lags a whole layer behind still finds its inputs intact
+  static_assert(sizeof(MegaOffsets) == 14 * 4, "MegaOffsets");
+  MegaOffsets o;
+  for (int p = 0; p < 2; ++p) {
+    o.q[p] = take(HD); o.k[p] = take(KD); o.v[p] = take(KD); o.attn[p] = take(HD); o.ao[p] = take(E);
+    o.hid[p] = take(F); o.fo[p] = take(E);
+  }
+  m->mega_off.assign(reinterpret_cast<uint32_t*>(&o), reinterpret_cast<uint32_t*>(&o) + 14);
+  return LLMI_OK;
+}
+
+int mega_fill_mat(MegaPhase& P, int i, llmi_weight_t w, uint32_t out_off) {
+  P.m[i] = llmi_gemv_args(*w);
+  P.slab_q[i] = slab_bytes(w->type, w->nb, 0);
+  P.slab_d[i] = slab_bytes(w->type, w->nb, 1);
+  P.slab_x[i] = slab_bytes(w->type, w->nb, 2);
+  // a K-chunk (work item) is 16 blocks of 32, 2 super-blocks of 256 or 16 groups of 8 halves (gemv_bodies.cuh Body::C)
+  const uint64_t per_chunk = (w->type == LLMI_Q4_K || w->type == LLMI_Q6_K) ? 2 : 16;
+  P.chunk_q[i] = slab_bytes(w->type, per_chunk, 0);
+  P.chunk_d[i] = slab_bytes(w->type, per_chunk, 1);
+  P.chunk_x[i] = slab_bytes(w->type, per_chunk, 2);
+  P.out_off[i] = out_off;
+  return LLMI_OK;
+}
+
+// The program of one token (mega.h) and the kernel's static arguments.  Called at the end of load_impl.
+int mega_build(llmi_model_s* m) {
+  if (!m->use_mega) return LLMI_OK;
+  const uint32_t E = m->E, F = m->F, HD = m->H * m->D, L = m->L;
+  MegaArgs& a = m->mega;
+  MegaOffsets o;
+  memcpy(&o, m->mega_off.data(), sizeof(o));
+  a.L = L; a.E = E; a.F = F; a.H = m->H; a.HK = m->HK; a.D = m->D; a.V = m->V; a.t_max = m->t_max;
+  a.eps = m->eps;
+  a.attn_scale = m->attn_scale; a.attn_softcap = m->attn_softcap; a.final_softcap = m->final_softcap;
+  a.embed_scale = std::sqrt(float(E));
+  a.embd_type = m->embd->type; a.embd_nb = m->embd->nb;
+  a.embd_row_begin = uint32_t(m->embd->row_begin); a.embd_row_end = uint32_t(m->embd->row_end);
+  a.embd_q = m->embd->p_q; a.embd_d = m->embd->p_d; a.embd_x = m->embd->p_x;
+  a.rank = uint32_t(m->rank); a.world = uint32_t(m->world);
+  a.err = m->d_llerr;
+  a.tag_mul = MEGA_TAGS_PER_LAYER * L + 8;
+  a.tag_h = MEGA_TAGS_PER_LAYER * L + 1; a.tag_key = a.tag_h + 1; a.tag_tok = a.tag_h + 2; a.tag_logits = a.tag_h + 3;
+  // head-sharded attention: the q/k/v rows of this rank are exactly the rows of its own heads, so q/k/v never
+  // leave the rank and only the heads' outputs travel; otherwise every rank runs every head
+  bool head_sharded = m->sharded() && m->H % m->world == 0 && m->HK % m->world == 0;
+  if (head_sharded) {
+    uint64_t rb = 0, re = 0;
+    M_RC(llmi_shard_range(HD, m->world, m->rank, &rb, &re));
+    const uint64_t per = HD / m->world;
+    if (rb != per * m->rank || re != rb + per) head_sharded = false;
+    M_RC(llmi_shard_range(m->HK * m->D, m->world, m->rank, &rb, &re));
+    const uint64_t perk = uint64_t(m->HK) * m->D / m->world;
+    if (rb != perk * m->rank || re != rb + perk) head_sharded = false;
+  }
+  if (const char* e = getenv("LLMI_NO_HEAD_SHARD")) head_sharded = head_sharded && !(e[0] == '1');
+  a.attn_push_all = head_sharded ? 1u : 0u;
+  a.head_begin = head_sharded ? m->rank * (m->H / m->world) : 0u;
+  a.head_end = head_sharded ? a.head_begin + m->H / m->world : m->H;
+  a.logits = m->logits; a.key = m->d_key; a.done_ctr = m->d_done; a.d_tok = m->d_tok; a.d_pos = m->d_pos;
+
+  m->mega_ctas = llmi_mega_max_ctas();  // the same on every rank: the arrival counts depend on it
+  if (const char* e = getenv("LLMI_MEGA_CTAS")) m->mega_ctas = std::min<uint32_t>(m->mega_ctas, uint32_t(std::max(1, atoi(e))));
+  a.hints = 1;
+  if (const char* e = getenv("LLMI_MEGA_NO_HINTS")) a.hints = e[0] == '1' ? 0u : 1u;
+  std::vector<MegaPhase> prog;
+  std::vector<MegaAttn> attn(L);
+  size_t act_max = 0;
+  uint32_t jmax = 1;
+  auto tag_of = [&](uint32_t l, uint32_t i) { return 1 + MEGA_TAGS_PER_LAYER * l + i; };  // i: qkv, attn, ao, hid, fo
+  // one mat-vec entry: the matrices of `ws` that share the format of ws[first]
+  // exchange i (qkv, attn, ao, hid, fo) of layer l: its counter slot; bumps per use of an exchange
+  auto slot_of = [&](uint32_t l, uint32_t i) { return MEGA_CNT_LAYER + (l & 1u) * MEGA_TAGS_PER_LAYER + i; };
+  auto arrivals = [&](bool all) { return m->mega_ctas * (all ? uint32_t(m->world) : 1u); };
+  auto add_gemv = [&](std::vector<llmi_weight_t> ws, std::vector<uint32_t> offs, uint32_t K, uint32_t pro, uint32_t epi,
+                      uint32_t in_off, uint32_t in_tag, uint32_t out_tag, bool push_all, const float* w_post,
+                      const float* w_next, uint32_t in_slot, uint32_t in_layer, uint32_t in_arr, uint32_t out_slot) -> int {
+    std::vector<bool> done(ws.size(), false);
+    bool first = true;
+    const size_t first_entry = prog.size();
+    for (size_t i = 0; i < ws.size(); ++i) {
+      if (done[i]) continue;
+      MegaPhase P;
+      memset(&P, 0, sizeof(P));
+      P.kind = MEGA_GEMV;
+      P.type = ws[i]->type;
+      P.act_kind = uint32_t(llmi_act_kind_for(ws[i]->type));
+      P.K = K;
+      P.J = llmi_gemv_chunks(*ws[i]);
+      P.pro = first ? pro : uint32_t(MEGA_PRO_REUSE);
+      P.epi = epi;
+      P.in_off = in_off; P.in_tag = in_tag; P.out_tag = out_tag; P.push_all = push_all ? 1u : 0u;
+      P.w_post = w_post; P.w_next = w_next;
+      P.in_slot = in_slot; P.in_layer = in_layer; P.in_arrivals = in_arr; P.out_slot = out_slot;
+      int n = 0;
+      uint32_t v_total = 0;
+      for (size_t j = i; j < ws.size(); ++j)
+        if (!done[j] && ws[j]->type == ws[i]->type && (epi == MEGA_EPI_GEGLU || n < MEGA_MAX_MATS)) {
+          if (ws[j]->n_cols != K) return llmi_fail(LLMI_ERR_SIZE, "llmi_model_load: matrices of one stage differ in K");
+          mega_fill_mat(P, n, ws[j], offs[j]);
+          v_total += uint32_t(ws[j]->n_slabs);
+          done[j] = true;
+          ++n;
+        }
+      P.n_mats = uint32_t(n);
+      P.v_total = epi == MEGA_EPI_GEGLU ? uint32_t(ws[i]->n_slabs) : v_total;
+      act_max = std::max(act_max, act_bytes(int(P.act_kind), K));
+      jmax = std::max(jmax, P.J);
+      prog.push_back(P);
+      first = false;
+    }
+    if (prog.size() > first_entry && epi != MEGA_EPI_LOGITS) prog.back().bump = 1;
+    return LLMI_OK;
+  };
+  for (uint32_t l = 0; l < L; ++l) {
+    const LayerW& w = m->layers[l];
+    const int p = int(l & 1), pp = int((l + 1) & 1);  // this layer's copies, the previous layer's
+    M_RC(add_gemv({w.q, w.k, w.v}, {o.q[p], o.k[p], o.v[p]}, E, l == 0 ? uint32_t(MEGA_PRO_FIRST) : uint32_t(MEGA_PRO_NORM),
+                  MEGA_EPI_FLAG, l ? o.fo[pp] : 0u, l ? tag_of(l - 1, 4) : 0u, tag_of(l, 0), !head_sharded,
+                  l ? m->layers[l - 1].post_ffw_norm : nullptr, w.attn_norm, l ? slot_of(l - 1, 4) : 0u, l ? l - 1 : 0u,
+                  arrivals(true), slot_of(l, 0)));
+    MegaPhase T;
+    memset(&T, 0, sizeof(T));
+    T.kind = MEGA_ATTN;
+    T.layer = l;
+    prog.push_back(T);
+    MegaAttn& t = attn[l];
+    t.q_norm = w.q_norm; t.k_norm = w.k_norm;
+    t.kcache = m->kcache + size_t(l) * m->t_max * m->HK * m->D;
+    t.vcache = m->vcache + size_t(l) * m->t_max * m->HK * m->D;
+    t.rope = w.swa ? m->rope_swa : m->rope_global;
+    t.off_q = o.q[p]; t.off_k = o.k[p]; t.off_v = o.v[p]; t.in_tag = tag_of(l, 0);
+    t.off_out = o.attn[p]; t.out_tag = tag_of(l, 1);
+    M_RC(add_gemv({w.o}, {o.ao[p]}, HD, MEGA_PRO_QUANT, MEGA_EPI_FLAG, o.attn[p], tag_of(l, 1), tag_of(l, 2), true,
+                  nullptr, nullptr, slot_of(l, 1), l, arrivals(head_sharded), slot_of(l, 2)));
+    M_RC(add_gemv({w.gate, w.up}, {o.hid[p], o.hid[p]}, E, MEGA_PRO_NORM, MEGA_EPI_GEGLU, o.ao[p], tag_of(l, 2),
+                  tag_of(l, 3), true, w.post_attn_norm, w.ffn_norm, slot_of(l, 2), l, arrivals(true), slot_of(l, 3)));
+    M_RC(add_gemv({w.down}, {o.fo[p]}, F, MEGA_PRO_QUANT, MEGA_EPI_FLAG, o.hid[p], tag_of(l, 3), tag_of(l, 4), true,
+                  nullptr, nullptr, slot_of(l, 3), l, arrivals(true), slot_of(l, 4)));
+  }
+  M_RC(add_gemv({m->embd}, {a.off_logits}, E, MEGA_PRO_NORM, MEGA_EPI_LOGITS, o.fo[(L - 1) & 1], tag_of(L - 1, 4),
+                a.tag_logits, true, m->layers[L - 1].post_ffw_norm, m->out_norm, slot_of(L - 1, 4), L - 1, arrivals(true),
+                0u));
+  // shared memory: [h][xs][activation][chunk partials], the attention scratch over everything but h
+  auto up128 = [](size_t v) { return (v + 127) / 128 * 128; };
+  uint32_t type_mask = 0;
+  for (const MegaPhase& P : prog)
+    if (P.kind == MEGA_GEMV) type_mask |= mega_type_bit(P.type);
+  size_t limit = 0;
+  m->mega_variant = llmi_mega_select(type_mask, m->D, &limit);
+  if (m->mega_variant < 0) {
+    m->use_mega = false;
+    return LLMI_OK;
+  }
+  a.sm_h = 0;
+  a.sm_xs = uint32_t(up128(size_t(E) * 4));
+  a.sm_act = a.sm_xs + uint32_t(up128(size_t(E) * 4));
+  a.sm_part = a.sm_act + uint32_t(up128(act_max));
+  a.sm_attn = a.sm_xs;
+  size_t part_bytes = 32 * 1024;
+  const size_t part_min = size_t(LLMI_SLAB) * jmax * 2 * 4;
+  if (part_bytes < part_min) part_bytes = up128(part_min);
+  size_t attn_bytes = 0;
+  a.attn_nbuf = limit > a.sm_attn ? llmi_mega_attention_nbuf(m->t_max, m->D, limit - a.sm_attn, &attn_bytes) : 0;
+  if (a.attn_nbuf == 0 || a.sm_part + part_bytes > limit) {
+    m->use_mega = false;  // context or K too large for one CTA's shared memory: the per-launch path runs it
+    return LLMI_OK;
+  }
+  a.part_floats = uint32_t(part_bytes / 4);
+  m->mega_smem = std::max<size_t>(a.sm_part + part_bytes, a.sm_attn + attn_bytes);
+  a.n_prog = uint32_t(prog.size());
+  M_RC(dev_alloc(m, (void**)&m->d_prog, prog.size() * sizeof(MegaPhase)));
+  M_RC(dev_alloc(m, (void**)&m->d_mattn, attn.size() * sizeof(MegaAttn)));
+  M_TRY(cudaMemcpy(m->d_prog, prog.data(), prog.size() * sizeof(MegaPhase), cudaMemcpyHostToDevice));
+  M_TRY(cudaMemcpy(m->d_mattn, attn.data(), attn.size() * sizeof(MegaAttn), cudaMemcpyHostToDevice));
+  a.prog = m->d_prog;
+  a.attn = m->d_mattn;
+  return LLMI_OK;
+}
+
+// n_steps tokens in ONE launch.  tokens_dev: the token of every step (prompts) or null (first_token, then the
+// argmax of the previous step).  logits_mode as in MegaArgs.
+int mega_run(llmi_model_s* m, const int32_t* tokens_dev, int32_t first_token, int pos, uint32_t n_steps,
+             uint32_t logits_mode) {
+  if (m->sharded() && m->mega.peers.n != uint32_t(m->world))
+    return llmi_fail(LLMI_ERR_STATE, "row-sharded model: llmi_model_comm_connect has not been called");
+  MegaArgs a = m->mega;
+  a.tokens = tokens_dev;
+  a.first_token = first_token;
+  a.pos0 = pos;
+  a.n_steps = n_steps;
+  a.logits_mode = logits_mode;
+  a.gen = logits_mode == 2 ? m->d_gen : nullptr;
+  a.epoch0 = m->mega_epoch;
+  a.tok_uses0 = m->mega_tok_uses;
+  m->mega_epoch += n_steps;
+  if (logits_mode == 2) m->mega_tok_uses += n_steps;
+  M_TRY(llmi_launch_mega(m->mega_variant, a, m->mega_ctas, m->mega_smem, m->stream));
+  m->mega_launches++;
+  if (m->sharded() && logits_mode == 1) {  // host-facing logits: the rows of every rank, soft-capped by their producers
+    LLTag t;
+    t.add = (a.epoch0 + n_steps - 1) * a.tag_mul + a.tag_logits;
+    t.err = m->d_llerr;
+    M_TRY(llmi_launch_ll_unpack(m->comm + a.off_logits, t, m->logits, m->V, 0.0f, m->stream));
+    m->mega_launches++;
+  }
+  return LLMI_OK;
+}
+
+// A consumer that gave up waiting (launch.cuh ll_wait) leaves a sticky flag: the results of that call are garbage.
+int check_exchange(llmi_model_s* m, const char* who) {
+  uint32_t e = 0;
+  M_TRY(cudaMemcpy(&e, m->d_llerr, 4, cudaMemcpyDeviceToHost));
+  if (e)
+    return llmi_fail(LLMI_ERR_STATE, std::string(who) + ": a kernel gave up waiting for exchanged rows (a peer rank died, "
+                                                        "stalled for seconds, or ran different steps); call "
+                                                        "llmi_model_comm_reset on every rank to continue");
+  return LLMI_OK;
+}
+
 double kv_f(const llmi::GgufImage& g, const std::string& key, double dflt, bool* found = nullptr) {
   const llmi::GgufValue* v = g.find(key);
   if (found) *found = v != nullptr;
@@ -547,26 +829,36 @@ int load_impl(llmi_model_s* m, const uint8_t* image, uint64_t size, uint32_t t_m
   }
   if (m->batch < 2) m->prefill_ok = false;
   if (const char* e = getenv("LLMI_NO_PREFILL")) m->prefill_ok = m->prefill_ok && !(e[0] == '1');
-  if (m->sharded()) {
-    m->prefill_ok = false;  // prompts of a sharded model go token by token through the exchange path
-    // one exchange buffer, same layout on every rank (element = {value bits, tag})
+  {
+    // one exchange buffer, same layout on every rank (element = {value bits, tag}): the region of the per-launch
+    // path (sharded models only), then the region of the persistent decode kernel
     uint32_t off = 0;
     auto take = [&](uint32_t n) { const uint32_t o = off; off += (n + 1u) & ~1u; return o; };
-    m->off_h = take(E); m->off_q = take(HD); m->off_k = take(KD); m->off_v = take(KD); m->off_ao = take(E);
-    m->off_gate = take(F); m->off_up = take(F); m->off_fo = take(E); m->off_key = take(2 * LLMI_MAX_WORLD);
-    m->off_logits = take(m->V);
+    if (m->sharded()) {
+      m->prefill_ok = false;  // prompts of a sharded model go token by token through the exchange path
+      m->off_h = take(E); m->off_q = take(HD); m->off_k = take(KD); m->off_v = take(KD); m->off_ao = take(E);
+      m->off_gate = take(F); m->off_up = take(F); m->off_fo = take(E); m->off_key = take(2 * LLMI_MAX_WORLD);
+      m->off_logits = take(m->V);
+    }
+    M_RC(mega_plan(m, off));
     m->comm_elems = off;
     M_TRY(cudaMalloc((void**)&m->comm, size_t(off) * sizeof(uint2)));  // not in `owned`: exported through CUDA IPC
     M_TRY(cudaMemset(m->comm, 0, size_t(off) * sizeof(uint2)));
     M_RC(dev_alloc(m, (void**)&m->d_epoch, 16));
     M_RC(dev_alloc(m, (void**)&m->d_llerr, 16));
+    M_RC(dev_alloc(m, (void**)&m->d_done, 16));
     const uint32_t one = 1;
     M_TRY(cudaMemcpy(m->d_epoch, &one, 4, cudaMemcpyHostToDevice));
     M_TRY(cudaMemset(m->d_llerr, 0, 16));
+    M_TRY(cudaMemset(m->d_done, 0, 16));
     m->ll.rank = uint32_t(rank);
     m->ll.tag.epoch = m->d_epoch;
     m->ll.tag.mul = 4 * m->L + 4;
     m->ll.tag.err = m->d_llerr;
+    if (!m->sharded()) {  // a single GPU is a world of one: the kernel's "peers" are its own buffer
+      m->mega.peers.n = 1;
+      m->mega.peers.base[0] = m->comm;
+    }
     M_TRY(cudaDeviceSynchronize());
   }
   M_RC(dev_alloc(m, (void**)&m->logits, size_t(m->V) * 4));
@@ -594,6 +886,7 @@ int load_impl(llmi_model_s* m, const uint8_t* image, uint64_t size, uint32_t t_m
   M_TRY(llmi_launch_rope_table(m->rope_swa, t_max, m->D, 10000.0f, m->rope_scale, m->stream));
   M_TRY(llmi_launch_rope_table(m->rope_global, t_max, m->D, m->rope_base, m->rope_scale, m->stream));
   M_TRY(cudaStreamSynchronize(m->stream));
+  M_RC(mega_build(m));
   return LLMI_OK;
 }
 
@@ -716,12 +1009,29 @@ int llmi_model_comm_connect(llmi_model_t m, const void* handles /* world x 64 by
     m->ll.peers.base[r] = static_cast<uint2*>(p);
   }
   m->ll.peers.n = uint32_t(m->world);
+  m->mega.peers = m->ll.peers;
+  return LLMI_OK;
+}
+
+// After a failed exchange (llmi_model_comm_error != 0; forward / decode_greedy returned LLMI_ERR_STATE): clears the
+// sticky flag.  Every rank must call it, after all ranks have drained their streams, before the next step.
+int llmi_model_comm_reset(llmi_model_t m) {
+  if (!m) return llmi_fail(LLMI_ERR_ARG, "llmi_model_comm_reset: null model");
+  M_TRY(cudaStreamSynchronize(m->stream));
+  M_TRY(cudaMemset(m->d_llerr, 0, 16));
+  M_TRY(cudaMemset(m->d_done, 0, 16));
+  M_TRY(cudaMemset(m->d_key, 0, 16));
+  if (m->use_mega) {  // the arrival counters restart with the step count (identically on every rank)
+    M_TRY(cudaMemset(m->comm + m->mega.off_cnt, 0, size_t(MEGA_CNT_SLOTS) * MEGA_CNT_STRIDE * sizeof(uint2)));
+    m->mega_epoch = 1;
+    m->mega_tok_uses = 0;
+  }
   return LLMI_OK;
 }
 
 // 1 when a kernel gave up waiting for a peer's rows (the peer died or the ranks ran different steps).
 int llmi_model_comm_error(llmi_model_t m) {
-  if (!m || !m->sharded()) return 0;
+  if (!m || !m->d_llerr) return 0;
   uint32_t e = 0;
   if (cudaMemcpy(&e, m->d_llerr, 4, cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
   return int(e);
@@ -750,8 +1060,14 @@ int llmi_model_forward(llmi_model_t m, const int32_t* tokens, int n_tokens, int 
   M_TRY(cudaMemcpyAsync(m->d_toks, tokens, size_t(n_tokens) * 4, cudaMemcpyHostToDevice, s));
   M_TRY(cudaMemcpyAsync(m->d_pos, &pos, 4, cudaMemcpyHostToDevice, s));
   m->prefill_launches = 0;
+  m->mega_launches = 0;
   M_TRY(cudaEventRecord(m->ev0, s));
-  if (m->prefill_ok && n_tokens > 1) {
+  if (m->use_mega && (n_tokens == 1 || !m->prefill_ok)) {
+    // one token (a decode step through the reference-facing call), or a prompt of a model without the batched
+    // path (row-sharded): all tokens in one launch of the persistent kernel, logits of the last one
+    M_RC(mega_run(m, m->d_toks, 0, pos, uint32_t(n_tokens), 1));
+    m->prefill_launches = m->mega_launches;
+  } else if (m->prefill_ok && n_tokens > 1) {
     for (int t = 0; t < n_tokens; t += int(m->batch)) {
       const int nb = std::min(int(m->batch), n_tokens - t);
       M_RC(run_batch(m, m->d_toks + t, uint32_t(nb), t + nb == n_tokens));
@@ -765,6 +1081,7 @@ int llmi_model_forward(llmi_model_t m, const int32_t* tokens, int n_tokens, int 
   M_TRY(cudaEventRecord(m->ev1, s));
   M_TRY(cudaMemcpyAsync(m->logits_pinned, m->logits, size_t(m->V) * 4, cudaMemcpyDeviceToHost, s));
   M_TRY(cudaStreamSynchronize(s));
+  M_RC(check_exchange(m, "llmi_model_forward"));
   memcpy(logits_host, m->logits_pinned, size_t(m->V) * 4);
   return LLMI_OK;
 }
@@ -780,8 +1097,19 @@ int llmi_model_decode_greedy(llmi_model_t m, int32_t first_token, int pos, int n
     return llmi_fail(LLMI_ERR_SIZE, "llmi_model_decode_greedy: position exceeds the KV cache capacity");
   if (first_token < 0 || uint32_t(first_token) >= m->V)
     return llmi_fail(LLMI_ERR_ARG, "llmi_model_decode_greedy: bad token id");
-  M_RC(ensure_decode_graph(m));
   cudaStream_t s = m->stream;
+  if (m->use_mega) {  // all n_steps tokens in one launch of the persistent kernel
+    m->mega_launches = 0;
+    M_TRY(cudaEventRecord(m->ev0, s));
+    M_RC(mega_run(m, nullptr, first_token, pos, uint32_t(n_steps), 2));
+    M_TRY(cudaEventRecord(m->ev1, s));
+    M_TRY(cudaMemcpyAsync(out_tokens, m->d_gen, size_t(n_steps) * 4, cudaMemcpyDeviceToHost, s));
+    M_TRY(cudaStreamSynchronize(s));
+    if (ms_device) M_TRY(cudaEventElapsedTime(ms_device, m->ev0, m->ev1));
+    m->launches_per_step = 1;
+    return check_exchange(m, "llmi_model_decode_greedy");
+  }
+  M_RC(ensure_decode_graph(m));
   const int32_t zero = 0;
   M_TRY(cudaMemcpyAsync(m->d_tok, &first_token, 4, cudaMemcpyHostToDevice, s));
   M_TRY(cudaMemcpyAsync(m->d_pos, &pos, 4, cudaMemcpyHostToDevice, s));
@@ -792,7 +1120,7 @@ int llmi_model_decode_greedy(llmi_model_t m, int32_t first_token, int pos, int n
   M_TRY(cudaMemcpyAsync(out_tokens, m->d_gen, size_t(n_steps) * 4, cudaMemcpyDeviceToHost, s));
   M_TRY(cudaStreamSynchronize(s));
   if (ms_device) M_TRY(cudaEventElapsedTime(ms_device, m->ev0, m->ev1));
-  return LLMI_OK;
+  return check_exchange(m, "llmi_model_decode_greedy");
 }
 
 // Logits of the last executed step (device -> host), e.g. after decode_greedy.

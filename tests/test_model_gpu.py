@@ -144,3 +144,41 @@ def test_batched_prefill_is_bitwise_the_token_by_token_path(gpu_ops, monkeypatch
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
     assert np.array_equal(outs["umma"][0].view(np.uint32), b.view(np.uint32))
     assert outs["batched"][1] < outs["single"][1] / 4  # 3 batches of launches instead of 37 tokens' worth
+
+
+@pytest.mark.parametrize("wt,et,hd", [(synth.Q4_0, synth.F16, 128), ("q4_k_m", synth.Q6_K, 256), (synth.Q8_0, synth.Q8_0, 64),
+                                      (synth.Q5_0, synth.Q5_0, 128)])
+def test_persistent_decode_kernel_is_bitwise_the_per_launch_path(gpu_ops, monkeypatch, wt, et, hd):
+    """The persistent decode kernel (mega.cu: one launch per decode call, flagged dataflow between the stages,
+    norms as mat-vec prologues, GEGLU as the gate/up epilogue) must give the bits of the per-launch path
+    (model.cu run_step: one kernel per stage) — logits, greedy tokens and KV cache — for any number of CTAs."""
+    from llm_inference_b200.model import Model
+    dims = synth.GemmaDims("small", 3, 512, 1024, 4, 2, hd, 648)
+    img = synth.build_gemma3_gguf(dims, wt, et, seed=21, embd_std=0.02)
+    prompt = (np.arange(11, dtype=np.int32) * 5 + 2) % dims.vocab
+    outs = {}
+    for mode, env in (("legacy", {"LLMI_DECODE": "legacy"}), ("mega", {"LLMI_DECODE": "mega"}),
+                      ("mega_5ctas", {"LLMI_DECODE": "mega", "LLMI_MEGA_CTAS": "5"}),
+                      ("mega_prompt", {"LLMI_DECODE": "mega", "LLMI_NO_PREFILL": "1"})):
+        for k in ("LLMI_DECODE", "LLMI_MEGA_CTAS", "LLMI_NO_PREFILL"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        m = Model(img, max_positions=64)
+        lg0 = m.forward(prompt, 0)              # legacy batched prefill, or (mega_prompt) token by token in the kernel
+        toks, _ = m.decode_greedy(int(lg0.argmax()), len(prompt), 12)
+        last = m.last_logits()
+        pos = len(prompt) + 12
+        lgs = [m.forward([int(toks[-1])], pos)]  # the reference-facing call on top of the cache the kernel wrote
+        lgs.append(m.forward([int(lgs[-1].argmax())], pos + 1))
+        outs[mode] = (lg0, toks, last, np.stack(lgs), m.launches_per_step)
+        m.close()
+    ref = outs["legacy"]
+    assert ref[4] > 8  # the per-launch path really ran
+    for mode in ("mega", "mega_5ctas", "mega_prompt"):
+        o = outs[mode]
+        assert o[4] == 1, mode
+        assert np.array_equal(o[0].view(np.uint32), ref[0].view(np.uint32)), f"{mode}: prompt logits"
+        assert np.array_equal(o[1], ref[1]), f"{mode}: greedy tokens {o[1]} vs {ref[1]}"
+        assert np.array_equal(o[2].view(np.uint32), ref[2].view(np.uint32)), f"{mode}: last logits of the greedy loop"
+        assert np.array_equal(o[3].view(np.uint32), ref[3].view(np.uint32)), f"{mode}: forward() logits after decode"
