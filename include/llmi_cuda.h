@@ -214,8 +214,12 @@ int llmi_model_last_forward_stats(llmi_model_t m, float* ms_device, int* launche
 int llmi_model_decode_greedy(llmi_model_t m, int32_t first_token, int pos, int n_steps, int32_t* out_tokens,
                              float* ms_device);
 int llmi_model_last_logits(llmi_model_t m, float* logits_host);
-/* kernels launched per decode token (for bench.py's gpu_launches) */
+/* kernels launched per decode token on the per-launch path; 1 (per llmi_model_decode_greedy / one-token
+ * llmi_model_forward call) on the persistent-kernel path (for bench.py's gpu_launches) */
 int llmi_model_launches_per_step(llmi_model_t m);
+/* 1: this model decodes with the persistent kernel (one cooperative launch per call, csrc/mega_impl.cuh; opt-in
+ * with LLMI_DECODE=mega at load time); 0: one CUDA graph of per-stage kernels per token. */
+int llmi_model_decode_path(llmi_model_t m);
 
 /* ---- device memory helpers (benches / tests; plain cudaMalloc wrappers) - */
 int llmi_dev_alloc(uint64_t bytes, void** out_dev);

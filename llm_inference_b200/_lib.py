@@ -61,6 +61,7 @@ SIGNATURES = {
     "llmi_model_last_logits": (_int, [_vp, _vp]),
     "llmi_gemm_tokens": (_int, [_vp, _vp, _u32, _vp, _vp]),
     "llmi_model_launches_per_step": (_int, [_vp]),
+    "llmi_model_decode_path": (_int, [_vp]),
     "llmi_model_last_forward_stats": (_int, [_vp, _vp, _vp]),
     "llmi_dev_alloc": (_int, [_u64, C.POINTER(_vp)]),
     "llmi_dev_free": (_int, [_vp]),

@@ -73,6 +73,7 @@ struct MegaArgs {
   uint32_t tag_mul, epoch0;
   uint32_t off_h, off_key, off_tok, off_logits, off_cnt;
   uint32_t hints;      // 1: consumers sleep on the arrival counters before they take flagged words
+  uint32_t pf_mode;    // 1: L2 prefetch of the weights ahead of their loads (0: off, for A/B measurements)
   uint32_t tok_uses0;  // greedy steps this model ran before this launch (the token counter's value)
   uint32_t tag_h, tag_key, tag_tok, tag_logits;
   uint32_t head_begin, head_end;  // query heads this rank runs
@@ -88,7 +89,7 @@ struct MegaArgs {
   uint32_t* done_ctr;
   int32_t *gen, *d_tok, *d_pos;
   // shared-memory layout (byte offsets into the dynamic segment)
-  uint32_t sm_h, sm_xs, sm_act, sm_part, sm_attn;
+  uint32_t sm_h, sm_xs, sm_wp, sm_wn, sm_act, sm_part, sm_attn;
   uint32_t part_floats, attn_nbuf;
 };
 
@@ -97,7 +98,7 @@ constexpr uint32_t MEGA_TAGS_PER_LAYER = 5;  // qkv, attention, attn_output, hid
 // five per-layer exchanges in two copies (layer parity)
 constexpr uint32_t MEGA_CNT_STRIDE = 16, MEGA_CNT_H = 0, MEGA_CNT_TOK = 1, MEGA_CNT_LAYER = 2;
 constexpr uint32_t MEGA_CNT_SLOTS = MEGA_CNT_LAYER + 2 * MEGA_TAGS_PER_LAYER;
-constexpr int MEGA_THREADS = 512;  // one CTA per SM with a 128-register budget per thread
+constexpr int MEGA_THREADS = 512;  // one CTA per SM with a 128-register budget per thread (at 1024 threads / 64 registers the weight fragments spill)
 
 // One instantiation of the kernel (mega_impl.cuh): the weight formats it carries code for, its head size (0: any).
 struct MegaVariant {

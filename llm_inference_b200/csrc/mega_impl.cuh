@@ -44,7 +44,7 @@ namespace {
 constexpr int MEGA_WARPS = MEGA_THREADS / 32;
 constexpr int NORM_PER = 6;                      // elements per thread of the norm stage (norm_act_kernel)
 constexpr uint32_t PREFETCH_BYTES = 160 * 1024;  // of a CTA's share requested into L2 at phase start
-constexpr uint32_t PREFETCH_AHEAD = 3;           // rounds (2 items per warp) the rolling prefetch runs ahead of the loads
+constexpr uint32_t PREFETCH_AHEAD = 6;           // rounds (one item per warp) the rolling prefetch runs ahead of the loads
 
 struct PhaseRun {  // per-CTA view of the current entry
   uint32_t my_count, SB, sub, in_tag, out_tag;
@@ -69,14 +69,22 @@ __device__ __forceinline__ void mega_stamp(uint32_t pc, int i) {
     g_mega_stamp[blockIdx.x ? 1 : 0][pc][i] = t;
   }
 }
-__shared__ uint32_t s_pc;  // the entry being run, for stamps from inside the helpers
+
 #define MEGA_STAMP(pc, i) mega_stamp(pc, i)
+// cheap cycle stamps of CTA 0 / thread 0 inside the helpers (slot = 32 per entry)
+__device__ long long g_mega_cyc[1024][32];
+__shared__ uint32_t s_pc;  // the entry being run
+#define MEGA_CYC(i) do { if (threadIdx.x == 0 && blockIdx.x == 0 && s_pc < 1024) g_mega_cyc[s_pc][i] = clock64(); } while (0)
 #else
 #define MEGA_STAMP(pc, i) do { } while (0)
+#define MEGA_CYC(i) do { } while (0)
 #endif
 
-__device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+// One cache line into L2.  Per-lane addresses: a warp covers 32 lines (4 KB) with one instruction — unlike the bulk
+// prefetch (cp.async.bulk.prefetch.L2), whose operands must be warp-uniform and which ptxas therefore wraps in a
+// lane-serializing loop.
+__device__ __forceinline__ void l2_prefetch_line(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p) : "memory");
 }
 __device__ __forceinline__ uint2* my_buf() { return sA.peers.base[sA.rank]; }
 
@@ -130,25 +138,115 @@ __device__ __forceinline__ uint32_t layer_uses(uint32_t g, uint32_t l) {
 
 // ---- prologues: the phase's input vector becomes the quantized activation in shared memory -------------------
 
-// MEGA_PRO_NORM / _FIRST: norm_act_kernel's arithmetic, thread for thread.  That kernel runs T = 512 or 1024
-// threads (by n), thread t holding elements t + k*T; a CTA here has MEGA_THREADS threads, so thread t also plays
-// thread t + MEGA_THREADS of the T = 1024 shape (NORM_PASS passes), and the block sum adds the T/32 warp sums in
-// the same fixed order.
+// Q8_0 quantizer of a vector in shared memory, QI blocks per warp at a time so that their shuffle chains overlap
+// (a CTA has few warps and the stage is latency-bound); per block the arithmetic of warp_quantize_q8_0.
+template <int QI>
+__device__ __forceinline__ void quantize_q8_0_ilp(const float (&v)[QI], const uint32_t (&b)[QI], const bool (&ok)[QI],
+                                                  uint32_t n, uint8_t* buf, int lane) {
+  float amax[QI];
+#pragma unroll
+  for (int k = 0; k < QI; ++k) amax[k] = fabsf(v[k]);
+#pragma unroll
+  for (int o = 16; o; o >>= 1)
+#pragma unroll
+    for (int k = 0; k < QI; ++k) amax[k] = fmaxf(amax[k], __shfl_xor_sync(0xffffffffu, amax[k], o));
+  int q[QI], sum[QI];
+  float d[QI];
+#pragma unroll
+  for (int k = 0; k < QI; ++k) {
+    d[k] = __fdiv_rn(amax[k], 127.0f);
+    const float id = d[k] != 0.0f ? __fdiv_rn(1.0f, d[k]) : 0.0f;
+    q[k] = nearest_int_fma(v[k], id);
+    sum[k] = q[k];
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1)
+#pragma unroll
+    for (int k = 0; k < QI; ++k) sum[k] += __shfl_xor_sync(0xffffffffu, sum[k], o);
+#pragma unroll
+  for (int k = 0; k < QI; ++k) {
+    if (!ok[k]) continue;
+    reinterpret_cast<int8_t*>(buf)[b[k] * 32 + lane] = (int8_t)q[k];
+    if (lane == 0)
+      reinterpret_cast<uint32_t*>(buf + n)[b[k]] =
+          uint32_t(__half_as_ushort(__float2half_rn(d[k]))) | (uint32_t(uint16_t(int16_t(sum[k]))) << 16);
+  }
+}
+
+// activation of kind `kind` from the fp32 vector xs[0..n) in shared memory (emit_act of glue_device.cuh, with the
+// Q8_0 blocks interleaved)
+template <uint32_t KM>
+__device__ __forceinline__ void emit_act_mega(int kind, const float* xs, uint32_t n, uint8_t* buf) {
+  if ((KM & (1u << ACT_Q8_0)) && kind == ACT_Q8_0) {
+    constexpr int QI = 4;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t nblk = n / 32;
+    for (uint32_t b0 = warp; b0 < nblk; b0 += QI * MEGA_WARPS) {
+      float v[QI];
+      uint32_t b[QI];
+      bool ok[QI];
+#pragma unroll
+      for (int k = 0; k < QI; ++k) {
+        b[k] = b0 + k * MEGA_WARPS;
+        ok[k] = b[k] < nblk;
+        v[k] = ok[k] ? xs[b[k] * 32 + lane] : 0.0f;
+      }
+      quantize_q8_0_ilp<QI>(v, b, ok, n, buf, lane);
+    }
+  } else {
+    emit_act<KM>(kind, xs, n, buf);
+  }
+}
+
+// MEGA_PRO_NORM / _FIRST: norm_act_kernel's arithmetic.  That kernel runs T = 512 or 1024 threads (by n), thread t
+// summing the squares of elements t, t + T, ... in that order, then a shuffle tree per warp, then the T/32 warp sums
+// left to right.  Here the vector sits in shared memory and thread t plays that kernel's threads t, t + MEGA_THREADS
+// (NORM_PASS of them): same partial sums, same tree, same final order — the bits of the per-launch path — with a
+// handful of live registers.  The norm weights were copied to shared memory (cp.async) before the CTA started to wait
+// for its input.
 constexpr int NORM_PASS = 1024 / MEGA_THREADS;
-__device__ __forceinline__ float norm_block_sum(const float (&v)[NORM_PASS], int nw) {
+__device__ __forceinline__ float norm_sum_sq(const float* x, uint32_t n, uint32_t T) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  __syncthreads();
 #pragma unroll
   for (int p = 0; p < NORM_PASS; ++p) {
-    float x = v[p];
+    const uint32_t lt = threadIdx.x + p * MEGA_THREADS;  // the per-launch kernel's thread
+    float ss = 0.0f;
+    if (lt < T)
+      for (uint32_t i = lt; i < n; i += T) ss += __fmul_rn(x[i], x[i]);
 #pragma unroll
-    for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-    if (lane == 0) s_red[warp + p * MEGA_WARPS] = x;
+    for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (lane == 0) s_red[warp + p * MEGA_WARPS] = ss;
   }
   __syncthreads();
+  const int nw = int(T / 32);
+  float4 r[8];  // all warp sums first (independent loads), then the left-to-right chain
+#pragma unroll
+  for (int k = 0; k < 8; ++k) r[k] = reinterpret_cast<const float4*>(s_red)[k];
   float s = 0.0f;
-  for (int i = 0; i < nw; ++i) s += s_red[i];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (4 * k < nw) {
+      s += r[k].x;
+      s += r[k].y;
+      s += r[k].z;
+      s += r[k].w;
+    }
+  }
+  __syncthreads();  // s_red is reused
   return s;
+}
+
+// norm weights of the entry -> shared memory, asynchronously (issued before the wait for the entry's input)
+__device__ __forceinline__ void stage_norm_weights(const MegaPhase& P) {
+  if (P.pro != MEGA_PRO_NORM && P.pro != MEGA_PRO_FIRST) return;
+  const uint32_t n4 = sA.E / 4;  // E is a multiple of 32
+  const uint32_t wp = smem_u32(smem + sA.sm_wp), wn = smem_u32(smem + sA.sm_wn);
+  for (uint32_t i = threadIdx.x; i < n4; i += MEGA_THREADS) {
+    if (P.w_post && P.pro == MEGA_PRO_NORM)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(wp + i * 16), "l"(P.w_post + i * 4) : "memory");
+    if (P.w_next) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(wn + i * 16), "l"(P.w_next + i * 4) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
 template <uint32_t TM>
@@ -156,67 +254,51 @@ __device__ MEGA_HOT void norm_prologue(uint32_t pb) {
   const MegaPhase& P = sP[pb];
   float* h_s = reinterpret_cast<float*>(smem + sA.sm_h);
   float* xs = reinterpret_cast<float*>(smem + sA.sm_xs);
+  const float* wps = reinterpret_cast<const float*>(smem + sA.sm_wp);
+  const float* wns = reinterpret_cast<const float*>(smem + sA.sm_wn);
   const uint32_t n = sA.E, T = n >= 2048 ? 1024u : 512u;
   const bool post = P.pro == MEGA_PRO_NORM;
-  const uint2* y = my_buf() + P.in_off;
-  constexpr int NE = NORM_PASS * NORM_PER;
-  float hv[NE], wp[NE], wn[NE];
-  uint32_t yb[NE];
-  const uint2* yp[NE];
-  bool ok[NE], oky[NE];
-#pragma unroll
-  for (int p = 0; p < NORM_PASS; ++p)
-#pragma unroll
-    for (int k = 0; k < NORM_PER; ++k) {
-      const uint32_t lt = threadIdx.x + p * MEGA_THREADS, i = lt + k * T;  // legacy thread, its k-th element
-      const int e = p * NORM_PER + k;
-      ok[e] = lt < T && i < n;
-      oky[e] = ok[e] && post;
-      yp[e] = y + i;
-      wp[e] = (oky[e] && P.w_post) ? P.w_post[i] : 0.0f;
-      wn[e] = (ok[e] && P.w_next) ? P.w_next[i] : 0.0f;
-      hv[e] = ok[e] ? h_s[i] : 0.0f;
-    }
-  ll_wait_n<NE>(yp, oky, sR.in_tag, yb);
+  MEGA_CYC(3);
   if (post) {  // h += (rms_scale(y) * y) * w_post (model.cpp:843-854, 915-924)
-    float ss[NORM_PASS];
+    const uint2* y = my_buf() + P.in_off;
+    for (uint32_t i0 = threadIdx.x; i0 < n; i0 += 4 * MEGA_THREADS) {
+      const uint2* p[4];
+      bool ok[4];
+      uint32_t v[4];
 #pragma unroll
-    for (int p = 0; p < NORM_PASS; ++p) {
-      ss[p] = 0.0f;
-#pragma unroll
-      for (int k = 0; k < NORM_PER; ++k)
-        ss[p] += __fmul_rn(__uint_as_float(yb[p * NORM_PER + k]), __uint_as_float(yb[p * NORM_PER + k]));
-    }
-    const float sc = rms_scale(norm_block_sum(ss, int(T / 32)), n, sA.eps);
-#pragma unroll
-    for (int p = 0; p < NORM_PASS; ++p)
-#pragma unroll
-      for (int k = 0; k < NORM_PER; ++k) {
-        const int e = p * NORM_PER + k;
-        const float yv = __uint_as_float(yb[e]);
-        const float add = P.w_post ? __fmul_rn(__fmul_rn(sc, yv), wp[e]) : yv;
-        hv[e] = __fadd_rn(hv[e], add);
-        if (ok[e]) h_s[threadIdx.x + p * MEGA_THREADS + k * T] = hv[e];
+      for (int k = 0; k < 4; ++k) {
+        ok[k] = i0 + k * MEGA_THREADS < n;
+        p[k] = y + i0 + k * MEGA_THREADS;
       }
+      ll_wait_n<4>(p, ok, sR.in_tag, v);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (ok[k]) xs[i0 + k * MEGA_THREADS] = __uint_as_float(v[k]);
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    MEGA_CYC(4);
+    const float sc = rms_scale(norm_sum_sq(xs, n, T), n, sA.eps);
+    MEGA_CYC(6);
+    for (uint32_t i = threadIdx.x; i < n; i += MEGA_THREADS) {
+      const float yv = xs[i];
+      const float add = P.w_post ? __fmul_rn(__fmul_rn(sc, yv), wps[i]) : yv;
+      h_s[i] = __fadd_rn(h_s[i], add);
+    }
+    __syncthreads();
+  } else {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
   }
   if (!P.w_next) return;
-  float ss[NORM_PASS];  // xn = (rms_scale(h) * h) * w (model.cpp:346-386)
-#pragma unroll
-  for (int p = 0; p < NORM_PASS; ++p) {
-    ss[p] = 0.0f;
-#pragma unroll
-    for (int k = 0; k < NORM_PER; ++k) ss[p] += __fmul_rn(hv[p * NORM_PER + k], hv[p * NORM_PER + k]);
-  }
-  const float sc = rms_scale(norm_block_sum(ss, int(T / 32)), n, sA.eps);
-#pragma unroll
-  for (int p = 0; p < NORM_PASS; ++p)
-#pragma unroll
-    for (int k = 0; k < NORM_PER; ++k) {
-      const int e = p * NORM_PER + k;
-      if (ok[e]) xs[threadIdx.x + p * MEGA_THREADS + k * T] = __fmul_rn(__fmul_rn(sc, hv[e]), wn[e]);
-    }
+  MEGA_CYC(7);
+  const float sc = rms_scale(norm_sum_sq(h_s, n, T), n, sA.eps);  // xn = (rms_scale(h) * h) * w (model.cpp:346-386)
+  MEGA_CYC(8);
+  for (uint32_t i = threadIdx.x; i < n; i += MEGA_THREADS) xs[i] = __fmul_rn(__fmul_rn(sc, h_s[i]), wns[i]);
   __syncthreads();
-  emit_act<llmi_kind_mask(TM)>(int(P.act_kind), xs, n, smem + sA.sm_act);
+  MEGA_CYC(9);
+  emit_act_mega<llmi_kind_mask(TM)>(int(P.act_kind), xs, n, smem + sA.sm_act);
+  MEGA_CYC(10);
 }
 
 // MEGA_PRO_QUANT: flagged fp32 vector -> activation (the quantizers attention_kernel / geglu_act_kernel fuse)
@@ -229,21 +311,23 @@ __device__ MEGA_HOT void quant_prologue(uint32_t pb) {
   const uint32_t n = P.K, in_tag = sR.in_tag;
   const uint2* x = my_buf() + P.in_off;
   if ((KM & (1u << ACT_Q8_0)) && P.act_kind == ACT_Q8_0) {
-    constexpr int G = 4;  // blocks in flight per warp
+    constexpr int G = 4;  // blocks in flight per warp (loads and shuffle chains)
     const uint32_t nblk = n / 32;
-    for (uint32_t b0 = warp * G; b0 < nblk; b0 += MEGA_WARPS * G) {
+    for (uint32_t b0 = warp; b0 < nblk; b0 += MEGA_WARPS * G) {
       const uint2* p[G];
       bool ok[G];
-      uint32_t v[G];
+      uint32_t v[G], b[G];
+      float f[G];
 #pragma unroll
       for (int k = 0; k < G; ++k) {
-        ok[k] = b0 + k < nblk;
-        p[k] = x + (b0 + k) * 32 + lane;
+        b[k] = b0 + k * MEGA_WARPS;
+        ok[k] = b[k] < nblk;
+        p[k] = x + b[k] * 32 + lane;
       }
       ll_wait_n<G>(p, ok, in_tag, v);
 #pragma unroll
-      for (int k = 0; k < G; ++k)
-        if (ok[k]) warp_quantize_q8_0(__uint_as_float(v[k]), b0 + k, n, act, lane);
+      for (int k = 0; k < G; ++k) f[k] = __uint_as_float(v[k]);
+      quantize_q8_0_ilp<G>(f, b, ok, n, act, lane);
     }
   } else if ((KM & (1u << ACT_Q8_K)) && P.act_kind == ACT_Q8_K) {
     for (uint32_t sb = warp; sb < n / 256; sb += MEGA_WARPS) {
@@ -368,21 +452,21 @@ __device__ __forceinline__ Item item_of(const MegaPhase& P, uint32_t t, uint32_t
   return it;
 }
 
-// the item's pieces of the planes into L2: chunk j of a slab is bytes [j * chunk, (j + 1) * chunk) of the slab's run in
-// every plane (the last chunk may be short)
-__device__ __forceinline__ void prefetch_item(const MegaPhase& P, const Item& it) {
+// The item's pieces of the planes into L2, by the whole warp: chunk j of a slab is bytes [j * chunk, (j + 1) * chunk)
+// of the slab's run in every plane (the last chunk may be short); lane l takes the l-th 128-byte line.
+__device__ __forceinline__ void prefetch_item(const MegaPhase& P, const Item& it, int lane) {
+  if (!sA.pf_mode) return;
   const GemvArgs& a = P.m[it.mi];
   const uint32_t bq = P.slab_q[it.mi], bd = P.slab_d[it.mi], bx = P.slab_x[it.mi];
   const uint32_t cq = P.chunk_q[it.mi], cd = P.chunk_d[it.mi], cx = P.chunk_x[it.mi];
-  const uint32_t q0 = it.j * cq;
-  l2_prefetch(a.q + size_t(it.s) * bq + q0, min(cq, bq - q0));
-  if (bd) {
-    const uint32_t d0 = it.j * cd;
-    l2_prefetch(a.d + size_t(it.s) * bd + d0, min(cd, bd - d0));
-  }
-  if (bx) {
-    const uint32_t x0 = it.j * cx;
-    l2_prefetch(a.x + size_t(it.s) * bx + x0, min(cx, bx - x0));
+  const uint32_t q0 = it.j * cq, d0 = it.j * cd, x0 = it.j * cx;
+  const uint32_t nq = (min(cq, bq - q0) + 127) / 128, nd = bd ? (min(cd, bd - d0) + 127) / 128 : 0u,
+                 nx = bx ? (min(cx, bx - x0) + 127) / 128 : 0u;
+  for (uint32_t l = lane; l < nq + nd + nx; l += 32) {
+    const uint8_t* p = l < nq ? a.q + size_t(it.s) * bq + q0 + l * 128
+                     : l < nq + nd ? a.d + size_t(it.s) * bd + d0 + (l - nq) * 128
+                                   : a.x + size_t(it.s) * bx + x0 + (l - nq - nd) * 128;
+    l2_prefetch_line(p);
   }
 }
 
@@ -399,40 +483,60 @@ __device__ MEGA_HOT void gemv_loop(uint32_t pb) {
   for (uint32_t i0 = 0; i0 < my_count; i0 += SB) {
     const uint32_t nsl = min(SB, my_count - i0);
     const uint32_t n_items = nsl * msub * J;
-#pragma unroll 1
-    for (uint32_t t = warp; t < n_items; t += 2 * MEGA_WARPS) {
-      // keep DRAM busy PREFETCH_AHEAD rounds ahead of the loads (the next batch included: lanes 0 / 1 take the
-      // round's two items)
-      if (lane < 2) {
-        const uint32_t tp = t + lane * MEGA_WARPS + PREFETCH_AHEAD * 2 * MEGA_WARPS;
-        if (tp < n_items) {
-          prefetch_item(P, item_of(P, tp, i0, J, msub));
-        } else if (i0 + SB < my_count && tp - n_items < min(SB, my_count - i0 - SB) * msub * J) {
-          prefetch_item(P, item_of(P, tp - n_items, i0 + SB, J, msub));
-        }
+    // Software pipeline over the warp's items t, t + W, t + 2W ...: the loads of the next item are in flight while
+    // this one is folded (two fragment sets, ping-pong), and lane 0 requests the item PREFETCH_AHEAD rounds further
+    // down into L2 (the next batch included).
+    auto prefetch_ahead = [&](uint32_t t) {
+      const uint32_t tp = t + PREFETCH_AHEAD * MEGA_WARPS;
+      if (tp < n_items) {
+        prefetch_item(P, item_of(P, tp, i0, J, msub), lane);
+      } else if (i0 + SB < my_count && tp - n_items < min(SB, my_count - i0 - SB) * msub * J) {
+        prefetch_item(P, item_of(P, tp - n_items, i0 + SB, J, msub), lane);
       }
-      // two items in flight per warp: 8 independent 128-bit loads (+ scales) before the first use
-      const uint32_t t1 = t + MEGA_WARPS;
-      const bool two = t1 < n_items;
-      const Item it0 = item_of(P, t, i0, J, msub), it1 = item_of(P, two ? t1 : t, i0, J, msub);
-      const GemvArgs& a0 = P.m[it0.mi];
-      const GemvArgs& a1 = P.m[it1.mi];
-      FragSet<B, N> f0, f1;
-      load_item<B, N>(f0, a0, it0.s, it0.j, r, sub);
-      if (two) load_item<B, N>(f1, a1, it1.s, it1.j, r, sub);
-      const float v0 = compute_item<B, N>(f0, a0, act, it0.j, sub);
-      if (lane < LLMI_SLAB) part[t * LLMI_SLAB + lane] = v0;
-      if (two) {
-        const float v1 = compute_item<B, N>(f1, a1, act, it1.j, sub);
-        if (lane < LLMI_SLAB) part[t1 * LLMI_SLAB + lane] = v1;
-      }
+    };
+    FragSet<B, N> fa, fb;
+    Item ia, ib;
+    uint32_t t = warp;
+    if (t < n_items) {
+      ia = item_of(P, t, i0, J, msub);
+      MEGA_CYC(13);
+      load_item<B, N>(fa, P.m[ia.mi], ia.s, ia.j, r, sub);
+      MEGA_CYC(21);
     }
-    MEGA_STAMP(s_pc, 6);
+#pragma unroll 1
+    while (t < n_items) {
+      const uint32_t t1 = t + MEGA_WARPS, t2 = t1 + MEGA_WARPS;
+      if (t1 < n_items) {
+        ib = item_of(P, t1, i0, J, msub);
+        load_item<B, N>(fb, P.m[ib.mi], ib.s, ib.j, r, sub);
+      }
+      prefetch_ahead(t);
+      if (t == uint32_t(warp)) MEGA_CYC(22);
+      {
+        const float v = compute_item<B, N>(fa, P.m[ia.mi], act, ia.j, sub);
+        if (t == uint32_t(warp)) MEGA_CYC(23);
+        if (lane < LLMI_SLAB) part[t * LLMI_SLAB + lane] = v;
+      }
+      if (t == uint32_t(warp)) MEGA_CYC(24);
+      if (t1 >= n_items) break;
+      if (t2 < n_items) {
+        ia = item_of(P, t2, i0, J, msub);
+        load_item<B, N>(fa, P.m[ia.mi], ia.s, ia.j, r, sub);
+      }
+      prefetch_ahead(t1);
+      {
+        const float v = compute_item<B, N>(fb, P.m[ib.mi], act, ib.j, sub);
+        if (lane < LLMI_SLAB) part[t1 * LLMI_SLAB + lane] = v;
+      }
+      t = t2;
+    }
+    MEGA_CYC(14);
     __syncthreads();
-    MEGA_STAMP(s_pc, 7);
+    MEGA_CYC(15);
     best = gemv_epilogue(pb, i0, nsl, best);
-    MEGA_STAMP(s_pc, 8);
+    MEGA_CYC(16);
     __syncthreads();  // the partials are reused by the next batch
+    MEGA_CYC(17);
   }
   if (P.epi == MEGA_EPI_LOGITS && sA.logits_mode == 2) {  // greedy argmax: warp keys -> the rank's key
 #pragma unroll
@@ -444,18 +548,18 @@ __device__ MEGA_HOT void gemv_loop(uint32_t pb) {
   }
 }
 
-// The first PREFETCH_BYTES of this CTA's share of the phase's weights, requested into L2: one bulk prefetch per
-// (slab, plane), issued by as many threads as there are ranges.
+// The first PREFETCH_BYTES of this CTA's share of an entry's weights, requested into L2 line by line (thread t takes
+// lines t, t + MEGA_THREADS ... of the concatenation of its first slabs' planes).
 __device__ __forceinline__ void prefetch_share(const MegaPhase& P) {
-  if (P.kind != MEGA_GEMV) return;
+  if (P.kind != MEGA_GEMV || !sA.pf_mode) return;
   const uint32_t my_count = P.v_total > blockIdx.x ? (P.v_total - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
   const uint32_t msub = P.epi == MEGA_EPI_GEGLU ? 2u : 1u;
   if (my_count == 0) return;
-  uint32_t per = P.slab_q[0] + P.slab_d[0] + P.slab_x[0];  // bytes of one virtual slab (GEGLU: both matrices)
-  per *= msub;
-  const uint32_t n_pf = min(my_count, max(1u, PREFETCH_BYTES / max(per, 1u)));
-  for (uint32_t t = threadIdx.x; t < n_pf * msub * 3; t += MEGA_THREADS) {
-    const uint32_t plane = t % 3, sl = t / 3;
+  const uint32_t lq = (P.slab_q[0] + 127) / 128, ld = (P.slab_d[0] + 127) / 128, lx = (P.slab_x[0] + 127) / 128;
+  const uint32_t per = lq + ld + lx;  // lines of one slab (all matrices of an entry share K, so also their slab sizes)
+  const uint32_t n_sl = min(my_count * msub, max(1u, PREFETCH_BYTES / 128 / max(per, 1u)));
+  for (uint32_t t = threadIdx.x; t < n_sl * per; t += MEGA_THREADS) {
+    const uint32_t sl = t / per, l = t - sl * per;
     const uint32_t v = blockIdx.x + (sl / msub) * gridDim.x;
     uint32_t mi, s;
     if (msub == 2) {
@@ -465,9 +569,10 @@ __device__ __forceinline__ void prefetch_share(const MegaPhase& P) {
       resolve(P, v, mi, s);
     }
     const GemvArgs& a = P.m[mi];
-    const uint32_t bytes = plane == 0 ? P.slab_q[mi] : (plane == 1 ? P.slab_d[mi] : P.slab_x[mi]);
-    const uint8_t* base = plane == 0 ? a.q : (plane == 1 ? a.d : a.x);
-    if (bytes) l2_prefetch(base + size_t(s) * bytes, bytes);
+    const uint8_t* p = l < lq ? a.q + size_t(s) * P.slab_q[mi] + l * 128
+                     : l < lq + ld ? a.d + size_t(s) * P.slab_d[mi] + (l - lq) * 128
+                                   : a.x + size_t(s) * P.slab_x[mi] + (l - lq - ld) * 128;
+    l2_prefetch_line(p);
   }
 }
 
@@ -484,18 +589,19 @@ __device__ __forceinline__ void gemv_phase(uint32_t pb, uint32_t tagbase, uint32
     sR = R;
   }
   __syncthreads();
-  MEGA_STAMP(pc, 3);
+  MEGA_CYC(0);
   // the weights depend on nothing: ask for the NEXT entry's share now (its descriptor has landed in sP[1]), so that it
   // is in L2 a whole phase before its first load; entry 0's own share goes out here too
   if (pc == 0) prefetch_share(P);
   if (pc + 1 < sA.n_prog) prefetch_share(sP[1]);
-  MEGA_STAMP(pc, 4);
+  stage_norm_weights(P);
+  MEGA_CYC(1);
   if (P.pro != MEGA_PRO_REUSE && P.pro != MEGA_PRO_FIRST) {
     // sleep on the producers' arrival counter first (one thread), then take the flagged words
     if (threadIdx.x == 0 && sA.hints) hint_wait(P.in_slot, layer_uses(g, P.in_layer) * P.in_arrivals);
     __syncthreads();
   }
-  MEGA_STAMP(pc, 5);
+  MEGA_CYC(2);
   if (P.pro == MEGA_PRO_QUANT) {
     // (a CTA without rows here still prepares the activation: a MEGA_PRO_REUSE entry may follow)
     quant_prologue<TM>(pb);
@@ -504,6 +610,7 @@ __device__ __forceinline__ void gemv_phase(uint32_t pb, uint32_t tagbase, uint32
   }
   __syncthreads();
   MEGA_STAMP(pc, 1);
+  MEGA_CYC(12);
   if (sR.my_count != 0) {
     // (only the formats of this instantiation exist in its code: see the note at decode_mega_kernel)
     const uint32_t ty = P.type;
@@ -756,6 +863,7 @@ cudaError_t mega_variant_launch(const MegaArgs& a, uint32_t n_ctas, size_t smem_
 cudaError_t mega_variant_stamps(unsigned long long* out) {
   return cudaMemcpyFromSymbol(out, g_mega_stamp, sizeof(unsigned long long) * 2 * 1024 * 16);
 }
+cudaError_t mega_variant_cycles(long long* out) { return cudaMemcpyFromSymbol(out, g_mega_cyc, sizeof(long long) * 1024 * 32); }
 #endif
 
 #define MEGA_VARIANT(TM, DS) MegaVariant{TM, DS, mega_variant_init<TM, DS>, mega_variant_launch<TM, DS>}

@@ -9,4 +9,5 @@ const MegaVariant* llmi_mega_variants_q4(int* n) {
 
 #ifdef LLMI_MEGA_TIMING  // dev only (tools/mega_timeline.py): the stamps of this file's instantiations
 extern "C" int llmi_debug_mega_stamps_q4(unsigned long long* out /*[2][1024][16]*/) { return int(mega_variant_stamps(out)); }
+extern "C" int llmi_debug_mega_cycles_q4(long long* out /*[1024][32]*/) { return int(mega_variant_cycles(out)); }
 #endif

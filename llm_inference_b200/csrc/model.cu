@@ -567,6 +567,8 @@ int mega_build(llmi_model_s* m) {
   if (const char* e = getenv("LLMI_MEGA_CTAS")) m->mega_ctas = std::min<uint32_t>(m->mega_ctas, uint32_t(std::max(1, atoi(e))));
   a.hints = 1;
   if (const char* e = getenv("LLMI_MEGA_NO_HINTS")) a.hints = e[0] == '1' ? 0u : 1u;
+  a.pf_mode = 1;
+  if (const char* e = getenv("LLMI_MEGA_PF")) a.pf_mode = uint32_t(atoi(e));
   std::vector<MegaPhase> prog;
   std::vector<MegaAttn> attn(L);
   size_t act_max = 0;
@@ -658,14 +660,24 @@ int mega_build(llmi_model_s* m) {
   }
   a.sm_h = 0;
   a.sm_xs = uint32_t(up128(size_t(E) * 4));
-  a.sm_act = a.sm_xs + uint32_t(up128(size_t(E) * 4));
+  a.sm_wp = a.sm_xs + uint32_t(up128(size_t(E) * 4));  // norm weights of the running entry (post-norm, next norm)
+  a.sm_wn = a.sm_wp + uint32_t(up128(size_t(E) * 4));
+  a.sm_act = a.sm_wn + uint32_t(up128(size_t(E) * 4));
   a.sm_part = a.sm_act + uint32_t(up128(act_max));
   a.sm_attn = a.sm_xs;
   size_t part_bytes = 32 * 1024;
   const size_t part_min = size_t(LLMI_SLAB) * jmax * 2 * 4;
   if (part_bytes < part_min) part_bytes = up128(part_min);
   size_t attn_bytes = 0;
+  // K/V tiles of the attention ring: what fits, but no more than 3 — the rest of the 228 KB stays L1 (the kernel's
+  // few spill slots and the descriptors live there)
+  size_t attn_cap = 3;
+  if (const char* e = getenv("LLMI_MEGA_NBUF")) attn_cap = size_t(std::max(2, atoi(e)));
   a.attn_nbuf = limit > a.sm_attn ? llmi_mega_attention_nbuf(m->t_max, m->D, limit - a.sm_attn, &attn_bytes) : 0;
+  if (a.attn_nbuf > attn_cap) {
+    attn_bytes -= (a.attn_nbuf - attn_cap) * 32768;
+    a.attn_nbuf = uint32_t(attn_cap);
+  }
   if (a.attn_nbuf == 0 || a.sm_part + part_bytes > limit) {
     m->use_mega = false;  // context or K too large for one CTA's shared memory: the per-launch path runs it
     return LLMI_OK;
@@ -1136,6 +1148,7 @@ int llmi_model_last_logits(llmi_model_t m, float* logits_host) {
 }
 
 int llmi_model_launches_per_step(llmi_model_t m) { return m ? m->launches_per_step : 0; }
+int llmi_model_decode_path(llmi_model_t m) { return m && m->use_mega ? 1 : 0; }
 
 int llmi_model_last_forward_stats(llmi_model_t m, float* ms_device, int* launches) {
   if (!m) return llmi_fail(LLMI_ERR_ARG, "llmi_model_last_forward_stats: null model");

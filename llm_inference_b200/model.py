@@ -86,6 +86,11 @@ class Model:
     def launches_per_step(self) -> int:
         return int(_lib.load().llmi_model_launches_per_step(self.h))
 
+    @property
+    def persistent(self) -> bool:
+        """True when this model decodes with the persistent kernel (LLMI_DECODE=mega at load time)."""
+        return bool(_lib.load().llmi_model_decode_path(self.h))
+
     def close(self) -> None:
         if self.h:
             _lib.load().llmi_model_free(self.h)

@@ -54,15 +54,17 @@ for c in range(2):
             print(f"  pc {pc:4d} {name:6s} start {(a-t0)/1e3:9.2f} us  wait+prologue {pro:7.2f}  work {mv:7.2f}")
     for name, (pro, mv, cnt) in sorted(kinds.items()):
         print(f"  {name}: n={cnt} wait+prologue {pro:.1f} us (avg {pro/cnt:.2f})  work {mv:.1f} us (avg {mv/cnt:.2f})")
-    # finer stamps of the mat-vec entries: 0 start, 3 setup done, 4 prefetch issued, 5 hint seen, 1 prologue done,
-    # 6 items done (thread 0), 7 barrier, 8 epilogue stores issued, 2 end
-    order = [0, 3, 4, 5, 1, 6, 7, 8, 2]
-    names = ["setup", "prefetch", "hint_wait", "prologue", "items", "barrier", "epilogue", "tail"]
-    for k in range(5):
-        rows = [st[pc] for pc in range(n - 1) if st[pc, 1] != 0 and pc % 5 == k and st[pc, 6] != 0]
-        if not rows:
-            continue
-        a = np.array(rows, dtype=np.float64)
-        d = [(a[:, order[i + 1]] - a[:, order[i]]).mean() / 1e3 for i in range(len(order) - 1)]
-        print(f"  gemv{k} avg us: " + "  ".join(f"{nm} {v:.2f}" for nm, v in zip(names, d)))
+m_cyc = np.zeros((1024, 32), np.int64)
+fc = getattr(L, f"llmi_debug_mega_cycles_{tu}")
+fc.argtypes = [C.c_void_p]
+fc(m_cyc.ctypes.data)
+# cycle stamps of CTA 0 / thread 0: 0 entry setup done, 1 prefetch issued, 2 hint seen, 3 norm: static loads issued,
+# 4 flagged words in, 5 first block sum, 6 first scale, 7 h updated, 8 second scale, 9 xn in smem, 10 activation
+# quantized, 12 prologue barrier passed, 13 first item: addresses ready, 14 items done, 15 barrier, 16 epilogue, 17 barrier
+order = [0, 1, 2, 3, 4, 6, 7, 8, 9, 10, 12, 13, 21, 22, 23, 24, 14, 15, 16, 17]
+for k in (0, 3):
+    rows = [m_cyc[pc] for pc in range(5, 120) if pc % 5 == k]
+    a = np.array(rows, dtype=np.float64)
+    d = [(a[:, order[i + 1]] - a[:, order[i]]).mean() for i in range(len(order) - 1)]
+    print(f"gemv{k} cycles between stamps " + " ".join(f"{order[i]}-{order[i+1]}:{v:.0f}" for i, v in enumerate(d)))
 m.close()
