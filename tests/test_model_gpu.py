@@ -7,7 +7,10 @@ and the attention value accumulator is rounded to f16 at every cached position
 (model.cpp:461-474, 528-538) — where a 1e-7 upstream difference (summation
 order of the mat-vecs, libm vs CUDA tanhf/expf/sincosf) occasionally flips one
 rounding (2^-11 relative on that element, persistent once it sits in the KV
-cache; SURVEY §7 hard part 7).  So: median error <= 1e-5, every step <= 5e-2."""
+cache; SURVEY §7 hard part 7).  So: MEDIAN error <= 1e-5, every step <= 5e-2 —
+and tests/test_reference_conditioning.py shows that the reference
+itself moves by the same order under a 1-ulp change of one weight, i.e. the 5e-2
+bar is the conditioning of the reference's fp16 arithmetic, not slack for ours."""
 import numpy as np
 import pytest
 
@@ -37,7 +40,7 @@ def test_forward_matches_reference_golden(gpu_ops, mg, name):
         lg = m.forward([t], pos)
         errs.append(float(np.abs(lg - ref_logits[i + 1]).max() / np.abs(ref_logits[i + 1]).max()))
         pos += 1
-    assert max(errs) <= TOL_WORST and min(errs) <= TOL_TYPICAL, errs
+    assert max(errs) <= TOL_WORST and float(np.median(errs)) <= TOL_TYPICAL, errs
     m.close()
 
 
@@ -78,22 +81,27 @@ def test_32_greedy_steps_token_identical_vs_compiled_reference(gpu_ops):
         ref, m = R.model(img), Model(img, max_positions=128)
         prompt = np.arange(5, 21, dtype=np.int32)
         a, b = ref.forward(prompt, 0), m.forward(prompt, 0)
-        pos, margins, errs, toks = len(prompt), [], [], []
+        pos, margins, errs, toks, near_ties = len(prompt), [], [], [], 0
         for step in range(32):
             ta, tb = int(a.argmax()), int(b.argmax())
             srt = np.sort(a)
             margins.append(float((srt[-1] - srt[-2]) / np.abs(a).max()))
             errs.append(float(np.abs(a - b).max() / np.abs(a).max()))
-            if margins[-1] > 2 * errs[-1]:  # a tie within the error bound is not a failure of the path
-                assert ta == tb, f"{wt}: token {step} differs (margin {margins[-1]:.3e}, err {errs[-1]:.3e})"
+            near_ties += margins[-1] <= 2 * errs[-1]  # top-1 / top-2 closer than the observed error: reported, not excused
+            assert ta == tb, f"{wt}: token {step} differs (margin {margins[-1]:.3e}, err {errs[-1]:.3e})"
             toks.append(ta)
             a, b = ref.forward([ta], pos), m.forward([ta], pos)
             pos += 1
+        # Nothing is excused: the tokens above are asserted at EVERY step.  near_ties only reports how many steps were
+        # decided by less than twice the logit error — on the small-embedding models that error sits at the reference's
+        # own chaos floor (tests/test_reference_conditioning.py: ~2e-2 under a 1-ulp perturbation, because an int8
+        # activation rounding or an f16 KV rounding that flips is a 2^-8 .. 2^-11 relative step), so such steps exist.
         # N(0,1) embeddings: logits are dominated by well-conditioned terms; small embeddings make the
         # logits tiny next to the activations, so one flipped f16 rounding in the KV cache shows as ~1e-2
         assert max(errs) <= (1e-3 if std == 1.0 else TOL_WORST), errs
         print(f"{wt} std={std}: 32 greedy tokens identical ({len(set(toks))} distinct), min margin/max "
-              f"{min(margins):.2e}, logits err/max: median {np.median(errs):.1e} max {max(errs):.1e}")
+              f"{min(margins):.2e}, logits err/max: median {np.median(errs):.1e} max {max(errs):.1e}, steps with margin <= "
+              f"2 x err: {near_ties}")
         ref.close()
         m.close()
 
@@ -182,3 +190,54 @@ def test_persistent_decode_kernel_is_bitwise_the_per_launch_path(gpu_ops, monkey
         assert np.array_equal(o[1], ref[1]), f"{mode}: greedy tokens {o[1]} vs {ref[1]}"
         assert np.array_equal(o[2].view(np.uint32), ref[2].view(np.uint32)), f"{mode}: last logits of the greedy loop"
         assert np.array_equal(o[3].view(np.uint32), ref[3].view(np.uint32)), f"{mode}: forward() logits after decode"
+
+
+def _ref_greedy(ref_model, prompt, n_steps):
+    """The reference's generation loop (main.cpp:165-221): the n_steps + 1 greedy tokens after the prompt, the
+    top-1 / top-2 margin of every step (relative to max |logit|) and the logits of the last step."""
+    lg = ref_model.forward(prompt, 0)
+    pos, toks, margins = len(prompt), [], []
+    for _ in range(n_steps + 1):
+        srt = np.sort(lg)
+        margins.append(float((srt[-1] - srt[-2]) / np.abs(lg).max()))
+        toks.append(int(lg.argmax()))
+        if len(toks) == n_steps + 1:
+            break
+        lg = ref_model.forward([toks[-1]], pos)
+        pos += 1
+    return toks, margins, lg
+
+
+@pytest.mark.parametrize("workload,prompt_len,steps", [("gemma-3-1b-q4_0", 64, 32), ("gemma-3-4b-q4_k_m", 16, 8)])
+def test_free_running_greedy_decode_at_baseline_dims_matches_reference(gpu_ops, workload, prompt_len, steps):
+    """BASELINE.json configs 2 and 3 at FULL dimensions (gemma-3-1b: 26 layers, E 1152, F 6912, 4/1 heads x 256,
+    V 262144, Q4_0 + F16 logits; gemma-3-4b Q4_K_M layout: 34 layers, E 2560, mixed Q4_K / Q6_K, Q6_K embeddings):
+    prompt through the batched prefill, then the on-device greedy loop FREE-RUNNING (every token feeds the next step,
+    nothing is teacher-forced) against the reference's own generation loop on its CPU code (oracle/_ref).  Bar
+    (north_star): identical tokens; the minimum top-1 / top-2 margin is reported."""
+    from oracle import binding
+    if not binding.ref_available():
+        pytest.skip("oracle/_ref did not travel to this box")
+    import bench
+    from llm_inference_b200.model import Model
+    dims_name, wt, et = bench.WORKLOADS[workload]
+    dims = synth.GEMMA3[dims_name]
+    # embeddings small next to the layer outputs, so that the tied logits depend on the whole network instead of echoing
+    # the input token (layers >= 1 reuse layer 0's generated bytes: generation time only)
+    img = synth.build_gemma3_gguf(dims, wt, et, seed=4321, embd_std=0.02, distinct_layers=False)
+    prompt = ((np.arange(prompt_len, dtype=np.int64) * 7919 + 13) % dims.vocab).astype(np.int32)
+    R = binding.Ref(n_threads=__import__("os").cpu_count() or 1)
+    ref = R.model(img)
+    ref_toks, margins, ref_last = _ref_greedy(ref, prompt, steps)
+    ref.close()
+    m = Model(img, max_positions=prompt_len + steps + 8)
+    first = int(m.forward(prompt, 0).argmax())
+    toks, _ = m.decode_greedy(first, prompt_len, steps)
+    ours = [first] + [int(t) for t in toks]
+    last = m.last_logits()  # logits of the step that consumed ours[-2]: they produced ours[-1]
+    m.close()
+    assert ours == ref_toks, f"{workload}: free-running greedy tokens differ\nours {ours}\nref  {ref_toks}\nmargins {margins}"
+    err = float(np.abs(last - ref_last).max() / np.abs(ref_last).max())
+    assert err <= TOL_WORST, err
+    print(f"{workload}: {steps + 1} free-running greedy tokens identical ({len(set(ours))} distinct), min margin / max|logit| "
+          f"{min(margins):.2e}, last-step logits err / max {err:.1e}")
