@@ -672,8 +672,11 @@ cudaError_t launch_umma(const GemvArgs* args, int n, cudaStream_t s) {
   alignas(64) CUtensorMap tms[GEMV_MAX_BATCH];
   for (int i = 0; i < GEMV_MAX_BATCH; ++i)
     if ((e = make_plane_map(&tms[i], b.a[i], IS_Q8)) != cudaSuccess) return e;
-  e = llmi_launch(gemm_umma_kernel<IS_Q8>, dim3(ctas, tiles_n, gz), dim3(umma::WARPS * 32), umma::Cfg<IS_Q8>::SMEM_BYTES, s, b,
-                  (const uint4*)g_bq, (const float*)g_bd, nj, tms[0], tms[1], tms[2]);
+  if (gz == 1)  // every CTA walks all chunks of its tile: running totals in registers, rows stored once, no reduce launch
+    return llmi_launch(gemm_umma_kernel<IS_Q8, true>, dim3(ctas, tiles_n, 1), dim3(umma::WARPS * 32),
+                       umma::Cfg<IS_Q8>::SMEM_BYTES, s, b, (const uint4*)g_bq, (const float*)g_bd, nj, tms[0], tms[1], tms[2]);
+  e = llmi_launch(gemm_umma_kernel<IS_Q8, false>, dim3(ctas, tiles_n, gz), dim3(umma::WARPS * 32),
+                  umma::Cfg<IS_Q8>::SMEM_BYTES, s, b, (const uint4*)g_bq, (const float*)g_bd, nj, tms[0], tms[1], tms[2]);
   if (e != cudaSuccess) return e;
   const unsigned rb = unsigned(std::min<uint64_t>((outs + 255) / 256, uint64_t(g_sm_count) * 8));
   return llmi_launch(toklane_reduce_kernel, dim3(rb, n), dim3(256), 0, s, b);
@@ -808,9 +811,13 @@ void llmi_gemv_read_env() {
 cudaError_t llmi_gemv_init() {
   cudaError_t e0;
   llmi_gemv_read_env();
-  if ((e0 = cudaFuncSetAttribute(gemm_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  if ((e0 = cudaFuncSetAttribute(gemm_umma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  int(umma::Cfg<false>::SMEM_BYTES))) != cudaSuccess) return e0;
-  if ((e0 = cudaFuncSetAttribute(gemm_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  if ((e0 = cudaFuncSetAttribute(gemm_umma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 int(umma::Cfg<true>::SMEM_BYTES))) != cudaSuccess) return e0;
+  if ((e0 = cudaFuncSetAttribute(gemm_umma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 int(umma::Cfg<false>::SMEM_BYTES))) != cudaSuccess) return e0;
+  if ((e0 = cudaFuncSetAttribute(gemm_umma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  int(umma::Cfg<true>::SMEM_BYTES))) != cudaSuccess) return e0;
   if ((e0 = cudaFuncSetAttribute(gemm_toklane_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  int(tl_smem(8)))) != cudaSuccess) return e0;

@@ -163,7 +163,11 @@ __device__ long long g_umma_stamp[10][160];
 #endif
 
 // grid = (row tiles of all matrices of the batch, token tiles, K-chunk groups of `nj` chunks)
-template <bool IS_Q8>
+// DIRECT: the CTA walks ALL K-chunks of its tile in order (grid.z == 1, true for every large matrix): the chunk
+// partials are added left to right in registers — the canonical order — and each (token, row) is stored once.  The
+// partials never travel through memory (they were 5.5x the call's algorithmic traffic, profiles/r01_ncu_umma_q8_final.csv)
+// and the reduce launch disappears.  !DIRECT: K-chunk groups across grid.z, partials to part[], toklane_reduce_kernel.
+template <bool IS_Q8, bool DIRECT>
 __global__ void __launch_bounds__(umma::WARPS * 32, 1)
 gemm_umma_kernel(const GemvBatch batch, const uint4* __restrict__ bq, const float* __restrict__ bd, uint32_t nj,
                  const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
@@ -356,6 +360,7 @@ gemm_umma_kernel(const GemvBatch batch, const uint4* __restrict__ bq, const floa
     if (lane == 0)
       for (int t = 0; t < NTMEM; ++t) mbar_arrive(&tempty[t]);
     float acc[4][EC];
+    float total[DIRECT ? EC : 1];  // DIRECT: running sum of the chunk partials of (row, token column k)
 #pragma unroll
     for (int c = 0; c < 4; ++c)
 #pragma unroll
@@ -440,7 +445,13 @@ gemm_umma_kernel(const GemvBatch batch, const uint4* __restrict__ bq, const floa
 #pragma unroll
         for (int k = 0; k < EC; ++k) {
           const float p = (acc[0][k] + acc[1][k]) + (acc[2][k] + acc[3][k]);
-          if (row_ok && tok0 + k < a.n_tok) a.part[(size_t(j) * a.n_tok + tok0 + k) * rows_p + row] = p;
+          if constexpr (DIRECT) {
+            total[k] = j ? total[k] + p : p;  // p0, then + p1, + p2 ...: the order of toklane_reduce_kernel
+            if (b_last == nb - 1 && row < a.n_local && tok0 + k < a.n_tok)
+              a.out[size_t(tok0 + k) * a.out_stride + row] = total[k];
+          } else {
+            if (row_ok && tok0 + k < a.n_tok) a.part[(size_t(j) * a.n_tok + tok0 + k) * rows_p + row] = p;
+          }
           acc[0][k] = acc[1][k] = acc[2][k] = acc[3][k] = 0.0f;
         }
       }

@@ -367,3 +367,28 @@ def test_every_kernel_is_bitwise_the_canonical_order_oracle(gpu_ops, port, t):
                 ops.gemm_tokens(w, xs, m, out)
                 got = out.get().reshape(m, n)
             assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (t, k, n, m)
+
+
+@pytest.mark.parametrize("t", [Q4_0, Q8_0])
+def test_tensor_core_prefill_direct_store_is_bitwise_single_calls(gpu_ops, t):
+    """A token batch large enough that every CTA of the tcgen05 int8 kernel walks ALL K-chunks of its tile
+    (grid.z == 1: rows/128 x tokens/32 >= 2 CTAs per SM): the chunk partials are then added in registers and each
+    (token, row) is stored once — no partials buffer, no reduce launch (umma_prefill.cuh, DIRECT).  Sampled tokens,
+    bit for bit against the one-token mat-vec; ragged N, ragged token tile and a K that ends inside a chunk."""
+    ops = gpu_ops
+    k, n, m = 1184 if t == Q4_0 else 1056, 4099, 331
+    w_host = synth.random_blocks(t, n, k, seed=91)
+    w = ops.DeviceWeight(w_host, t, k, n)
+    act = ops.Activation(k)
+    x = np.random.default_rng(5).standard_normal((m, k)).astype(np.float32)
+    xs, out = ops.DeviceVector(m * k, x), ops.DeviceVector(m * n, np.full(m * n, np.nan, np.float32))
+    ops.gemm_tokens(w, xs, m, out)
+    got = out.get().reshape(m, n)
+    assert not np.isnan(got).any()
+    one, o1 = ops.DeviceVector(k), ops.DeviceVector(n)
+    for i in (0, 31, 32, 170, 319, 320, 330):
+        one.set(x[i])
+        ops.mat_vec_mul_dev(w, one, act, o1)
+        assert np.array_equal(got[i].view(np.uint32), o1.get().view(np.uint32)), (t, i)
+    for v in (xs, out, one, o1, act, w):
+        v.close()
