@@ -36,7 +36,21 @@ struct Context {
   size_t scratch_cap = 0;
   uint8_t* tok_act = nullptr;  // quantized activations of a token batch (llmi_gemm_tokens)
   size_t tok_act_cap = 0;
-  std::map<std::tuple<const void*, uint32_t, uint64_t, uint64_t>, llmi_weight_t> registry;
+  // registry of the ops.h drop-in: repacked weights keyed by (host pointer, type, K, N), each with a fingerprint of
+  // the host bytes it was built from (see llmi_registry_get)
+  struct RegEntry {
+    llmi_weight_t w = nullptr;
+    uint64_t fp = 0;
+  };
+  std::map<std::tuple<const void*, uint32_t, uint64_t, uint64_t>, RegEntry> registry;
+  // upload pipeline: raw GGUF rows -> pinned staging -> device staging -> repack kernel, two slots
+  // deep, on its own stream; allocated on first use, reused by every upload of the process
+  cudaStream_t up_stream = nullptr;
+  uint8_t* up_pinned[2] = {nullptr, nullptr};
+  uint8_t* up_dev[2] = {nullptr, nullptr};
+  cudaEvent_t up_done[2] = {nullptr, nullptr};
+  size_t up_cap = 0;
+  int up_next = 0;
 };
 Context g;
 std::mutex g_mu;
@@ -59,6 +73,8 @@ int ensure_cap(void** p, size_t* cap, size_t need) {
   *cap = want;
   return LLMI_OK;
 }
+
+void upload_pipeline_free();  // defined with the upload pipeline below
 
 #define LLMI_NEED_INIT() \
   if (!g.ready) return llmi_fail(LLMI_ERR_STATE, "llmi_init() has not been called")
@@ -127,8 +143,10 @@ int llmi_shutdown(void) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (!g.ready) return LLMI_OK;
   cudaDeviceSynchronize();
-  for (auto& kv : g.registry) llmi_weight_free(kv.second);
+  for (auto& kv : g.registry) llmi_weight_free(kv.second.w);
   g.registry.clear();
+  upload_pipeline_free();
+  if (g.tok_act) cudaFree(g.tok_act);
   if (g.act) llmi_act_free(g.act);
   if (g.x_dev) cudaFree(g.x_dev);
   if (g.o_dev) cudaFree(g.o_dev);
@@ -141,8 +159,50 @@ int llmi_shutdown(void) {
 
 // ------------------------------------------------------------------ weights
 
-int llmi_weight_upload(const void* host_blocks, uint32_t ggml_type, uint64_t n_cols, uint64_t n_rows,
-                       uint64_t row_begin, uint64_t row_end, llmi_weight_t* out) {
+}  // extern "C"
+
+namespace {
+
+constexpr size_t UPLOAD_SLOT_BYTES = size_t(64) << 20;
+
+int upload_pipeline_init(size_t need) {
+  const size_t cap = std::max(UPLOAD_SLOT_BYTES, round_up(need, size_t(1) << 20));
+  if (g.up_cap >= cap) return LLMI_OK;
+  if (g.up_stream) LLMI_CUDA_TRY(cudaStreamSynchronize(g.up_stream));
+  for (int i = 0; i < 2; ++i) {
+    if (g.up_pinned[i]) cudaFreeHost(g.up_pinned[i]);
+    if (g.up_dev[i]) cudaFree(g.up_dev[i]);
+    g.up_pinned[i] = g.up_dev[i] = nullptr;
+  }
+  g.up_cap = 0;
+  if (!g.up_stream) LLMI_CUDA_TRY(cudaStreamCreateWithFlags(&g.up_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    LLMI_CUDA_TRY(cudaMallocHost(reinterpret_cast<void**>(&g.up_pinned[i]), cap));
+    LLMI_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&g.up_dev[i]), cap));
+    if (!g.up_done[i]) LLMI_CUDA_TRY(cudaEventCreateWithFlags(&g.up_done[i], cudaEventDisableTiming));
+  }
+  g.up_cap = cap;
+  return LLMI_OK;
+}
+
+void upload_pipeline_free() {
+  if (g.up_stream) cudaStreamSynchronize(g.up_stream);
+  for (int i = 0; i < 2; ++i) {
+    if (g.up_pinned[i]) cudaFreeHost(g.up_pinned[i]);
+    if (g.up_dev[i]) cudaFree(g.up_dev[i]);
+    if (g.up_done[i]) cudaEventDestroy(g.up_done[i]);
+  }
+  if (g.up_stream) cudaStreamDestroy(g.up_stream);
+}
+
+}  // namespace
+
+// GGUFFile::get_tensor_data (gguf.cpp:354-356) becomes: stream this handle's raw rows through the staging pipeline
+// in chunks of whole slabs and repack each chunk on the device.  While the copy engine moves chunk i and the repack
+// kernel rewrites it, the host fills chunk i + 1 into the other pinned slot.  No allocation, no stream
+// synchronization per tensor: the planes are valid once the upload stream has drained (llmi_upload_wait).
+int llmi_weight_upload_async(const void* host_blocks, uint32_t ggml_type, uint64_t n_cols, uint64_t n_rows,
+                             uint64_t row_begin, uint64_t row_end, llmi_weight_t* out) {
   LLMI_NEED_INIT();
   if (!host_blocks || !out) return llmi_fail(LLMI_ERR_ARG, "llmi_weight_upload: null pointer");
   if (!supported(ggml_type))
@@ -171,23 +231,46 @@ int llmi_weight_upload(const void* host_blocks, uint32_t ggml_type, uint64_t n_c
   w->p_q = w->base + reinterpret_cast<size_t>(w->p_q);
   w->p_d = w->base + reinterpret_cast<size_t>(w->p_d);
   w->p_x = w->base + reinterpret_cast<size_t>(w->p_x);
-  // stage the raw rows of this shard, repack on the device, drop the staging copy
-  const size_t raw_bytes = size_t(w->n_local) * rb;
-  uint8_t* raw = nullptr;
-  e = cudaMalloc(&raw, raw_bytes);
-  if (e == cudaSuccess)
-    e = cudaMemcpyAsync(raw, static_cast<const uint8_t*>(host_blocks) + size_t(row_begin) * rb, raw_bytes,
-                        cudaMemcpyHostToDevice, g.stream);
-  if (e == cudaSuccess) e = llmi_launch_repack(*w, raw, g.stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
-  if (raw) cudaFree(raw);
-  if (e != cudaSuccess) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  int rc = upload_pipeline_init(size_t(rb) * LLMI_SLAB);
+  const uint8_t* src = static_cast<const uint8_t*>(host_blocks) + size_t(row_begin) * rb;
+  const uint64_t slabs_per_chunk = std::max<uint64_t>(1, g.up_cap / (rb * LLMI_SLAB));
+  for (uint64_t s0 = 0; rc == LLMI_OK && s0 < w->n_slabs; s0 += slabs_per_chunk) {
+    const uint64_t n_sl = std::min<uint64_t>(slabs_per_chunk, w->n_slabs - s0);
+    const uint64_t r0 = s0 * LLMI_SLAB, r1 = std::min<uint64_t>(w->n_local, (s0 + n_sl) * LLMI_SLAB);
+    const size_t bytes = size_t(r1 - r0) * rb;
+    const int slot = g.up_next;
+    g.up_next ^= 1;
+    e = cudaEventSynchronize(g.up_done[slot]);  // the slot's previous chunk has been copied AND repacked
+    if (e == cudaSuccess) {
+      memcpy(g.up_pinned[slot], src + size_t(r0) * rb, bytes);
+      e = cudaMemcpyAsync(g.up_dev[slot], g.up_pinned[slot], bytes, cudaMemcpyHostToDevice, g.up_stream);
+    }
+    if (e == cudaSuccess) e = llmi_launch_repack_slabs(*w, g.up_dev[slot], s0, n_sl, g.up_stream);
+    if (e == cudaSuccess) e = cudaEventRecord(g.up_done[slot], g.up_stream);
+    if (e != cudaSuccess) rc = llmi_cuda_fail(e, "weight upload/repack");
+  }
+  if (rc != LLMI_OK) {
+    cudaStreamSynchronize(g.up_stream);
     cudaFree(w->base);
     delete w;
-    return llmi_cuda_fail(e, "weight upload/repack");
+    return rc;
   }
   *out = w;
   return LLMI_OK;
+}
+
+int llmi_upload_wait() {
+  if (g.up_stream) LLMI_CUDA_TRY(cudaStreamSynchronize(g.up_stream));
+  return LLMI_OK;
+}
+
+extern "C" {
+
+int llmi_weight_upload(const void* host_blocks, uint32_t ggml_type, uint64_t n_cols, uint64_t n_rows,
+                       uint64_t row_begin, uint64_t row_end, llmi_weight_t* out) {
+  const int rc = llmi_weight_upload_async(host_blocks, ggml_type, n_cols, n_rows, row_begin, row_end, out);
+  return rc == LLMI_OK ? llmi_upload_wait() : rc;
 }
 
 int llmi_weight_free(llmi_weight_t w) {
@@ -209,25 +292,55 @@ int llmi_weight_dims(llmi_weight_t w, uint32_t* t, uint64_t* k, uint64_t* n, uin
 
 uint64_t llmi_weight_device_bytes(llmi_weight_t w) { return w ? w->bytes : 0; }
 
+namespace {
+// Cheap content fingerprint of a host tensor: length, first and last KB and 64 samples in between (FNV-1a).  The
+// registry is keyed by host ADDRESS (what an unmodified model.cpp hands to mat_vec_mul); if a GGUF image or a
+// std::vector is freed and another one of the same shape lands at the same address, the address matches but the
+// bytes do not — the stale device copy must not be used.
+uint64_t fingerprint(const uint8_t* p, uint64_t bytes) {
+  uint64_t h = 1469598103934665603ull ^ bytes;
+  auto eat = [&](const uint8_t* q, uint64_t n) {
+    for (uint64_t i = 0; i < n; ++i) h = (h ^ q[i]) * 1099511628211ull;
+  };
+  const uint64_t edge = std::min<uint64_t>(bytes, 1024);
+  eat(p, edge);
+  if (bytes > edge) eat(p + bytes - edge, edge);
+  if (bytes > 4096)
+    for (uint64_t i = 1; i <= 64; ++i) eat(p + (bytes / 65) * i, 16);
+  return h;
+}
+}  // namespace
+
 int llmi_registry_get(const void* host_blocks, uint32_t t, uint64_t k, uint64_t n, llmi_weight_t* out) {
   LLMI_NEED_INIT();
-  if (!out) return llmi_fail(LLMI_ERR_ARG, "llmi_registry_get: null out");
+  if (!out || !host_blocks) return llmi_fail(LLMI_ERR_ARG, "llmi_registry_get: null pointer");
+  const uint64_t bytes = llmi_row_bytes(t, k) * n;
+  const uint64_t fp = fingerprint(static_cast<const uint8_t*>(host_blocks), bytes);
   auto key = std::make_tuple(host_blocks, t, k, n);
-  auto it = g.registry.find(key);
-  if (it != g.registry.end()) {
-    *out = it->second;
-    return LLMI_OK;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g.registry.find(key);
+    if (it != g.registry.end()) {
+      if (it->second.fp == fp) {
+        *out = it->second.w;
+        return LLMI_OK;
+      }
+      llmi_weight_free(it->second.w);  // same address, other bytes: the host buffer was recycled
+      g.registry.erase(it);
+    }
   }
   llmi_weight_t w = nullptr;
   const int rc = llmi_weight_upload(host_blocks, t, k, n, 0, n, &w);
   if (rc != LLMI_OK) return rc;
-  g.registry[key] = w;
+  std::lock_guard<std::mutex> lk(g_mu);
+  g.registry[key] = Context::RegEntry{w, fp};
   *out = w;
   return LLMI_OK;
 }
 
 int llmi_registry_clear(void) {
-  for (auto& kv : g.registry) llmi_weight_free(kv.second);
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (auto& kv : g.registry) llmi_weight_free(kv.second.w);
   g.registry.clear();
   return LLMI_OK;
 }

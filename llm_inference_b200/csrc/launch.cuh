@@ -101,10 +101,13 @@ __device__ __forceinline__ void ll_store(uint2* p, uint32_t bits, uint32_t tag) 
 // persistent decode kernel has dozens of wait sites whose code must stay small (instruction cache).
 static __device__ __noinline__ uint32_t ll_wait_slow(const uint2* p, uint32_t tag, uint32_t* err) {
   uint32_t v, f;
+  unsigned long long limit_ns = 4000000000ull;  // err[1]: the limit in milliseconds (LLMI_EXCHANGE_TIMEOUT_MS at load)
   if (err) {  // an earlier wait already timed out: the run is lost, drain quickly
-    uint32_t dead;
+    uint32_t dead, ms;
     asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(dead) : "l"(err) : "memory");
     if (dead) return 0;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(ms) : "l"(err + 1) : "memory");
+    if (ms) limit_ns = (unsigned long long)ms * 1000000ull;
   }
   unsigned long long t0;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
@@ -114,7 +117,7 @@ static __device__ __noinline__ uint32_t ll_wait_slow(const uint2* p, uint32_t ta
     if ((spins & 1023u) == 0) {
       unsigned long long t1;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      if (t1 - t0 > 4000000000ull) {
+      if (t1 - t0 > limit_ns) {
         if (err) *err = 1;
         return 0;
       }

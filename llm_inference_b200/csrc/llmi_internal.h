@@ -141,6 +141,13 @@ int llmi_cuda_fail(cudaError_t e, const char* what);
 // launchers implemented in the .cu files -------------------------------------
 // repack.cu: raw (reference layout, rows [0,n_local)) -> planes of w
 cudaError_t llmi_launch_repack(const llmi_weight_s& w, const uint8_t* raw_dev, cudaStream_t s);
+cudaError_t llmi_launch_repack_slabs(const llmi_weight_s& w, const uint8_t* raw_chunk, uint64_t slab0, uint64_t n_sl,
+                                     cudaStream_t s);
+// capi.cu: llmi_weight_upload without the final wait (model load uploads hundreds of matrices back to back through
+// the staging pipeline and waits once, llmi_upload_wait)
+int llmi_weight_upload_async(const void* host_blocks, uint32_t ggml_type, uint64_t n_cols, uint64_t n_rows,
+                             uint64_t row_begin, uint64_t row_end, llmi_weight_t* out);
+int llmi_upload_wait();
 size_t llmi_plan_planes(llmi_weight_s& w);  // fills nb/n_slabs, returns total bytes, sets plane offsets relative to 0
 
 // quantize.cu

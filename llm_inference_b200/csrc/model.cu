@@ -136,7 +136,7 @@ int upload_matrix(llmi_model_s* m, const llmi::GgufTensor* t, uint64_t k, uint64
   // ops.cpp:439-448 lifted to devices)
   uint64_t rb = 0, re = n;
   M_RC(llmi_shard_range(n, m->world, m->rank, &rb, &re));
-  M_RC(llmi_weight_upload(t->data, t->type, k, n, rb, re, out));
+  M_RC(llmi_weight_upload_async(t->data, t->type, k, n, rb, re, out));  // one wait for all of them: load_impl
   m->weight_bytes += llmi_row_bytes(t->type, k) * (re - rb);
   return LLMI_OK;
 }
@@ -770,6 +770,9 @@ int load_impl(llmi_model_s* m, const uint8_t* image, uint64_t size, uint32_t t_m
     return llmi_fail(LLMI_ERR_SIZE, "llmi_model_load: head_dim must be a multiple of 64 and n_head a multiple of n_head_kv");
   if (kv_f(g, a + ".attention.max_alibi_bias", 0.0) > 0.0)
     return llmi_fail(LLMI_ERR_TYPE, "llmi_model_load: ALiBi is not supported");
+  if (m->E > 6144 || m->E % 32)
+    return llmi_fail(LLMI_ERR_SIZE, "llmi_model_load: embedding_length must be a multiple of 32 and at most 6144 (the "
+                                    "norm stage holds 6 elements per thread of a 1024-thread CTA)");
   m->attn_scale = 1.0f / std::sqrt(float(m->D));  // model.cpp:117
   m->attn_softcap = float(kv_f(g, a + ".attention.logit_softcapping", 0.0));
   m->final_softcap = float(kv_f(g, a + ".attention.final_logit_softcapping", 0.0));  // key as in model.cpp:142
@@ -814,6 +817,7 @@ int load_impl(llmi_model_s* m, const uint8_t* image, uint64_t size, uint32_t t_m
     M_RC(upload_matrix(m, T("ffn_up"), E, F, &w.up, "ffn_up"));
     M_RC(upload_matrix(m, T("ffn_down"), F, E, &w.down, "ffn_down"));
   }
+  M_RC(llmi_upload_wait());  // every matrix has gone through the staging pipeline and its repack kernel
   const size_t mx = std::max<size_t>({E, F, HD});
   m->batch = 256;  // >= 128 tokens per batch go through the tensor-core mat-vec (gemv.cu launch_tokens)
   if (const char* e = getenv("LLMI_PREFILL_BATCH")) m->batch = uint32_t(std::max(1, atoi(e)));
@@ -863,6 +867,11 @@ int load_impl(llmi_model_s* m, const uint8_t* image, uint64_t size, uint32_t t_m
     M_TRY(cudaMemcpy(m->d_epoch, &one, 4, cudaMemcpyHostToDevice));
     M_TRY(cudaMemset(m->d_llerr, 0, 16));
     M_TRY(cudaMemset(m->d_done, 0, 16));
+    {  // word 1 of the error flag: how long a consumer waits for exchanged rows before it gives up (launch.cuh)
+      uint32_t ms = 4000;
+      if (const char* e = getenv("LLMI_EXCHANGE_TIMEOUT_MS")) ms = uint32_t(std::max(1, atoi(e)));
+      M_TRY(cudaMemcpy(m->d_llerr + 1, &ms, 4, cudaMemcpyHostToDevice));
+    }
     m->ll.rank = uint32_t(rank);
     m->ll.tag.epoch = m->d_epoch;
     m->ll.tag.mul = 4 * m->L + 4;
@@ -892,6 +901,10 @@ int load_impl(llmi_model_s* m, const uint8_t* image, uint64_t size, uint32_t t_m
   M_TRY(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
   M_TRY(cudaEventCreate(&m->ev0));
   M_TRY(cudaEventCreate(&m->ev1));
+  if (llmi_attention_smem(t_max, m->D) == 0)
+    return llmi_fail(LLMI_ERR_SIZE, "llmi_model_load: max_positions " + std::to_string(t_max) + " is too large: the attention "
+                                    "stage keeps 17 bytes per position in shared memory next to its K/V tiles (limit "
+                                    "about 9500 positions)");
   M_TRY(llmi_attention_init(t_max, m->D));
   M_RC(dev_alloc(m, (void**)&m->rope_swa, size_t(t_max) * (m->D / 2) * sizeof(float2)));
   M_RC(dev_alloc(m, (void**)&m->rope_global, size_t(t_max) * (m->D / 2) * sizeof(float2)));
@@ -902,7 +915,7 @@ int load_impl(llmi_model_s* m, const uint8_t* image, uint64_t size, uint32_t t_m
   return LLMI_OK;
 }
 
-int ensure_decode_graph(llmi_model_s* m) {
+int ensure_decode_graph(llmi_model_s* m, int pos) {
   if (m->decode_graph) return LLMI_OK;
   // warm-up run creates every lazily-allocated activation buffer outside capture
   const int32_t zero[4] = {0, 0, 0, 0};
@@ -910,6 +923,9 @@ int ensure_decode_graph(llmi_model_s* m) {
   M_TRY(cudaMemcpy(&saved_pos, m->d_pos, 4, cudaMemcpyDeviceToHost));
   M_TRY(cudaMemcpy(&saved_cnt, m->d_gen_count, 4, cudaMemcpyDeviceToHost));
   M_TRY(cudaMemcpy(m->d_tok, zero, 4, cudaMemcpyHostToDevice));
+  // warm up at the caller's (validated) position: its K/V row is the one the first real step rewrites anyway, whereas
+  // the device counter may sit at t_max after a forward that filled the cache (row t_max is out of bounds)
+  M_TRY(cudaMemcpy(m->d_pos, &pos, 4, cudaMemcpyHostToDevice));
   M_RC(run_step(m, m->d_tok, true, true));
   M_TRY(cudaStreamSynchronize(m->stream));
   M_TRY(cudaMemcpy(m->d_pos, &saved_pos, 4, cudaMemcpyHostToDevice));
@@ -1030,7 +1046,7 @@ int llmi_model_comm_connect(llmi_model_t m, const void* handles /* world x 64 by
 int llmi_model_comm_reset(llmi_model_t m) {
   if (!m) return llmi_fail(LLMI_ERR_ARG, "llmi_model_comm_reset: null model");
   M_TRY(cudaStreamSynchronize(m->stream));
-  M_TRY(cudaMemset(m->d_llerr, 0, 16));
+  M_TRY(cudaMemset(m->d_llerr, 0, 4));  // (word 1 holds the time limit)
   M_TRY(cudaMemset(m->d_done, 0, 16));
   M_TRY(cudaMemset(m->d_key, 0, 16));
   if (m->use_mega) {  // the arrival counters restart with the step count (identically on every rank)
@@ -1121,7 +1137,7 @@ int llmi_model_decode_greedy(llmi_model_t m, int32_t first_token, int pos, int n
     m->launches_per_step = 1;
     return check_exchange(m, "llmi_model_decode_greedy");
   }
-  M_RC(ensure_decode_graph(m));
+  M_RC(ensure_decode_graph(m, pos));
   const int32_t zero = 0;
   M_TRY(cudaMemcpyAsync(m->d_tok, &first_token, 4, cudaMemcpyHostToDevice, s));
   M_TRY(cudaMemcpyAsync(m->d_pos, &pos, 4, cudaMemcpyHostToDevice, s));

@@ -42,10 +42,12 @@ struct RepackArgs {
   uint8_t *q, *d, *x;
 };
 
-__global__ void repack_kernel(RepackArgs a, const uint8_t* __restrict__ raw) {
-  const uint64_t cell = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
-  const uint64_t n_cells = a.n_slabs * a.nb * LLMI_SLAB;
-  if (cell >= n_cells) return;
+// cells [cell0, cell0 + n_cells) of the planes = a range of whole slabs; `raw` is the address local row 0 WOULD have
+// (the caller subtracts the rows in front of the staged chunk)
+__global__ void repack_kernel(RepackArgs a, const uint8_t* __restrict__ raw, uint64_t cell0, uint64_t n_cells) {
+  const uint64_t idx = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+  if (idx >= n_cells) return;
+  const uint64_t cell = cell0 + idx;
   const int r = int(cell % LLMI_SLAB);
   const uint64_t su = cell / LLMI_SLAB;  // s*nb + u
   const uint64_t u = su % a.nb, s = su / a.nb;
@@ -154,11 +156,20 @@ size_t llmi_plan_planes(llmi_weight_s& w) {
 }
 
 cudaError_t llmi_launch_repack(const llmi_weight_s& w, const uint8_t* raw_dev, cudaStream_t s) {
+  return llmi_launch_repack_slabs(w, raw_dev, 0, w.n_slabs, s);
+}
+
+// Slabs [slab0, slab0 + n_sl) only; raw_chunk holds the raw rows of exactly those slabs (upload pipeline, capi.cu).
+cudaError_t llmi_launch_repack_slabs(const llmi_weight_s& w, const uint8_t* raw_chunk, uint64_t slab0, uint64_t n_sl,
+                                     cudaStream_t s) {
   RepackArgs a{w.type, w.n_local, w.n_slabs, w.nb, w.n_cols, w.p_q, w.p_d, w.p_x};
-  const uint64_t cells = w.n_slabs * w.nb * LLMI_SLAB;
+  const uint64_t cells = n_sl * w.nb * LLMI_SLAB;
   if (cells == 0) return cudaSuccess;
+  const uint64_t row_bytes = llmi_row_bytes(w.type, w.n_cols);
+  const uint8_t* vraw = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(raw_chunk) -
+                                                         uintptr_t(slab0) * LLMI_SLAB * row_bytes);
   const int threads = 256;
   const uint64_t blocks = (cells + threads - 1) / threads;
-  repack_kernel<<<dim3((unsigned)blocks), threads, 0, s>>>(a, raw_dev);
+  repack_kernel<<<dim3((unsigned)blocks), threads, 0, s>>>(a, vraw, slab0 * w.nb * LLMI_SLAB, cells);
   return cudaGetLastError();
 }
