@@ -5,6 +5,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <tuple>
 #include <vector>
 
@@ -185,6 +186,25 @@ int upload_pipeline_init(size_t need) {
   return LLMI_OK;
 }
 
+// host copy into the pinned slot on a few threads: one thread moves ~4 GB/s out of a page-cache mapping (page faults
+// included), which would make the CPU, not PCIe, the bound of a 17 GB load
+void parallel_copy(uint8_t* dst, const uint8_t* src, size_t bytes) {
+  constexpr size_t MIN_PER_THREAD = size_t(4) << 20;
+  unsigned n = std::min<unsigned>(8, std::max(1u, std::thread::hardware_concurrency() / 2));
+  n = unsigned(std::min<size_t>(n, std::max<size_t>(1, bytes / MIN_PER_THREAD)));
+  if (n <= 1) {
+    memcpy(dst, src, bytes);
+    return;
+  }
+  std::vector<std::thread> th;
+  const size_t per = (bytes / n + 4095) & ~size_t(4095);
+  for (unsigned i = 0; i < n; ++i) {
+    const size_t b0 = std::min(bytes, per * i), b1 = std::min(bytes, per * (i + 1));
+    if (b1 > b0) th.emplace_back([=] { memcpy(dst + b0, src + b0, b1 - b0); });
+  }
+  for (auto& t : th) t.join();
+}
+
 void upload_pipeline_free() {
   if (g.up_stream) cudaStreamSynchronize(g.up_stream);
   for (int i = 0; i < 2; ++i) {
@@ -243,7 +263,7 @@ int llmi_weight_upload_async(const void* host_blocks, uint32_t ggml_type, uint64
     g.up_next ^= 1;
     e = cudaEventSynchronize(g.up_done[slot]);  // the slot's previous chunk has been copied AND repacked
     if (e == cudaSuccess) {
-      memcpy(g.up_pinned[slot], src + size_t(r0) * rb, bytes);
+      parallel_copy(g.up_pinned[slot], src + size_t(r0) * rb, bytes);
       e = cudaMemcpyAsync(g.up_dev[slot], g.up_pinned[slot], bytes, cudaMemcpyHostToDevice, g.up_stream);
     }
     if (e == cudaSuccess) e = llmi_launch_repack_slabs(*w, g.up_dev[slot], s0, n_sl, g.up_stream);

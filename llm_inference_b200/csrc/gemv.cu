@@ -32,6 +32,7 @@
 #include "llmi_internal.h"
 
 #include "gemv_bodies.cuh"
+#include "glue_device.cuh"  // geglu(), the warp quantizers
 
 namespace {
 
@@ -88,6 +89,9 @@ __device__ __forceinline__ void stage_activation(const GemvArgs& a, uint8_t* sm_
 
 // PUSH: row-sharded model — the rows go, flagged, into every rank's exchange buffer instead of `out` (its own
 // instantiation: the peer table and the tag would cost the single-GPU kernel registers, i.e. resident warps).
+// (Two items in flight per warp — 8 instead of 4 128-bit loads per lane — were measured in round 2 and are slower on
+// every shape but one: 27b gate 14.3 -> 16.0 us, 4b gate 4.7 -> 5.7 us, profiles/r02_sweep_unroll.txt.  Occupancy, not
+// per-warp depth, is what feeds HBM here.)
 template <class B, int W, bool PUSH>
 __global__ void __launch_bounds__(W * 32) gemv_slab_kernel(const GemvBatch batch) {
   extern __shared__ __align__(128) uint8_t sm_act[];  // [act_bytes][S * chunks * 8 floats]
@@ -169,6 +173,87 @@ __global__ void __launch_bounds__(W * 32) gemv_slab_kernel(const GemvBatch batch
 #undef SLOT
 }
 
+
+// ------------------------------------------------------------------ L2 prefetch
+// The first `lines` 128-byte lines of up to 6 plane ranges into L2.  Launched on a side stream while a glue kernel
+// (attention, norm, GEGLU: a handful of CTAs, no HBM traffic to speak of) holds the main stream, so that the HBM
+// pipe works through the gap and the next mat-vec finds the front of its weights in L2 (model.cu run_step).
+struct PrefetchArgs {
+  const uint8_t* p[6];
+  uint32_t lines[6];
+  int n;
+};
+__global__ void l2_prefetch_kernel(const PrefetchArgs a) {
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  for (int i = 0; i < a.n; ++i)
+    for (uint32_t l = tid; l < a.lines[i]; l += nth)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(a.p[i] + size_t(l) * 128) : "memory");
+}
+
+// ---------------------------------------------------------------- gate/up + GEGLU
+// ffn_gate and ffn_up (model.cpp:875, 877) consume the same vector and GEGLU (model.cpp:887-901) combines their rows
+// pairwise, so a CTA that owns the SAME slabs of both matrices can finish the stage: it owns 4 consecutive slabs =
+// 32 rows of gate and of up (items: 8 slabs x J chunks, dealt to the warps as in gemv_slab_kernel), sums every row
+// in the canonical order, and one warp then computes hidden = gelu(gate) * up for the 32 rows and
+//   * writes them as one Q8_0 block of the activation of ffn_down (32 rows = one block: the quantizer of
+//     geglu_act_kernel, bit for bit), so the GEGLU launch and its round trip of two F-vectors disappear, or
+//   * PUSH (row-sharded model): stores them flagged into every rank's exchange buffer — half the words the separate
+//     gate and up vectors took.
+template <class B, int W, bool PUSH>
+__global__ void __launch_bounds__(W * 32) gemv_geglu_kernel(const GemvBatch batch, uint8_t* act_out, uint32_t act_n) {
+  extern __shared__ __align__(128) uint8_t sm_act[];  // [act_bytes][2 matrices * 4 slabs * chunks * 8 floats]
+  __shared__ __align__(8) uint64_t bar;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = lane & 7, sub = lane >> 3;
+  const GemvArgs& ag = batch.a[0];  // gate; batch.a[1] = up (same shape, same format)
+  pdl_trigger();
+  if (threadIdx.x == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  constexpr int N = B::C;
+  const uint32_t J = ag.chunks;
+  const uint32_t slab0 = blockIdx.x * 4;
+  const uint32_t n_sl = min(4u, ag.n_slabs - slab0);
+  const uint32_t n_items = 2 * n_sl * J;  // item t: matrix t / (n_sl * J), slab, chunk
+  float* part = reinterpret_cast<float*>(sm_act + ag.act_bytes);
+  bool waited = false;
+#pragma unroll 1
+  for (uint32_t t = warp; t < n_items; t += W) {
+    const uint32_t mi = t / (n_sl * J), rem = t - mi * (n_sl * J), sl = rem / J, j = rem - sl * J;
+    const GemvArgs& a = batch.a[mi];
+    FragSet<B, N> f;
+    load_item<B, N>(f, a, slab0 + sl, j, r, sub);  // weights: independent of the predecessor kernel
+    if (!waited) {
+      stage_activation(ag, sm_act, &bar);
+      waited = true;
+    }
+    const float v = compute_item<B, N>(f, a, sm_act, j, sub);
+    if (lane < LLMI_SLAB) part[t * LLMI_SLAB + lane] = v;
+  }
+  if (!waited) stage_activation(ag, sm_act, &bar);
+  __syncthreads();
+  if (warp != 0) return;
+  const uint32_t sl = lane >> 3, rr = lane & 7;
+  const uint32_t row = (slab0 + sl) * LLMI_SLAB + rr;
+  float hidden = 0.0f;
+  if (sl < n_sl) {
+    const float* pg = part + size_t(sl) * J * LLMI_SLAB + rr;
+    const float* pu = pg + size_t(n_sl) * J * LLMI_SLAB;
+    float g = pg[0], u = pu[0];
+    for (uint32_t j = 1; j < J; ++j) {  // canonical order
+      g += pg[j * LLMI_SLAB];
+      u += pu[j * LLMI_SLAB];
+    }
+    if (row < ag.n_local) hidden = geglu(g, u);
+  }
+  if (PUSH) {
+    const uint32_t tag = ll_tag(batch.tag);
+    if (sl < n_sl && row < ag.n_local)
+      for (uint32_t p = 0; p < batch.peers.n; ++p)
+        ll_store(batch.peers.base[p] + ag.ll_off + ag.row0 + row, __float_as_uint(hidden), tag);
+  } else {
+    warp_quantize_q8_0(hidden, blockIdx.x, act_n, act_out, lane);  // rows 32c .. 32c+31 = Q8_0 block c of ffn_down's input
+  }
+}
 
 // ------------------------------------------------------ token-batched (prefill)
 // The same work decomposition for M tokens at once: a warp loads the weights
@@ -755,7 +840,15 @@ cudaError_t optin() {
                                 MAX_DYN_SMEM)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(gemv_slab_tok_kernel<B, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 MAX_DYN_SMEM)) != cudaSuccess) return e;
-  return cudaFuncSetAttribute(gemv_slab_tok_kernel<B, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
+  if ((e = cudaFuncSetAttribute(gemv_slab_tok_kernel<B, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                MAX_DYN_SMEM)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(gemv_geglu_kernel<B, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                MAX_DYN_SMEM)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(gemv_geglu_kernel<B, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                MAX_DYN_SMEM)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(gemv_geglu_kernel<B, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                MAX_DYN_SMEM)) != cudaSuccess) return e;
+  return cudaFuncSetAttribute(gemv_geglu_kernel<B, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
 }
 
 uint32_t units_of(const llmi_weight_s& w) {
@@ -898,6 +991,96 @@ cudaError_t llmi_launch_gemv_batch(const llmi_weight_s* const* ws, float* const*
     case LLMI_Q6_K: return launch_batch<Q6_K>(args, m, s, ll);
     case LLMI_F16: return launch_batch<F16>(args, m, s, ll);
     case LLMI_BF16: return launch_batch<BF16>(args, m, s, ll);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// Bytes [offset, offset + budget) of the concatenation of up to two matrices, taken as the same fraction window of
+// each of a matrix' planes.  The CTAs of a mat-vec grid are scheduled in order — matrix by matrix, slab by slab, all
+// planes of a slab together — so this is the order in which the mat-vec will read them.
+cudaError_t llmi_launch_l2_prefetch(const llmi_weight_s* const* ws, int n, size_t offset_bytes, size_t budget_bytes,
+                                    cudaStream_t s) {
+  if (n < 1 || n > 2) return cudaErrorInvalidValue;
+  if (budget_bytes == 0) return cudaSuccess;
+  PrefetchArgs a;
+  a.n = 0;
+  uint64_t lines = 0;
+  size_t cum = 0;
+  for (int i = 0; i < n; ++i) {
+    const llmi_weight_s& w = *ws[i];
+    const size_t lo = std::max(offset_bytes, cum), hi = std::min(offset_bytes + budget_bytes, cum + w.bytes);
+    cum += w.bytes;
+    if (!w.base || hi <= lo) continue;
+    const double f0 = double(lo - (cum - w.bytes)) / double(w.bytes), f1 = double(hi - (cum - w.bytes)) / double(w.bytes);
+    const uint8_t* starts[3] = {w.p_q, w.p_d, w.p_x};
+    const uint8_t* ends[3] = {w.p_d, w.p_x, w.base + w.bytes};  // planes are laid out q, d, x in one allocation
+    for (int k = 0; k < 3; ++k) {
+      const size_t plane = size_t(ends[k] - starts[k]);
+      const size_t b0 = size_t(double(plane) * f0) & ~size_t(127), b1 = size_t(double(plane) * f1);
+      if (b1 < b0 + 128) continue;
+      a.p[a.n] = starts[k] + b0;
+      a.lines[a.n] = uint32_t((b1 - b0) / 128);
+      lines += a.lines[a.n];
+      ++a.n;
+    }
+  }
+  if (a.n == 0) return cudaSuccess;
+  const unsigned blocks = unsigned(std::min<uint64_t>((lines + 255) / 256, uint64_t(g_sm_count) * 4));
+  l2_prefetch_kernel<<<blocks, 256, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+template <class B>
+cudaError_t launch_geglu(const GemvArgs& g, const GemvArgs& u, uint8_t* act_out, uint32_t act_n, cudaStream_t s,
+                         const GemvLL* ll) {
+  GemvBatch b;
+  b.n = 2;
+  b.a[0] = g;
+  b.a[1] = u;
+  b.a[2] = g;
+  if (ll) {
+    b.peers = ll->peers;
+    b.tag = ll->tag;
+  }
+  const uint32_t ctas = (g.n_slabs + 3) / 4;
+  for (int i = 0; i < GEMV_MAX_BATCH; ++i) {
+    b.S[i] = 4;
+    b.cta_end[i] = ctas;
+  }
+  if (ctas == 0) return cudaSuccess;
+  const size_t smem = g.act_bytes + size_t(8) * g.chunks * LLMI_SLAB * 4;
+  if (smem > size_t(MAX_DYN_SMEM)) return cudaErrorInvalidValue;
+  // 8 slabs x J items per CTA: 8 warps when a warp then still gets >= 2 items, else 4
+  const bool w8 = uint64_t(8) * g.chunks >= 16;
+  if (ll) {
+    if (w8) return llmi_launch(gemv_geglu_kernel<B, 8, true>, dim3(ctas), dim3(256), smem, s, b, act_out, act_n);
+    return llmi_launch(gemv_geglu_kernel<B, 4, true>, dim3(ctas), dim3(128), smem, s, b, act_out, act_n);
+  }
+  if (w8) return llmi_launch(gemv_geglu_kernel<B, 8, false>, dim3(ctas), dim3(256), smem, s, b, act_out, act_n);
+  return llmi_launch(gemv_geglu_kernel<B, 4, false>, dim3(ctas), dim3(128), smem, s, b, act_out, act_n);
+}
+
+// ffn_gate + ffn_up + GEGLU (+ the Q8_0 quantizer of ffn_down's input) as ONE launch (gemv_geglu_kernel).  gate and up:
+// same format, same shape, same row range.  Single GPU (ll == nullptr): act_out receives the ACT_Q8_0 activation of
+// length gate.n_rows (a multiple of 32).  Row-sharded (ll): the hidden rows go, flagged, to ll->off[0] of every rank.
+cudaError_t llmi_launch_gemv_geglu(const llmi_weight_s& gate, const llmi_weight_s& up, const llmi_act_s& a, uint8_t* act_out,
+                                   cudaStream_t s, const GemvLL* ll) {
+  if (gate.type != up.type || gate.n_cols != up.n_cols || gate.n_rows != up.n_rows || gate.row_begin != up.row_begin ||
+      gate.row_end != up.row_end)
+    return cudaErrorInvalidValue;
+  if (!ll && (gate.n_rows % 32 || gate.row_begin != 0 || gate.row_end != gate.n_rows)) return cudaErrorInvalidValue;
+  if (gate.n_slabs == 0) return cudaSuccess;
+  GemvArgs g = make_args(gate, a, nullptr), u = make_args(up, a, nullptr);
+  if (ll) g.ll_off = u.ll_off = ll->off[0];
+  const uint32_t n = uint32_t(gate.n_rows);
+  switch (gate.type) {
+    case LLMI_Q4_0: return launch_geglu<Q4_0>(g, u, act_out, n, s, ll);
+    case LLMI_Q8_0: return launch_geglu<Q8_0>(g, u, act_out, n, s, ll);
+    case LLMI_Q5_0: return launch_geglu<Q5_0>(g, u, act_out, n, s, ll);
+    case LLMI_Q4_K: return launch_geglu<Q4_K>(g, u, act_out, n, s, ll);
+    case LLMI_Q6_K: return launch_geglu<Q6_K>(g, u, act_out, n, s, ll);
+    case LLMI_F16: return launch_geglu<F16>(g, u, act_out, n, s, ll);
+    case LLMI_BF16: return launch_geglu<BF16>(g, u, act_out, n, s, ll);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -167,6 +167,7 @@ struct GegluIn {
   uint32_t tag;
   uint32_t* err;
   __device__ __forceinline__ float operator()(uint32_t e) const {
+    if (ll_gate && !ll_up) return ll_waitf(ll_gate + e, tag, err);  // hidden rows already combined by their producers
     if (ll_gate) return geglu(ll_waitf(ll_gate + e, tag, err), ll_waitf(ll_up + e, tag, err));
     return geglu(gate[e], up[e]);
   }
@@ -362,7 +363,7 @@ cudaError_t llmi_launch_geglu_act(const float* gate, const float* up, uint32_t n
                                   const uint2* ll_gate, const uint2* ll_up, const LLTag* tag) {
   const uint32_t warps = kind == ACT_Q8_0 ? n / 32 : (kind == ACT_Q8_K ? n / 256 : (n + 31) / 32);
   const uint32_t blocks = (warps + 3) / 4 ? (warps + 3) / 4 : 1;
-  if (ll_gate && (n_tok != 1 || !ll_up || !tag)) return cudaErrorInvalidValue;
+  if (ll_gate && (n_tok != 1 || !tag)) return cudaErrorInvalidValue;  // ll_up == nullptr: ll_gate carries gelu(gate)*up
   return llmi_launch(geglu_act_kernel, dim3(blocks, n_tok), dim3(128), 0, s, gate, up, n, kind, buf, hidden_out,
                      act_stride, ll_gate, ll_up, tag ? *tag : LLTag());
 }

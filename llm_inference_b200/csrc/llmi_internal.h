@@ -168,6 +168,12 @@ cudaError_t llmi_launch_gemv_tokens(const llmi_weight_s* const* ws, float* const
                                     cudaStream_t s);
 cudaError_t llmi_launch_gemv_batch(const llmi_weight_s* const* ws, float* const* outs, int n, const llmi_act_s& a,
                                    cudaStream_t s, const GemvLL* ll = nullptr);  // same format, same activation, n <= 3
+// front of the weights of up to two matrices into L2 (side stream, during a glue kernel): gemv.cu l2_prefetch_kernel
+cudaError_t llmi_launch_l2_prefetch(const llmi_weight_s* const* ws, int n, size_t offset_bytes, size_t budget_bytes,
+                                    cudaStream_t s);
+// gate + up + GEGLU (+ Q8_0 quantizer of the result) in one launch: gemv.cu gemv_geglu_kernel
+cudaError_t llmi_launch_gemv_geglu(const llmi_weight_s& gate, const llmi_weight_s& up, const llmi_act_s& a, uint8_t* act_out,
+                                   cudaStream_t s, const GemvLL* ll = nullptr);
 uint32_t llmi_gemv_chunks(const llmi_weight_s& w);
 void llmi_gemv_set_shape(int warps, int slabs_per_cta);  // 0 = heuristic  // K-chunks (work items) per slab
 cudaError_t llmi_launch_gemv_argmax(const llmi_weight_s& w, const llmi_act_s& a, float* out, unsigned long long* key,

@@ -64,7 +64,18 @@ struct llmi_model_s {
   uint8_t *bact_E[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}, *bact_HD[5] = {nullptr, nullptr, nullptr, nullptr, nullptr},
           *bact_F[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   uint32_t* qbuf = nullptr;  // [batch][H][D] rotated q between the two prefill attention kernels
+  // L2 prefetch of the next mat-vec's weights on a side stream while a glue kernel holds the main stream (run_step):
+  // megabytes requested during attention / the post-attention norm / GEGLU / the post-ffw norm (LLMI_PF_MB, 0 = off)
+  cudaStream_t pf_stream = nullptr;
+  std::vector<cudaEvent_t> pf_events;
+  size_t pf_next = 0;
+  bool pf_used = false;
+  size_t pf_mb[4] = {48, 24, 24, 24};
   bool prefill_ok = true;
+  bool fuse_geglu = false;  // LLMI_FUSE_GEGLU=1: gate, up and GEGLU as one launch (gemv_geglu_kernel).  Bit-identical, one
+                            // launch fewer per layer, but measured SLOWER (1b 0.828 vs 0.765 ms/token, 27b 5.25 vs 5.02): a
+                            // CTA that owns 32 rows of both matrices walks 3-11 items per warp one after the other,
+                            // the separate grids put every item on its own warp (profiles/r02_notes.md)
   int prefill_launches = 0;
   // row-sharded model: every matrix holds the slab-aligned row range of `rank`; the vectors the
   // mat-vecs produce travel through `comm`, one flagged-exchange buffer per rank with the same layout everywhere
@@ -227,6 +238,21 @@ int run_step(llmi_model_s* m, const int32_t* tok, bool want_logits, bool want_ar
     for (uint32_t o : offs) gl.off[i++] = o;
     return &gl;
   };
+  // side-stream L2 prefetch of bytes [off, off + mb MB) of `ws`, ordered after everything launched on `s` so far
+  auto prefetch = [&](std::initializer_list<llmi_weight_t> ws, size_t off, size_t mb) -> int {
+    if (!m->pf_stream || mb == 0) return LLMI_OK;
+    const llmi_weight_s* v[2];
+    int n = 0;
+    for (llmi_weight_t w : ws)
+      if (n < 2) v[n++] = w;
+    cudaEvent_t ev = m->pf_events[m->pf_next++ % m->pf_events.size()];
+    M_TRY(cudaEventRecord(ev, s));
+    M_TRY(cudaStreamWaitEvent(m->pf_stream, ev, 0));
+    M_TRY(llmi_launch_l2_prefetch(v, n, off, mb << 20, m->pf_stream));
+    m->pf_used = true;
+    return LLMI_OK;
+  };
+  m->pf_used = false;
   for (uint32_t l = 0; l < m->L; ++l) {
     LayerW& w = m->layers[l];
     const int kq = llmi_act_kind_for(w.q->type);
@@ -259,6 +285,9 @@ int run_step(llmi_model_s* m, const int32_t* tok, bool want_logits, bool want_ar
       aa.act_kind = ko;
       aa.act_buf = ko_buf;
     }
+    // while attention runs (H CTAs, no HBM traffic to speak of): attn_output, then the front of gate/up
+    M_RC(prefetch({w.o}, 0, m->pf_mb[0]));
+    if ((w.o->bytes >> 20) < m->pf_mb[0]) M_RC(prefetch({w.gate, w.up}, 0, m->pf_mb[0] - (w.o->bytes >> 20)));
     M_TRY(llmi_launch_attention(aa, s));
     m->launches_per_step++;
     if (!fuse_act) {
@@ -272,20 +301,39 @@ int run_step(llmi_model_s* m, const int32_t* tok, bool want_logits, bool want_ar
       na.y = m->attn_out; na.w_post = w.post_attn_norm; na.h = m->h; na.w = w.ffn_norm; na.n = E; na.eps = m->eps;
       if (sh) { na.y = nullptr; na.ll_y = m->comm + m->off_ao; na.ll_tag = m->tag(2 + 4 * l); }
       na.xn_out = m->xn; na.act_kind = kg; na.act_buf = get_act(m->act_E, kg, E)->buf;
+      {  // while the single-CTA norm runs: gate/up, continuing behind what the attention gap asked for
+        const size_t done = (w.o->bytes >> 20) < m->pf_mb[0] ? m->pf_mb[0] - (w.o->bytes >> 20) : 0;
+        M_RC(prefetch({w.gate, w.up}, done << 20, m->pf_mb[1]));
+      }
       M_TRY(llmi_launch_norm_act(na, s));
       m->launches_per_step++;
       M_RC(extra_acts(m, m->act_E, m->xn, E, kg, {w.up}));
     }
-    M_RC(gemv_group(m, {w.gate, w.up}, {m->gate, m->up}, m->act_E,
-                    push(3 + 4 * l, {m->off_gate, m->off_up})));  // model.cpp:875, 877
     const int kd = llmi_act_kind_for(w.down->type);
-    {
+    // gate, up and GEGLU as one launch (gemv_geglu_kernel): single GPU when ffn_down takes Q8_0 activations (the CTA
+    // that owns 32 rows of gate and up writes their Q8_0 block); row-sharded always (the hidden rows travel instead
+    // of the gate and the up rows: half the exchange, and the quantizer below only gathers them)
+    const bool fuse_geglu = m->fuse_geglu && w.gate->type == w.up->type && (sh || (kd == ACT_Q8_0 && F % 32 == 0));
+    if (fuse_geglu) {
+      llmi_act_t ag = m->act_E.a[llmi_act_kind_for(w.gate->type)];
+      uint8_t* act_f = get_act(m->act_F, kd, F)->buf;
+      M_TRY(llmi_launch_gemv_geglu(*w.gate, *w.up, *ag, act_f, s, push(3 + 4 * l, {m->off_gate})));  // model.cpp:875-901
+      m->launches_per_step++;
+      if (sh) {
+        const LLTag tg = m->tag(3 + 4 * l);
+        M_TRY(llmi_launch_geglu_act(nullptr, nullptr, F, kd, act_f, nullptr, s, 1, 0, m->comm + m->off_gate, nullptr, &tg));
+        m->launches_per_step++;
+      }
+    } else {
+      M_RC(gemv_group(m, {w.gate, w.up}, {m->gate, m->up}, m->act_E,
+                      push(3 + 4 * l, {m->off_gate, m->off_up})));  // model.cpp:875, 877
       const LLTag tg = m->tag(3 + 4 * l);
+      M_RC(prefetch({w.down}, 0, m->pf_mb[2]));  // while GEGLU runs
       M_TRY(llmi_launch_geglu_act(m->gate, m->up, F, kd, get_act(m->act_F, kd, F)->buf, nullptr, s, 1, 0,
                                   sh ? m->comm + m->off_gate : nullptr, sh ? m->comm + m->off_up : nullptr,
                                   sh ? &tg : nullptr));
+      m->launches_per_step++;
     }
-    m->launches_per_step++;
     M_RC(gemv_group(m, {w.down}, {m->ffn_out}, m->act_F, push(4 + 4 * l, {m->off_fo})));  // model.cpp:909
     {
       NormArgs na;  // post-ffw norm + residual (model.cpp:915-924), then the next norm
@@ -302,9 +350,20 @@ int run_step(llmi_model_s* m, const int32_t* tok, bool want_logits, bool want_ar
           na.w = m->out_norm; na.act_kind = kl; na.act_buf = get_act(m->act_E, kl, E)->buf;
         }
       }
+      // while the single-CTA norm runs: the next layer's q/k/v (or the front of the logits matrix)
+      if (l + 1 < m->L) {
+        M_RC(prefetch({m->layers[l + 1].q, m->layers[l + 1].k}, 0, m->pf_mb[3]));
+      } else if (want_logits) {
+        M_RC(prefetch({m->embd}, 0, m->pf_mb[3]));
+      }
       M_TRY(llmi_launch_norm_act(na, s));
       m->launches_per_step++;
     }
+  }
+  if (m->pf_used) {  // join the side stream (a captured graph must end in one stream)
+    cudaEvent_t ev = m->pf_events[m->pf_next++ % m->pf_events.size()];
+    M_TRY(cudaEventRecord(ev, m->pf_stream));
+    M_TRY(cudaStreamWaitEvent(s, ev, 0));
   }
   if (want_logits) {
     if (want_argmax) {  // logits mat-vec (model.cpp:1000 / 1027) with the soft-cap + argmax epilogue
@@ -845,6 +904,7 @@ int load_impl(llmi_model_s* m, const uint8_t* image, uint64_t size, uint32_t t_m
   }
   if (m->batch < 2) m->prefill_ok = false;
   if (const char* e = getenv("LLMI_NO_PREFILL")) m->prefill_ok = m->prefill_ok && !(e[0] == '1');
+  if (const char* e = getenv("LLMI_FUSE_GEGLU")) m->fuse_geglu = e[0] == '1';
   {
     // one exchange buffer, same layout on every rank (element = {value bits, tag}): the region of the per-launch
     // path (sharded models only), then the region of the persistent decode kernel
@@ -899,6 +959,22 @@ int load_impl(llmi_model_s* m, const uint8_t* image, uint64_t size, uint32_t t_m
   M_TRY(cudaMemset(m->d_gen_count, 0, 16));
   M_TRY(cudaMallocHost((void**)&m->logits_pinned, size_t(m->V) * 4));
   M_TRY(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+  {
+    bool on = false;  // LLMI_PF_MB="attn,norm1,geglu,norm2" megabytes (e.g. 48,24,24,24) turns the side-stream prefetch on
+    if (const char* e = getenv("LLMI_PF_MB")) {
+      unsigned a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+      const int k = sscanf(e, "%u,%u,%u,%u", &a0, &a1, &a2, &a3);
+      if (k >= 1) {
+        m->pf_mb[0] = a0; m->pf_mb[1] = k > 1 ? a1 : a0; m->pf_mb[2] = k > 2 ? a2 : a0; m->pf_mb[3] = k > 3 ? a3 : a0;
+        on = m->pf_mb[0] + m->pf_mb[1] + m->pf_mb[2] + m->pf_mb[3] > 0;
+      }
+    }
+    if (on) {
+      M_TRY(cudaStreamCreateWithFlags(&m->pf_stream, cudaStreamNonBlocking));
+      m->pf_events.resize(16);
+      for (auto& ev : m->pf_events) M_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    }
+  }
   M_TRY(cudaEventCreate(&m->ev0));
   M_TRY(cudaEventCreate(&m->ev1));
   if (llmi_attention_smem(t_max, m->D) == 0)
@@ -999,6 +1075,8 @@ int llmi_model_free(llmi_model_t m) {
   for (void* p : m->ipc_opened) cudaIpcCloseMemHandle(p);
   if (m->comm) cudaFree(m->comm);
   if (m->logits_pinned) cudaFreeHost(m->logits_pinned);
+  for (cudaEvent_t ev : m->pf_events) cudaEventDestroy(ev);
+  if (m->pf_stream) cudaStreamDestroy(m->pf_stream);
   if (m->ev0) cudaEventDestroy(m->ev0);
   if (m->ev1) cudaEventDestroy(m->ev1);
   if (m->stream) cudaStreamDestroy(m->stream);

@@ -20,7 +20,8 @@ t0 = time.time()
 img = bench.build_image(wl)
 print(f"image {len(img)/1e9:.2f} GB in {time.time()-t0:.1f}s", flush=True)
 res = {}
-for mode in (["legacy", "mega"] if os.environ.get("QUICK_LEGACY", "1") == "1" else ["mega"]):
+modes = os.environ.get("QUICK_MODES", "legacy,mega" if os.environ.get("QUICK_LEGACY", "1") == "1" else "mega").split(",")
+for mode in modes:
     if mode == "legacy":
         os.environ["LLMI_DECODE"] = "legacy"
     else:
