@@ -1,5 +1,6 @@
 // C ABI of libllmi_cuda.so (include/llmi_cuda.h): context, weights, activations,
 // the host-vector tier used by the ops.h drop-in, and small device helpers.
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -132,6 +133,12 @@ int llmi_init(int device) {
   }
   g.sm_count = prop.multiProcessorCount;
   if (const char* e = getenv("LLMI_NO_PDL")) g_llmi_pdl = !(e[0] == '1');
+  if (const char* e = getenv("LLMI_GEMV_RING")) {  // "mode[,ctas_per_sm[,depth]]" (llmi_set_gemv_ring), A/B runs
+    int mode = 0, cps = 0, depth = 0;
+    sscanf(e, "%d,%d,%d", &mode, &cps, &depth);
+    if (mode >= 0 && mode <= 2 && cps >= 0 && cps <= 4 && (depth == 0 || (depth >= 2 && depth <= 4)))
+      llmi_gemv_set_ring(mode, cps, depth);
+  }
   LLMI_CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
   LLMI_CUDA_TRY(llmi_gemv_init());
   LLMI_CUDA_TRY(llmi_mega_init());
@@ -472,6 +479,13 @@ int llmi_set_gemv_shape(int warps, int slabs_per_cta) {
   if ((warps != 0 && warps != 4 && warps != 8 && warps != 16) || slabs_per_cta < 0 || slabs_per_cta > 64)
     return llmi_fail(LLMI_ERR_ARG, "llmi_set_gemv_shape: warps in {0,4,8,16}, slabs_per_cta in [0,64]");
   llmi_gemv_set_shape(warps, slabs_per_cta);
+  return LLMI_OK;
+}
+
+int llmi_set_gemv_ring(int mode, int ctas_per_sm, int depth) {
+  if (mode < 0 || mode > 2 || ctas_per_sm < 0 || ctas_per_sm > 4 || (depth != 0 && (depth < 2 || depth > 4)))
+    return llmi_fail(LLMI_ERR_ARG, "llmi_set_gemv_ring: mode in {0,1,2}, ctas_per_sm in [0,4], depth in {0,2,3,4}");
+  llmi_gemv_set_ring(mode, ctas_per_sm, depth);
   return LLMI_OK;
 }
 

@@ -26,6 +26,8 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <map>
+#include <mutex>
 #include <type_traits>
 
 #include "launch.cuh"
@@ -474,6 +476,7 @@ __global__ void toklane_reduce_kernel(const GemvBatch batch) {
 }
 
 #include "umma_prefill.cuh"
+#include "gemv_ring.cuh"
 
 // --------------------------------------------------------------- debug dump
 // One thread per (local row, block): recomputes the integer block dot with the
@@ -554,8 +557,129 @@ void pick_shape(const GemvArgs& a, uint64_t slabs_in_launch, int& W, uint32_t& S
   while (S > 1 && a.act_bytes + size_t(S) * a.chunks * LLMI_SLAB * 4 > size_t(MAX_DYN_SMEM)) --S;
 }
 
+
+// ---- persistent bulk-copy-fed kernel (gemv_ring.cuh) --------------------------------------------------------
+// g_ring_mode: 0 = heuristic (ring_wanted), 1 = never, 2 = wherever it fits.  g_ring_cps / g_ring_depth: CTAs per SM
+// and ring slots per warp (0 = default).  Results never depend on any of them.
+int g_ring_mode = 0, g_ring_cps = 0, g_ring_depth = 0;
+constexpr int RING_W = 8;
+constexpr uint32_t RING_MAX_CTAS = 148 * 4, RING_MAX_CHUNKS = 64, RING_MAX_PART_ITEMS = 768;
+constexpr size_t RING_MAX_SMEM = 112 * 1024;
+
+// Flagged scratch of the slabs split across CTAs: one buffer per stream (launches of one stream never overlap in
+// it, gemv_ring.cuh), zero between launches.  Allocated on a stream's first launch — outside graph capture: every
+// captured path is warmed up first.
+std::mutex g_fix_mu;
+std::map<cudaStream_t, uint2*> g_fix;
+cudaError_t ring_fix_for(cudaStream_t s, uint2** out) {
+  std::lock_guard<std::mutex> lk(g_fix_mu);
+  auto it = g_fix.find(s);
+  if (it != g_fix.end()) {
+    *out = it->second;
+    return cudaSuccess;
+  }
+  uint2* p = nullptr;
+  const size_t bytes = size_t(RING_MAX_CTAS) * RING_MAX_CHUNKS * LLMI_SLAB * sizeof(uint2);
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) return e;
+  if ((e = cudaMemset(p, 0, bytes)) != cudaSuccess) return e;
+  g_fix[s] = p;
+  *out = p;
+  return cudaSuccess;
+}
+
+template <class B>
+size_t ring_smem(int D, uint32_t act_bytes, uint32_t part_items) {
+  return size_t(RING_W) * D * RingGeo<B>::SLOT + ((act_bytes + 127u) & ~127u) + size_t(part_items) * LLMI_SLAB * 4;
+}
+
+// Grid and ring depth for a launch of `total` items; false: the launch does not fit this kernel.
+template <class B>
+bool ring_plan(const GemvArgs* args, int n, uint32_t& ctas, int& D, uint32_t& total, size_t& smem) {
+  uint64_t slabs = 0;
+  for (int i = 0; i < n; ++i) {
+    slabs += args[i].n_slabs;
+    if (args[i].nb != args[0].nb || args[i].act != args[0].act) return false;  // one activation, one K
+  }
+  const uint64_t t = slabs * args[0].chunks;
+  if (t == 0 || t > 0x7fffffffu || args[0].chunks > RING_MAX_CHUNKS) return false;
+  total = uint32_t(t);
+  const int cps = g_ring_cps ? g_ring_cps : 2;
+  D = g_ring_depth ? g_ring_depth : 3;
+  uint64_t c = std::min<uint64_t>(uint64_t(g_sm_count) * cps, RING_MAX_CTAS);
+  c = std::min<uint64_t>(c, (t + RING_W - 1) / RING_W);  // no CTA with fewer items than warps
+  ctas = uint32_t(std::max<uint64_t>(c, 1));
+  const uint32_t per = uint32_t((t + ctas - 1) / ctas);
+  if (per > RING_MAX_PART_ITEMS) return false;
+  smem = ring_smem<B>(D, args[0].act_bytes, per + args[0].chunks);  // + the collected chunks of a split last slab
+  return smem <= RING_MAX_SMEM;
+}
+
+// The heuristic of mode 0 (measured, profiles/r02_notes.md): the persistent kernel pays off once every warp streams
+// several items; short launches keep the many-small-CTA kernel.
+bool ring_wanted(uint32_t total, uint32_t ctas) {
+  (void)total;
+  (void)ctas;
+  return false;
+}
+
+template <class B>
+cudaError_t launch_ring(const GemvArgs* args, int n, cudaStream_t s, const GemvLL* ll, uint32_t ctas, int D, uint32_t total,
+                        size_t smem) {
+  RingBatch b;
+  b.n = n;
+  b.total = total;
+  b.part_items = uint32_t((uint64_t(total) + ctas - 1) / ctas);
+  uint32_t slabs = 0;
+  for (int i = 0; i < GEMV_MAX_BATCH; ++i) {
+    b.a[i] = args[i < n ? i : 0];
+    if (i < n) slabs += args[i].n_slabs;
+    b.slab_end[i] = slabs;
+  }
+  if (ll) {
+    b.peers = ll->peers;
+    b.tag = ll->tag;
+    for (int i = 0; i < n; ++i)
+      if (b.a[i].ll_off == LL_NONE) return cudaErrorInvalidValue;
+  }
+  cudaError_t e = ring_fix_for(s, &b.fix);
+  if (e != cudaSuccess) return e;
+  const dim3 grid(ctas), block(RING_W * 32);
+#define LLMI_RING_CASE(DD)                                                                                   \
+  case DD:                                                                                                   \
+    return ll ? llmi_launch(gemv_ring_kernel<B, RING_W, DD, true>, grid, block, smem, s, b)                  \
+              : llmi_launch(gemv_ring_kernel<B, RING_W, DD, false>, grid, block, smem, s, b)
+  switch (D) {
+    LLMI_RING_CASE(2);
+    LLMI_RING_CASE(3);
+    LLMI_RING_CASE(4);
+    default: return cudaErrorInvalidValue;
+  }
+#undef LLMI_RING_CASE
+}
+
+template <class B>
+cudaError_t ring_optin() {
+  cudaError_t e;
+#define LLMI_RING_OPT(DD, P)                                                                                        \
+  if ((e = cudaFuncSetAttribute(gemv_ring_kernel<B, RING_W, DD, P>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                int(RING_MAX_SMEM))) != cudaSuccess)                                                \
+    return e
+  LLMI_RING_OPT(2, false); LLMI_RING_OPT(3, false); LLMI_RING_OPT(4, false);
+  LLMI_RING_OPT(2, true); LLMI_RING_OPT(3, true); LLMI_RING_OPT(4, true);
+#undef LLMI_RING_OPT
+  return cudaSuccess;
+}
+
 template <class B>
 cudaError_t launch_batch(const GemvArgs* args, int n, cudaStream_t s, const GemvLL* ll) {
+  if (g_ring_mode != 1) {
+    uint32_t rc = 0, rt = 0;
+    int rd = 0;
+    size_t rs = 0;
+    if (ring_plan<B>(args, n, rc, rd, rt, rs) && (g_ring_mode == 2 || ring_wanted(rt, rc)))
+      return launch_ring<B>(args, n, s, ll, rc, rd, rt, rs);
+  }
   GemvBatch b;
   b.n = n;
   if (ll) {
@@ -877,6 +1001,12 @@ uint32_t llmi_gemv_chunks(const llmi_weight_s& w) {
   return (u + c - 1) / c;
 }
 
+void llmi_gemv_set_ring(int mode, int ctas_per_sm, int depth) {
+  g_ring_mode = mode;
+  g_ring_cps = ctas_per_sm;
+  g_ring_depth = depth;
+}
+
 void llmi_gemv_set_shape(int warps, int slabs_per_cta) {
   g_warps = warps;
   g_slabs_per_cta = slabs_per_cta;
@@ -884,6 +1014,11 @@ void llmi_gemv_set_shape(int warps, int slabs_per_cta) {
 
 // llmi_shutdown: the grow-only scratch of the token-batched launches (chunk partials, packed activations).
 void llmi_gemv_shutdown() {
+  {
+    std::lock_guard<std::mutex> lk(g_fix_mu);
+    for (auto& kv : g_fix) cudaFree(kv.second);
+    g_fix.clear();
+  }
   if (g_part) cudaFree(g_part);
   if (g_bq) cudaFree(g_bq);
   if (g_bd) cudaFree(g_bd);
@@ -921,6 +1056,13 @@ cudaError_t llmi_gemv_init() {
   if (e != cudaSuccess) return e;
   e = cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
   if (e != cudaSuccess) return e;
+  if ((e = ring_optin<Q4_0>()) != cudaSuccess) return e;
+  if ((e = ring_optin<Q8_0>()) != cudaSuccess) return e;
+  if ((e = ring_optin<Q5_0>()) != cudaSuccess) return e;
+  if ((e = ring_optin<Q4_K>()) != cudaSuccess) return e;
+  if ((e = ring_optin<Q6_K>()) != cudaSuccess) return e;
+  if ((e = ring_optin<F16>()) != cudaSuccess) return e;
+  if ((e = ring_optin<BF16>()) != cudaSuccess) return e;
   if ((e = optin<Q4_0>()) != cudaSuccess) return e;
   if ((e = optin<Q8_0>()) != cudaSuccess) return e;
   if ((e = optin<Q5_0>()) != cudaSuccess) return e;

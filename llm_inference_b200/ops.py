@@ -203,6 +203,11 @@ def set_gemv_shape(warps: int = 0, slabs_per_cta: int = 0) -> None:
     _lib.check(_lib.load().llmi_set_gemv_shape(warps, slabs_per_cta))
 
 
+def set_gemv_ring(mode: int = 0, ctas_per_sm: int = 0, depth: int = 0) -> None:
+    """Select the persistent bulk-copy-fed mat-vec kernel: 0 heuristic, 1 never, 2 wherever it fits.  Same bits."""
+    _lib.check(_lib.load().llmi_set_gemv_ring(mode, ctas_per_sm, depth))
+
+
 def device_sync() -> None:
     _lib.check(_lib.load().llmi_device_sync())
 
@@ -306,6 +311,6 @@ def registry_clear() -> None:
 __all__ = [
     "init_ops", "mat_vec_mul", "mat_vec_mul_q4_0", "mat_vec_mul_q4_k", "mat_vec_mul_q6_k", "mat_vec_mul_q8_0",
     "mat_vec_mul_q5_0", "mat_vec_mul_bf16", "mat_vec_mul_fp16", "quantize_row_q8_0", "quantize_row_q8_k",
-    "DeviceWeight", "DeviceVector", "TorchVector", "Activation", "gemv", "gemv_batch", "mat_vec_mul_dev", "block_dots", "set_gemv_shape",
+    "DeviceWeight", "DeviceVector", "TorchVector", "Activation", "gemv", "gemv_batch", "mat_vec_mul_dev", "block_dots", "set_gemv_shape", "set_gemv_ring",
     "device_sync", "registry_clear", "row_bytes",
 ]

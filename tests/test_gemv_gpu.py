@@ -31,8 +31,9 @@ def _weights(t, n, k, seed):
     return synth.random_blocks(t, n, k, seed=seed)
 
 
-def _run(ops, t, w, x, n, k, shape=(0, 0), row_range=None):
+def _run(ops, t, w, x, n, k, shape=(0, 0), row_range=None, ring=(0, 0, 0)):
     ops.set_gemv_shape(*shape)
+    ops.set_gemv_ring(*ring)
     rb, re = row_range or (0, n)
     dw = ops.DeviceWeight(w, t, k, n, rb, re)
     dx = ops.DeviceVector(k, x)
@@ -48,6 +49,7 @@ def _run(ops, t, w, x, n, k, shape=(0, 0), row_range=None):
     for h in (dw, dx, do, act):
         h.close()
     ops.set_gemv_shape(0, 0)
+    ops.set_gemv_ring(0, 0, 0)
     return o, extra
 
 
@@ -134,6 +136,50 @@ def test_result_is_independent_of_the_grid(gpu_ops, port, t, k, n):
     for shape in ((4, 4), (8, 1), (8, 3), (16, 1), (16, 7), (0, 0)):
         o, _ = _run(gpu_ops, t, w, x, n, k, shape=shape)
         assert np.array_equal(o.view(np.uint32), base.view(np.uint32)), f"shape={shape}"
+
+
+@pytest.mark.parametrize("t,k,n", [(Q4_0, 1152, 6912), (Q4_0, 6912, 1160), (Q4_0, 21504, 520), (Q8_0, 3840, 1544),
+                                   (Q4_K, 2560, 2056), (Q6_K, 2560, 1032), (F16, 1152, 3080), (Q5_0, 1152, 1032),
+                                   (BF16, 1184, 520), (Q4_0, 1184, 203), (Q4_0, 32, 8), (Q8_0, 512, 40)],
+                         ids=lambda v: str(v))
+def test_persistent_ring_kernel_is_bitwise_the_slab_kernel(gpu_ops, port, t, k, n):
+    """gemv_ring_kernel (persistent CTAs, per-warp bulk-copy rings, item-granular CTA ranges with flagged hand-over of
+    the chunk partials of split slabs) against gemv_slab_kernel: same items, same canonical order => same bits, for
+    every grid size and ring depth, including slabs split over two and over three CTAs (K = 21504: 42 chunks)."""
+    w = _weights(t, n, k, seed=11 + t + n)
+    x = np.random.default_rng(t + k).standard_normal(k).astype(np.float32)
+    base, _ = _run(gpu_ops, t, w, x, n, k, ring=(1, 0, 0))
+    _check(base, port.mat_vec_mul(t, w, x, n, k), "slab kernel")
+    for ring in ((2, 0, 0), (2, 1, 2), (2, 3, 2), (2, 4, 4), (2, 2, 3)):
+        for _ in range(2):  # twice: the hand-over words must be back to zero after a launch
+            o, _e = _run(gpu_ops, t, w, x, n, k, ring=ring)
+            assert np.array_equal(o.view(np.uint32), base.view(np.uint32)), f"ring={ring}"
+    # a row shard (ragged slab count) through the ring kernel
+    rb, re = 8 * ((n // 8) // 3), n
+    o, _e = _run(gpu_ops, t, w, x, n, k, row_range=(rb, re), ring=(2, 2, 3))
+    assert np.array_equal(o[rb:re].view(np.uint32), base[rb:re].view(np.uint32))
+
+
+def test_persistent_ring_kernel_batched_launch(gpu_ops):
+    """q/k/v as one persistent grid: CTA ranges cross the matrix boundaries."""
+    ops = gpu_ops
+    k = 2560
+    x = np.random.default_rng(9).standard_normal(k).astype(np.float32)
+    dx, act = ops.DeviceVector(k, x), ops.Activation(k)
+    for t in (Q4_0, Q4_K, Q8_0):
+        shapes = [2048, 1024, 1032]
+        dws = [ops.DeviceWeight(_weights(t, n, k, seed=n), t, k, n) for n in shapes]
+        outs = {m: [ops.DeviceVector(n, np.full(n, np.nan, np.float32)) for n in shapes] for m in (1, 2)}
+        act.prepare(dws[0], dx)
+        for m in (1, 2):
+            ops.set_gemv_ring(m, 0, 0)
+            ops.gemv_batch(dws, act, outs[m])
+        ops.set_gemv_ring(0, 0, 0)
+        ops.device_sync()
+        for a, b in zip(outs[1], outs[2]):
+            assert np.array_equal(a.get().view(np.uint32), b.get().view(np.uint32))
+        for h in dws + outs[1] + outs[2]:
+            h.close()
 
 
 def test_matvec_matches_golden_from_compiled_reference(gpu_ops, golden):

@@ -27,7 +27,7 @@ def peak_gbs() -> float:
     return json.loads(p.read_text())["hbm_gbs"] if p.exists() else 6650.0
 
 
-def time_case(t, k, n, shape, iters=20, with_quant=False):
+def time_case(t, k, n, shape, iters=20, with_quant=False, ring=(1, 0, 0)):
     wbytes = n * synth.row_bytes(t, k)
     copies = max(2, min(64, -(-2 * L2_BYTES // wbytes)))
     raw = synth.random_blocks(t, n, k, seed=1)
@@ -36,6 +36,7 @@ def time_case(t, k, n, shape, iters=20, with_quant=False):
     o = ops.DeviceVector(n)
     act = ops.Activation(k)
     ops.set_gemv_shape(*shape)
+    ops.set_gemv_ring(*ring)
     s = torch.cuda.Stream()
     with torch.cuda.stream(s):
         act.prepare(ws[0], x, s.cuda_stream)
@@ -61,6 +62,7 @@ def time_case(t, k, n, shape, iters=20, with_quant=False):
     for h in ws + [x, o, act]:
         h.close()
     ops.set_gemv_shape(0, 0)
+    ops.set_gemv_ring(0, 0, 0)
     return us, copies
 
 
@@ -69,6 +71,8 @@ def main():
     ap.add_argument("--shapes", default="0x0", help="comma list of WxS, 0x0 = heuristic")
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--with-quant", action="store_true")
+    ap.add_argument("--rings", default="", help="comma list of CPSxDEPTH for the persistent ring kernel (e.g. 2x3,3x2)")
+    ap.add_argument("--fmt", default="", help="only this format (e.g. Q4_0)")
     a = ap.parse_args()
     ops.init_ops(1, 0)
     peak = peak_gbs()
@@ -84,13 +88,16 @@ def main():
     if a.quick:
         cases = [(Q4_0, 1152, 6912), (Q4_0, 2560, 10240), (Q4_0, 10240, 2560), (Q4_0, 5376, 21504), (Q4_0, 21504, 5376),
                  (Q4_0, 5376, 4096), (F16, 1152, 262144), (Q8_0, 3840, 15360), (Q4_K, 2560, 10240), (Q6_K, 10240, 2560)]
+    variants = [("slab " + sh, tuple(int(v) for v in sh.split("x")), (1, 0, 0)) for sh in a.shapes.split(",") if sh]
+    variants += [("ring " + rg, (0, 0), (2,) + tuple(int(v) for v in rg.split("x"))) for rg in a.rings.split(",") if rg]
     for t, k, n in cases:
-        for shape in a.shapes.split(","):
-            W, S = (int(v) for v in shape.split("x"))
-            us, copies = time_case(t, k, n, (W, S), with_quant=a.with_quant)
+        if a.fmt and synth.TYPE_NAMES[t] != a.fmt:
+            continue
+        for name, shape, ring in variants:
+            us, copies = time_case(t, k, n, shape, with_quant=a.with_quant, ring=ring)
             b = synth.algorithmic_bytes(t, n, k)
             gbs = b / us * 1e-3
-            print(json.dumps({"fmt": synth.TYPE_NAMES[t], "K": k, "N": n, "shape": shape, "us": round(us, 3),
+            print(json.dumps({"fmt": synth.TYPE_NAMES[t], "K": k, "N": n, "shape": name, "us": round(us, 3),
                               "alg_MB": round(b / 1e6, 3), "GBps": round(gbs, 1),
                               "frac_of_measured_peak": round(gbs / peak, 4), "copies": copies}), flush=True)
 
