@@ -74,18 +74,26 @@ __device__ __forceinline__ unsigned long long gtime() {
 #else
 #define GEMV_STAMP(slot, i) do { } while (0)
 #endif
+#ifdef LLMI_TIMELINE
+#define TL_SLOT tl_slot
+#else
+#define TL_SLOT (-1)
+#endif
 
 // Called by every thread after its first weight loads are in flight: wait for
 // the predecessor grid (PDL), let thread 0 start the bulk copy of the activation
 // vector it produced, wait for the bytes to land.
-__device__ __forceinline__ void stage_activation(const GemvArgs& a, uint8_t* sm_act, uint64_t* bar, unsigned slot = 0) {
+__device__ __forceinline__ void stage_activation(const GemvArgs& a, uint8_t* sm_act, uint64_t* bar, unsigned slot = 0,
+                                                 int tl_slot = -1) {
   pdl_wait();
+  TL_MARK(1);
   GEMV_STAMP(slot, 1);
   if (threadIdx.x == 0) {
     mbar_expect_tx(bar, a.act_bytes);
     bulk_g2s(sm_act, a.act, a.act_bytes, bar);
   }
   mbar_wait(bar, 0);
+  TL_MARK(3);
   GEMV_STAMP(slot, 2);
 }
 
@@ -106,6 +114,7 @@ __global__ void __launch_bounds__(W * 32) gemv_slab_kernel(const GemvBatch batch
   const uint32_t S = batch.S[mi];
   const uint32_t cta = blockIdx.x - (mi ? batch.cta_end[mi - 1] : 0u);
   pdl_trigger();
+  TL_ENTER(1);
 #ifdef LLMI_GEMV_TIMING
   __shared__ unsigned slot_s;
   if (blockIdx.x == 0 && threadIdx.x == 0) slot_s = atomicAdd(&g_gemv_launch, 1u);
@@ -129,14 +138,15 @@ __global__ void __launch_bounds__(W * 32) gemv_slab_kernel(const GemvBatch batch
     FragSet<B, N> f;
     load_item<B, N>(f, a, slab0 + sl, j, r, sub);  // weights: independent of the predecessor kernel
     if (!waited) {
-      stage_activation(a, sm_act, &bar, SLOT);
+      stage_activation(a, sm_act, &bar, SLOT, TL_SLOT);
       waited = true;
     }
     const float v = compute_item<B, N>(f, a, sm_act, j, sub);
     if (lane < LLMI_SLAB) part[t * LLMI_SLAB + lane] = v;
   }
-  if (!waited) stage_activation(a, sm_act, &bar, SLOT);  // never exit with the bulk copy into our smem in flight
+  if (!waited) stage_activation(a, sm_act, &bar, SLOT, TL_SLOT);  // never exit with the bulk copy into our smem in flight
   __syncthreads();
+  TL_MARK(5);
   GEMV_STAMP(SLOT, 3);
   unsigned long long best = 0;
   const uint32_t tag = PUSH ? ll_tag(batch.tag) : 0u;  // every thread is past pdl_wait here
@@ -172,6 +182,7 @@ __global__ void __launch_bounds__(W * 32) gemv_slab_kernel(const GemvBatch batch
     if (lane == 0 && best) atomicMax(a.argmax_key, best);
   }
   GEMV_STAMP(SLOT, 4);
+  TL_MARK(2);
 #undef SLOT
 }
 
@@ -561,7 +572,7 @@ void pick_shape(const GemvArgs& a, uint64_t slabs_in_launch, int& W, uint32_t& S
 // ---- persistent bulk-copy-fed kernel (gemv_ring.cuh) --------------------------------------------------------
 // g_ring_mode: 0 = heuristic (ring_wanted), 1 = never, 2 = wherever it fits.  g_ring_cps / g_ring_depth: CTAs per SM
 // and ring slots per warp (0 = default).  Results never depend on any of them.
-int g_ring_mode = 0, g_ring_cps = 0, g_ring_depth = 0;
+int g_ring_mode = 0, g_ring_cps = 0, g_ring_depth = 0, g_ring_pf = 0;
 constexpr int RING_W = 8;
 constexpr uint32_t RING_MAX_CTAS = 148 * 4, RING_MAX_CHUNKS = 64, RING_MAX_PART_ITEMS = 768;
 constexpr size_t RING_MAX_SMEM = 112 * 1024;
@@ -630,6 +641,7 @@ cudaError_t launch_ring(const GemvArgs* args, int n, cudaStream_t s, const GemvL
   b.n = n;
   b.total = total;
   b.part_items = uint32_t((uint64_t(total) + ctas - 1) / ctas);
+  b.pf_items = uint32_t(g_ring_pf);
   uint32_t slabs = 0;
   for (int i = 0; i < GEMV_MAX_BATCH; ++i) {
     b.a[i] = args[i < n ? i : 0];
@@ -1002,6 +1014,7 @@ uint32_t llmi_gemv_chunks(const llmi_weight_s& w) {
 }
 
 void llmi_gemv_set_ring(int mode, int ctas_per_sm, int depth) {
+  if (const char* e = getenv("LLMI_RING_PF")) g_ring_pf = std::max(0, atoi(e));  // items per CTA prefetched to L2 (A/B)
   g_ring_mode = mode;
   g_ring_cps = ctas_per_sm;
   g_ring_depth = depth;
@@ -1296,6 +1309,8 @@ extern "C" int llmi_debug_umma_stamps(long long* out /*[10][160]*/) {
   return int(cudaMemcpyFromSymbol(out, g_umma_stamp, sizeof(long long) * 10 * 160));
 }
 #endif
+
+TL_EXPORT(llmi_debug_timeline_gemv)
 
 #ifdef LLMI_GEMV_TIMING
 extern "C" int llmi_debug_gemv_stamps(unsigned long long* out /*[256][6]*/, unsigned* n_launches, int reset) {

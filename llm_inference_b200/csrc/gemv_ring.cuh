@@ -129,6 +129,7 @@ struct RingBatch {
   int n;
   uint32_t total;   // work items of the launch = (slabs of all matrices) x chunks
   uint32_t part_items;  // capacity of the chunk-partial array of a CTA (items)
+  uint32_t pf_items;    // items behind the rings that every CTA sends to L2 before it waits for its predecessor
   uint2* fix;       // [gridDim.x][chunks][8] flagged chunk partials of slabs split across CTAs; all zero between launches
   LLPeers peers;
   LLTag tag;
@@ -276,6 +277,7 @@ __global__ void __launch_bounds__(W * 32) gemv_ring_kernel(const RingBatch batch
   __shared__ __align__(8) uint64_t bars[1];         // activation staging
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_trigger();
+  TL_ENTER(2);
   const GemvArgs& a0 = batch.a[0];
   const uint32_t J = a0.chunks, nb = a0.nb;
   const uint32_t smem_s = smem_u32(smem);
@@ -328,13 +330,32 @@ __global__ void __launch_bounds__(W * 32) gemv_ring_kernel(const RingBatch batch
     i_f += W;
     if (i_f < n_my) cf.template advance<W>(batch, J);
   }
+  // Still nothing here depends on the predecessor: the items BEHIND the rings go to L2 (cp.async.bulk.prefetch.L2, one
+  // instruction per plane of an item, no destination, no completion to wait for).  In the decode step the predecessor
+  // is a glue kernel with a handful of CTAs and an idle HBM pipe; what it leaves of its run time is spent here.
+  if (batch.pf_items && warp == W - 1) {
+    const uint32_t first = uint32_t(W) * D, last = min(n_my, first + batch.pf_items);
+    for (uint32_t i = first + lane; i < last; i += 32) {
+      const uint32_t g = g0 + i, S = g / J, j = g - S * J;
+      int mi = 0;
+      while (mi + 1 < batch.n && S >= batch.slab_end[mi]) ++mi;
+      const GemvArgs& a = batch.a[mi];
+      const uint32_t c0 = j * F::CELLS, nc = min(F::CELLS, nb - c0);
+      const size_t cell = size_t(S - (mi ? batch.slab_end[mi - 1] : 0u)) * nb + c0;
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.q + cell * F::QB), "r"(nc * F::QB) : "memory");
+      if (F::DB) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.d + cell * F::DB), "r"(nc * F::DB) : "memory");
+      if (F::XB) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.x + cell * F::XB), "r"(nc * F::XB) : "memory");
+    }
+  }
   // the activation vector is the predecessor's output
   pdl_wait();
+  TL_MARK(1);
   if (threadIdx.x == 0) {
     mbar_expect_tx(&bars[0], a0.act_bytes);
     bulk_g2s(sm_act, a0.act, a0.act_bytes, &bars[0]);
   }
   mbar_wait(&bars[0], 0);
+  TL_MARK(3);
   const uint32_t act_s = smem_s + act_off;
   int s = 0;
 #pragma unroll 1
@@ -360,6 +381,7 @@ __global__ void __launch_bounds__(W * 32) gemv_ring_kernel(const RingBatch batch
     s = s + 1 == D ? 0 : s + 1;
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
+  TL_MARK(4);
   // the trailing chunks of this CTA's last slab were computed by later CTAs (at the START of their sequences): every
   // missing (chunk, row) word is fetched by its own thread — one round trip for all of them — into the partials array
   const uint32_t Sa = j0 ? S0 + 1 : S0;  // first owned slab
@@ -373,6 +395,7 @@ __global__ void __launch_bounds__(W * 32) gemv_ring_kernel(const RingBatch batch
     }
   }
   __syncthreads();
+  TL_MARK(5);
   // rows of the slabs this CTA owns (first chunk in [g0, g1)): chunk partials left to right, the canonical order
   unsigned long long best = 0;
   const uint32_t tag = PUSH ? ll_tag(batch.tag) : 0u;
@@ -412,4 +435,5 @@ __global__ void __launch_bounds__(W * 32) gemv_ring_kernel(const RingBatch batch
     }
     if (lane == 0 && best) atomicMax(a0.argmax_key, best);
   }
+  TL_MARK(2);
 }

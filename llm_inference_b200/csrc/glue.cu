@@ -11,6 +11,8 @@
 
 #include <type_traits>
 
+#include <cstdlib>
+
 #include "glue.h"
 #include "launch.cuh"
 #include "quant_device.cuh"
@@ -49,6 +51,7 @@ __global__ void embed_kernel(EmbedArgs a, const int32_t* __restrict__ token, flo
 constexpr int NORM_PER = 6;
 __global__ void __launch_bounds__(1024) norm_act_kernel(NormArgs a) {
   pdl_trigger();
+  TL_ENTER(3);
   extern __shared__ float xs[];  // n floats
   __shared__ float red[32];
   const uint32_t n = a.n;
@@ -68,6 +71,7 @@ __global__ void __launch_bounds__(1024) norm_act_kernel(NormArgs a) {
     wn[k] = (ok && a.w) ? a.w[i] : 0.0f;
   }
   pdl_wait();
+  TL_MARK(1);
   const uint32_t tag = a.ll_y ? ll_tag(a.ll_tag) : 0u;
 #pragma unroll
   for (int k = 0; k < NORM_PER; ++k) {
@@ -94,7 +98,10 @@ __global__ void __launch_bounds__(1024) norm_act_kernel(NormArgs a) {
     // every thread read the epoch before block_sum's barriers: safe to open the next step's epoch now
     if (a.epoch_inc && threadIdx.x == 0) *a.epoch_inc += 1u;
   }
-  if (!a.w) return;
+  if (!a.w) {
+    TL_MARK(2);
+    return;
+  }
   float ss = 0.0f;
 #pragma unroll
   for (int k = 0; k < NORM_PER; ++k) ss += __fmul_rn(hv[k], hv[k]);
@@ -110,6 +117,163 @@ __global__ void __launch_bounds__(1024) norm_act_kernel(NormArgs a) {
   }
   __syncthreads();
   emit_act(a.act_kind, xs, n, a.act_buf);
+  TL_MARK(2);
+}
+
+// ---- the same stage on a thread-block CLUSTER of 8 CTAs (distributed shared memory) ----------------------------------
+// norm_act_kernel is ONE CTA of T = 512 / 1024 threads: on the timeline (tools/step_timeline.py) it holds the decode
+// step for 3.0 us (E = 1152) to 6.0 us (E = 5376) — issue-bound on a single SM (two reductions, IEEE divisions, the
+// quantizer: ~19k warp-instructions on one SM), 13 us of every 75 us gemma-3-27b layer.  Here the T LOGICAL threads
+// of that kernel are spread over 8 CTAs of T/8 threads: thread t still owns elements t, t + T, ..., a warp is still
+// the same 32 logical threads with the same xor-shuffle tree, and the T/32 warp sums — written by every warp into
+// the shared memory of ALL 8 CTAs (mapa + st.shared::cluster) — are still added left to right by every thread after
+// a cluster barrier.  Same partial sums, same tree, same order: bit-identical to norm_act_kernel (and to the persistent
+// kernel's norm_sum_sq).  A logical warp holds exactly one 32-element block per pass, so Q8_0 / F16 / F32 activations
+// are emitted straight from registers; Q8_K (256-element super-blocks span 8 warps) goes through the fp32 copy.
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void dsmem_store_all(float* local, float v) {  // *local = v in every CTA of the cluster
+  const uint32_t a = smem_u32(local);
+#pragma unroll
+  for (uint32_t r = 0; r < 8; ++r) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(r));
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
+  }
+}
+constexpr int NORM_CL = 8;
+template <int T>  // logical threads of norm_act_kernel: 512 or 1024
+__global__ void __launch_bounds__(T / NORM_CL) norm_act_cluster_kernel(NormArgs a) {
+  pdl_trigger();
+  TL_ENTER(3);
+  constexpr int TC = T / NORM_CL, NW = T / 32;
+  __shared__ float red1[NW], red2[NW];
+  const uint32_t n = a.n;
+  const uint32_t rank = cluster_rank(), tok = blockIdx.x / NORM_CL;
+  const uint32_t lt = rank * TC + threadIdx.x;  // logical thread
+  const int lane = threadIdx.x & 31, lwarp = int(lt >> 5);
+  {
+    const size_t off = size_t(tok) * n;
+    if (a.y) a.y += off;
+    a.h += off;
+    if (a.xn_out) a.xn_out += off;
+    if (a.act_buf) a.act_buf += size_t(tok) * a.act_stride;
+  }
+  float yv[NORM_PER], hv[NORM_PER], wp[NORM_PER], wn[NORM_PER];
+#pragma unroll
+  for (int k = 0; k < NORM_PER; ++k) {  // static inputs: under the predecessor's tail
+    const uint32_t i = lt + k * T;
+    const bool ok = i < n;
+    wp[k] = (ok && (a.y || a.ll_y) && a.w_post) ? a.w_post[i] : 0.0f;
+    wn[k] = (ok && a.w) ? a.w[i] : 0.0f;
+  }
+  cluster_arrive();  // every CTA of the cluster runs (its shared memory exists) before anyone stores into it
+  pdl_wait();
+  TL_MARK(1);
+  const uint32_t tag = a.ll_y ? ll_tag(a.ll_tag) : 0u;
+#pragma unroll
+  for (int k = 0; k < NORM_PER; ++k) {
+    const uint32_t i = lt + k * T;
+    const bool ok = i < n;
+    hv[k] = ok ? a.h[i] : 0.0f;
+    if (a.ll_y) yv[k] = ok ? ll_waitf(a.ll_y + i, tag, a.ll_tag.err) : 0.0f;
+    else yv[k] = (ok && a.y) ? a.y[i] : 0.0f;
+  }
+  if (a.pos_inc && lt == 0 && tok == 0) *a.pos_inc += int32_t(gridDim.x / NORM_CL);
+  cluster_wait();
+  TL_MARK(3);
+  if (a.y || a.ll_y) {
+    float ss = 0.0f;
+#pragma unroll
+    for (int k = 0; k < NORM_PER; ++k) ss += __fmul_rn(yv[k], yv[k]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (lane == 0) dsmem_store_all(&red1[lwarp], ss);
+    cluster_arrive();
+    cluster_wait();
+    if (__float_as_uint(yv[0]) == 0x7fc12345u) return;  // (timeline builds: makes stamp 4 wait for the loads)
+    TL_MARK(4);
+    float tot = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) tot += red1[i];
+    const float sc = rms_scale(tot, n, a.eps);
+    if (sc == 12345.678f) return;
+    TL_MARK(5);
+#pragma unroll
+    for (int k = 0; k < NORM_PER; ++k) {
+      const uint32_t i = lt + k * T;
+      const float add = a.w_post ? __fmul_rn(__fmul_rn(sc, yv[k]), wp[k]) : yv[k];
+      hv[k] = __fadd_rn(hv[k], add);
+      if (i < n) a.h[i] = hv[k];
+    }
+    if (a.epoch_inc && lt == 0) *a.epoch_inc += 1u;  // (every thread of the cluster read the epoch before the barrier)
+  }
+  if (!a.w) {
+    TL_MARK(2);
+    return;
+  }
+  float ss = 0.0f;
+#pragma unroll
+  for (int k = 0; k < NORM_PER; ++k) ss += __fmul_rn(hv[k], hv[k]);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if (lane == 0) dsmem_store_all(&red2[lwarp], ss);
+  cluster_arrive();
+  cluster_wait();
+  TL_MARK(6);
+  float tot = 0.0f;
+#pragma unroll
+  for (int i = 0; i < NW; ++i) tot += red2[i];
+  const float sc = rms_scale(tot, n, a.eps);
+  if (sc == 12345.678f) return;
+  TL_MARK(7);
+  float xv[NORM_PER];
+#pragma unroll
+  for (int k = 0; k < NORM_PER; ++k) {
+    const uint32_t i = lt + k * T;
+    xv[k] = __fmul_rn(__fmul_rn(sc, hv[k]), wn[k]);
+    if (i < n && a.xn_out) a.xn_out[i] = xv[k];
+  }
+  if (a.act_kind == ACT_Q8_0) {  // pass k of logical warp w = block k * T/32 + w (n is a multiple of 32)
+    bool live[NORM_PER];
+    uint32_t blk[NORM_PER];
+#pragma unroll
+    for (int k = 0; k < NORM_PER; ++k) {
+      live[k] = uint32_t(lwarp) * 32u + uint32_t(k) * T < n;
+      blk[k] = uint32_t(k) * NW + lwarp;
+    }
+    warp_quantize_q8_0_multi<NORM_PER>(xv, live, blk, n, a.act_buf, lane);
+  } else if (a.act_kind == ACT_F16) {
+    const uint32_t n_pad = (n + 7) & ~7u;
+#pragma unroll
+    for (int k = 0; k < NORM_PER; ++k) {
+      const uint32_t i = lt + k * T;
+      if (i < n_pad) reinterpret_cast<uint16_t*>(a.act_buf)[i] = i < n ? f2h(xv[k]) : uint16_t(0);
+    }
+  } else if (a.act_kind == ACT_F32) {
+    const uint32_t n_pad = (n + 3) & ~3u;
+#pragma unroll
+    for (int k = 0; k < NORM_PER; ++k) {
+      const uint32_t i = lt + k * T;
+      if (i < n_pad) reinterpret_cast<float*>(a.act_buf)[i] = i < n ? xv[k] : 0.0f;
+    }
+  } else if (a.act_kind == ACT_Q8_K) {  // super-blocks span 8 logical warps: through the fp32 copy (launcher: xn_out set)
+    cluster_arrive();
+    cluster_wait();  // release / acquire at cluster scope: the xn_out stores of all 8 CTAs are visible
+    const uint32_t gw = lt >> 5;
+    for (uint32_t sb = gw; sb < n / 256; sb += NW) {
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = __ldcg(a.xn_out + sb * 256 + lane * 8 + i);
+      warp_quantize_q8_k(v, sb, n, a.act_buf, lane);
+    }
+  }
+  TL_MARK(2);
 }
 
 // Generic multi-CTA quantizer of a device vector (after attention).
@@ -143,7 +307,12 @@ __global__ void act_kernel(const float* __restrict__ x, uint32_t n, int kind, ui
 template <int D, int MODE>
 __global__ void __launch_bounds__(1024) attention_kernel(AttnArgs a, uint32_t nbuf) {
   extern __shared__ __align__(128) uint8_t att_smem[];
+  TL_ENTER(4);
+#ifdef LLMI_TIMELINE
+  if (tl_slot >= 0) g_tl_attn_slot = tl_slot;
+#endif
   attention_body<D, MODE, false>(a, nbuf, blockIdx.x, blockIdx.y, att_smem, nullptr);
+  TL_MARK(2);
 }
 
 // RoPE factors for every (position, pair): ops.cpp:80-83 —
@@ -177,7 +346,9 @@ __global__ void geglu_act_kernel(const float* __restrict__ gate, const float* __
                                  uint8_t* buf, float* hidden_out, uint32_t act_stride, const uint2* ll_gate,
                                  const uint2* ll_up, LLTag lltag) {
   pdl_trigger();
+  TL_ENTER(5);
   pdl_wait();
+  TL_MARK(1);
   gate += size_t(blockIdx.y) * n;  // blockIdx.y: token of a prefill batch
   up += size_t(blockIdx.y) * n;
   const GegluIn in{gate, up, ll_gate, ll_up, ll_gate ? ll_tag(lltag) : 0u, lltag.err};
@@ -211,6 +382,7 @@ __global__ void geglu_act_kernel(const float* __restrict__ gate, const float* __
       else reinterpret_cast<float*>(buf)[i] = v;
     }
   }
+  TL_MARK(2);
 }
 
 // ------------------------------------------------------------ soft-cap + argmax
@@ -270,6 +442,8 @@ __global__ void softcap_kernel(float* logits, uint32_t n, float softcap) {
 
 }  // namespace
 
+TL_EXPORT(llmi_debug_timeline_glue)
+
 // ------------------------------------------------------------------ launchers
 
 cudaError_t llmi_launch_embed(const EmbedArgs& a, const int32_t* token, float scale, float* h, cudaStream_t s,
@@ -279,9 +453,35 @@ cudaError_t llmi_launch_embed(const EmbedArgs& a, const int32_t* token, float sc
                      ll ? *ll : LLCtx(), ll_off);
 }
 
+// LLMI_NORM_CLUSTER=0 keeps the single-CTA kernel (A/B); both produce the same bits.
+static int g_norm_cluster = -1;
 cudaError_t llmi_launch_norm_act(const NormArgs& a, cudaStream_t s) {
   const int threads = a.n >= 2048 ? 1024 : 512;
-  return llmi_launch(norm_act_kernel, dim3(a.n_tok ? a.n_tok : 1), dim3(threads), a.n * sizeof(float), s, a);
+  if (g_norm_cluster < 0) {
+    const char* e = getenv("LLMI_NORM_CLUSTER");
+    g_norm_cluster = (e && e[0] == '0') ? 0 : 1;
+  }
+  const uint32_t n_tok = a.n_tok ? a.n_tok : 1;
+  const bool kind_ok = a.act_kind != ACT_Q8_K || a.xn_out != nullptr;
+  if (g_norm_cluster && kind_ok && a.n <= uint32_t(NORM_PER * threads)) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(n_tok * NORM_CL);
+    cfg.blockDim = dim3(threads / NORM_CL);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = NORM_CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_llmi_pdl ? 2 : 1;
+    return threads == 1024 ? cudaLaunchKernelEx(&cfg, norm_act_cluster_kernel<1024>, a)
+                           : cudaLaunchKernelEx(&cfg, norm_act_cluster_kernel<512>, a);
+  }
+  return llmi_launch(norm_act_kernel, dim3(n_tok), dim3(threads), a.n * sizeof(float), s, a);
 }
 
 cudaError_t llmi_launch_act(const float* x, uint32_t n, int kind, uint8_t* buf, cudaStream_t s, uint32_t n_tok,

@@ -157,6 +157,13 @@ __device__ long long g_attn_stamp[16];
     if (blockIdx.x == 0 && threadIdx.x == 0) g_attn_stamp[i] = clock64(); \
   } while (0)
 #define ATTN_RAW(i, tid) do { if (blockIdx.x == 0 && threadIdx.x == (tid)) g_attn_stamp[i] = clock64(); } while (0)
+#elif defined(LLMI_TIMELINE)  // rough phase boundaries of CTA 0 on the step timeline (tools/step_timeline.py)
+static __device__ int g_tl_attn_slot;  // the running attention launch's record (set by its wrapper)
+#define ATTN_STAMP(i)                                                                                      \
+  do {                                                                                                     \
+    if (!MEGA && !(blockIdx.x | blockIdx.y | threadIdx.x)) g_tl[g_tl_attn_slot & 8191].t[3 + (i)] = tl_now(); \
+  } while (0)
+#define ATTN_RAW(i, tid) do { } while (0)
 #else
 #define ATTN_STAMP(i) do { } while (0)
 #define ATTN_RAW(i, tid) do { } while (0)
@@ -227,6 +234,9 @@ __device__ __forceinline__ void attention_body(AttnArgs a, const uint32_t nbuf, 
     for (uint32_t b = 0; b < nbuf; ++b) mbar_init(&bars[b], 1);
   ATTN_STAMP(0);
   if (!MEGA) pdl_wait();
+#ifdef LLMI_TIMELINE
+  if (!MEGA && !(blockIdx.x | blockIdx.y | threadIdx.x)) g_tl[g_tl_attn_slot & 8191].t[1] = tl_now();  // dev only
+#endif
   const int pos = MEGA ? mg->pos : *a.pos + int(tok), T = pos + 1;  // tok: token of a prefill batch (0 when decoding)
   a.q += size_t(tok) * a.H * D;
   a.k += size_t(tok) * a.HK * D;

@@ -59,6 +59,52 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+
+// ---- dev only (-DLLMI_TIMELINE, tools/step_timeline.py): %globaltimer stamps of CTA 0 / thread 0 of every launch:
+// entry, griddepcontrol.wait returned, last statement.  One record buffer per translation unit (no relocatable device
+// code in this build); the host merges them by time.
+#ifdef LLMI_TIMELINE
+struct TlRec {
+  unsigned long long t[10];  // 0 entry, 1 wait returned, 2 last statement, 3.. kernel-specific phase boundaries
+  unsigned kind, ctas;
+};
+static __device__ TlRec g_tl[8192];
+static __device__ unsigned g_tl_n;
+__device__ __forceinline__ unsigned long long tl_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ int tl_enter(unsigned kind) {
+  if (blockIdx.x | blockIdx.y | blockIdx.z | threadIdx.x) return -1;
+  const unsigned s = atomicAdd(&g_tl_n, 1u) & 8191u;
+  g_tl[s].kind = kind;
+  g_tl[s].ctas = gridDim.x * gridDim.y * gridDim.z;
+  g_tl[s].t[0] = tl_now();
+  for (int i = 1; i < 10; ++i) g_tl[s].t[i] = 0;
+  return int(s);
+}
+__device__ __forceinline__ void tl_mark(int slot, int i) {
+  if (slot >= 0) g_tl[slot].t[i] = tl_now();
+}
+#define TL_ENTER(kind) const int tl_slot = tl_enter(kind)
+#define TL_MARK(i) tl_mark(tl_slot, i)
+#define TL_EXPORT(name)                                                                        \
+  extern "C" int name(void* out, unsigned* n, int reset) {                                    \
+    if (out) cudaMemcpyFromSymbol(out, g_tl, sizeof(g_tl));                                    \
+    if (n) cudaMemcpyFromSymbol(n, g_tl_n, 4);                                                 \
+    if (reset) {                                                                               \
+      const unsigned z = 0;                                                                    \
+      cudaMemcpyToSymbol(g_tl_n, &z, 4);                                                       \
+    }                                                                                          \
+    return 0;                                                                                  \
+  }
+#else
+#define TL_ENTER(kind) do { } while (0)
+#define TL_MARK(i) do { } while (0)
+#define TL_EXPORT(name)
+#endif
+
 template <typename... KArgs, typename... Args>
 cudaError_t llmi_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
   cudaLaunchConfig_t cfg = {};

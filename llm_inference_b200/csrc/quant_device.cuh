@@ -32,6 +32,42 @@ __device__ __forceinline__ void warp_quantize_q8_0(float v, uint32_t b, uint32_t
         uint32_t(__half_as_ushort(__float2half_rn(d))) | (uint32_t(uint16_t(int16_t(sum))) << 16);
 }
 
+// NK blocks at once (lane = element of each): the same arithmetic with the NK shuffle chains interleaved, so the
+// warp pays the latency of one chain instead of NK.  Every lane runs every shuffle; only the stores look at live[k].
+template <int NK>
+__device__ __forceinline__ void warp_quantize_q8_0_multi(const float (&v)[NK], const bool (&live)[NK],
+                                                         const uint32_t (&b)[NK], uint32_t n, uint8_t* buf, int lane) {
+  float amax[NK];
+#pragma unroll
+  for (int k = 0; k < NK; ++k) amax[k] = fabsf(v[k]);
+#pragma unroll
+  for (int o = 16; o; o >>= 1)
+#pragma unroll
+    for (int k = 0; k < NK; ++k) amax[k] = fmaxf(amax[k], __shfl_xor_sync(0xffffffffu, amax[k], o));
+  float d[NK];
+  int q[NK], sum[NK];
+#pragma unroll
+  for (int k = 0; k < NK; ++k) {
+    d[k] = __fdiv_rn(amax[k], 127.0f);
+    const float id = d[k] != 0.0f ? __fdiv_rn(1.0f, d[k]) : 0.0f;
+    q[k] = nearest_int_fma(v[k], id);
+    sum[k] = q[k];
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1)
+#pragma unroll
+    for (int k = 0; k < NK; ++k) sum[k] += __shfl_xor_sync(0xffffffffu, sum[k], o);
+#pragma unroll
+  for (int k = 0; k < NK; ++k) {
+    if (live[k]) {
+      reinterpret_cast<int8_t*>(buf)[b[k] * 32 + lane] = (int8_t)q[k];
+      if (lane == 0)
+        reinterpret_cast<uint32_t*>(buf + n)[b[k]] =
+            uint32_t(__half_as_ushort(__float2half_rn(d[k]))) | (uint32_t(uint16_t(int16_t(sum[k]))) << 16);
+    }
+  }
+}
+
 // One warp quantizes super-block `sb` (256 values; lane holds elements
 // 8*lane .. 8*lane+7) into the ACT_Q8_K layout:
 // [n int8][n/16 int16 bsums][n/256 fp32 d].  The scale comes from the signed
