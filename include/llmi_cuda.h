@@ -135,9 +135,10 @@ int llmi_mat_vec_mul_dev(llmi_weight_t w, const float* x_dev, llmi_act_t a,
 int llmi_set_gemv_shape(int warps, int slabs_per_cta);
 /* Second tuning knob: the persistent, bulk-copy-fed form of the same mat-vec (one CTA range of (slab, K-chunk)
  * items per CTA, per-warp shared-memory rings filled by cp.async.bulk before the predecessor kernel has finished).
- * mode 0 = heuristic, 1 = never, 2 = wherever it fits; ctas_per_sm in 1..4 and depth (ring slots per warp) in 2..4,
- * 0 = default.  Bit-identical to the other form (same items, same canonical order).  Env: LLMI_GEMV_RING=mode,cps,depth. */
-int llmi_set_gemv_ring(int mode, int ctas_per_sm, int depth);
+ * mode 0 = heuristic (large Q4_0 launches), 1 = never, 2 = wherever it fits; ctas_per_sm in 1..4, depth (ring slots
+ * per warp) in 2..4 and warps per CTA (8 or 16), 0 = default (2 x 16 warps x 2 slots).  Bit-identical to the other
+ * form (same items, same canonical order).  Env: LLMI_GEMV_RING=mode,cps,depth,warps. */
+int llmi_set_gemv_ring(int mode, int ctas_per_sm, int depth, int warps);
 
 /* Token-batched mat-vec (prefill; the M >= 16 entry SURVEY §8b calls llmi_gemm_prefill): x_dev is
  * [n_tokens][n_cols] fp32, out_dev [n_tokens][n_rows] fp32 (a row-shard handle fills its own rows).  The

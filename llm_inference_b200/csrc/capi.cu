@@ -133,11 +133,11 @@ int llmi_init(int device) {
   }
   g.sm_count = prop.multiProcessorCount;
   if (const char* e = getenv("LLMI_NO_PDL")) g_llmi_pdl = !(e[0] == '1');
-  if (const char* e = getenv("LLMI_GEMV_RING")) {  // "mode[,ctas_per_sm[,depth]]" (llmi_set_gemv_ring), A/B runs
-    int mode = 0, cps = 0, depth = 0;
-    sscanf(e, "%d,%d,%d", &mode, &cps, &depth);
+  if (const char* e = getenv("LLMI_GEMV_RING")) {  // "mode[,ctas_per_sm[,depth[,warps]]]" (llmi_set_gemv_ring), A/B runs
+    int mode = 0, cps = 0, depth = 0, warps = 0;
+    sscanf(e, "%d,%d,%d,%d", &mode, &cps, &depth, &warps);
     if (mode >= 0 && mode <= 2 && cps >= 0 && cps <= 4 && (depth == 0 || (depth >= 2 && depth <= 4)))
-      llmi_gemv_set_ring(mode, cps, depth);
+      llmi_gemv_set_ring(mode, cps, depth, warps);
   }
   LLMI_CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
   LLMI_CUDA_TRY(llmi_gemv_init());
@@ -482,10 +482,11 @@ int llmi_set_gemv_shape(int warps, int slabs_per_cta) {
   return LLMI_OK;
 }
 
-int llmi_set_gemv_ring(int mode, int ctas_per_sm, int depth) {
-  if (mode < 0 || mode > 2 || ctas_per_sm < 0 || ctas_per_sm > 4 || (depth != 0 && (depth < 2 || depth > 4)))
-    return llmi_fail(LLMI_ERR_ARG, "llmi_set_gemv_ring: mode in {0,1,2}, ctas_per_sm in [0,4], depth in {0,2,3,4}");
-  llmi_gemv_set_ring(mode, ctas_per_sm, depth);
+int llmi_set_gemv_ring(int mode, int ctas_per_sm, int depth, int warps) {
+  if (mode < 0 || mode > 2 || ctas_per_sm < 0 || ctas_per_sm > 4 || (depth != 0 && (depth < 2 || depth > 4)) ||
+      (warps != 0 && warps != 8 && warps != 16))
+    return llmi_fail(LLMI_ERR_ARG, "llmi_set_gemv_ring: mode in {0,1,2}, ctas_per_sm in [0,4], depth in {0,2,3,4}, warps in {0,8,16}");
+  llmi_gemv_set_ring(mode, ctas_per_sm, depth, warps);
   return LLMI_OK;
 }
 

@@ -572,8 +572,7 @@ void pick_shape(const GemvArgs& a, uint64_t slabs_in_launch, int& W, uint32_t& S
 // ---- persistent bulk-copy-fed kernel (gemv_ring.cuh) --------------------------------------------------------
 // g_ring_mode: 0 = heuristic (ring_wanted), 1 = never, 2 = wherever it fits.  g_ring_cps / g_ring_depth: CTAs per SM
 // and ring slots per warp (0 = default).  Results never depend on any of them.
-int g_ring_mode = 0, g_ring_cps = 0, g_ring_depth = 0, g_ring_pf = 0;
-constexpr int RING_W = 8;
+int g_ring_mode = 0, g_ring_cps = 0, g_ring_depth = 0, g_ring_pf = 0, g_ring_w = 16;  // g_ring_w: warps per CTA, 8 or 16
 constexpr uint32_t RING_MAX_CTAS = 148 * 4, RING_MAX_CHUNKS = 64, RING_MAX_PART_ITEMS = 768;
 constexpr size_t RING_MAX_SMEM = 112 * 1024;
 
@@ -601,7 +600,7 @@ cudaError_t ring_fix_for(cudaStream_t s, uint2** out) {
 
 template <class B>
 size_t ring_smem(int D, uint32_t act_bytes, uint32_t part_items) {
-  return size_t(RING_W) * D * RingGeo<B>::SLOT + ((act_bytes + 127u) & ~127u) + size_t(part_items) * LLMI_SLAB * 4;
+  return size_t(g_ring_w) * D * RingGeo<B>::SLOT + ((act_bytes + 127u) & ~127u) + size_t(part_items) * LLMI_SLAB * 4;
 }
 
 // Grid and ring depth for a launch of `total` items; false: the launch does not fit this kernel.
@@ -616,9 +615,10 @@ bool ring_plan(const GemvArgs* args, int n, uint32_t& ctas, int& D, uint32_t& to
   if (t == 0 || t > 0x7fffffffu || args[0].chunks > RING_MAX_CHUNKS) return false;
   total = uint32_t(t);
   const int cps = g_ring_cps ? g_ring_cps : 2;
-  D = g_ring_depth ? g_ring_depth : 3;
+  D = g_ring_depth ? g_ring_depth : 2;
+  if (g_ring_w == 16 && D > 3) D = 3;  // instantiated: 8 warps x {2, 3, 4} slots, 16 warps x {2, 3}
   uint64_t c = std::min<uint64_t>(uint64_t(g_sm_count) * cps, RING_MAX_CTAS);
-  c = std::min<uint64_t>(c, (t + RING_W - 1) / RING_W);  // no CTA with fewer items than warps
+  c = std::min<uint64_t>(c, (t + g_ring_w - 1) / g_ring_w);  // no CTA with fewer items than warps
   ctas = uint32_t(std::max<uint64_t>(c, 1));
   const uint32_t per = uint32_t((t + ctas - 1) / ctas);
   if (per > RING_MAX_PART_ITEMS) return false;
@@ -626,12 +626,16 @@ bool ring_plan(const GemvArgs* args, int n, uint32_t& ctas, int& D, uint32_t& to
   return smem <= RING_MAX_SMEM;
 }
 
-// The heuristic of mode 0 (measured, profiles/r02_notes.md): the persistent kernel pays off once every warp streams
-// several items; short launches keep the many-small-CTA kernel.
-bool ring_wanted(uint32_t total, uint32_t ctas) {
-  (void)total;
-  (void)ctas;
-  return false;
+// The heuristic of mode 0 (measured in the decode step, profiles/r02_ab_ring_v2.txt and r02_notes.md): the persistent
+// kernel pays where its item body is the hand-scheduled one (Q4_0) and the launch streams enough bytes for the ring
+// prefill and the even item split to outweigh its longer prologue and tail — gemma-3-27b: 4.63 -> 4.29 ms per token;
+// it loses on gemma-3-1b's 0.15-9 MB launches (0.84 -> 0.93 ms) and, with the generic item body, on the k-quants.
+template <class B>
+bool ring_wanted(const GemvArgs* args, int n) {
+  if (!std::is_same<B, BodyQ4_0>::value) return false;
+  uint64_t bytes = 0;
+  for (int i = 0; i < n; ++i) bytes += uint64_t(args[i].n_slabs) * args[i].nb * (RingFmt<B>::QB + RingFmt<B>::DB + RingFmt<B>::XB);
+  return bytes >= (10ull << 20);
 }
 
 template <class B>
@@ -656,29 +660,31 @@ cudaError_t launch_ring(const GemvArgs* args, int n, cudaStream_t s, const GemvL
   }
   cudaError_t e = ring_fix_for(s, &b.fix);
   if (e != cudaSuccess) return e;
-  const dim3 grid(ctas), block(RING_W * 32);
-#define LLMI_RING_CASE(DD)                                                                                   \
-  case DD:                                                                                                   \
-    return ll ? llmi_launch(gemv_ring_kernel<B, RING_W, DD, true>, grid, block, smem, s, b)                  \
-              : llmi_launch(gemv_ring_kernel<B, RING_W, DD, false>, grid, block, smem, s, b)
-  switch (D) {
-    LLMI_RING_CASE(2);
-    LLMI_RING_CASE(3);
-    LLMI_RING_CASE(4);
-    default: return cudaErrorInvalidValue;
-  }
+  const dim3 grid(ctas), block(g_ring_w * 32);
+#define LLMI_RING_CASE(WW, DD)                                                                               \
+  if (g_ring_w == WW && D == DD)                                                                             \
+    return ll ? llmi_launch(gemv_ring_kernel<B, WW, DD, true>, grid, block, smem, s, b)                      \
+              : llmi_launch(gemv_ring_kernel<B, WW, DD, false>, grid, block, smem, s, b)
+  LLMI_RING_CASE(8, 2);
+  LLMI_RING_CASE(8, 3);
+  LLMI_RING_CASE(8, 4);
+  LLMI_RING_CASE(16, 2);
+  LLMI_RING_CASE(16, 3);
 #undef LLMI_RING_CASE
+  return cudaErrorInvalidValue;
 }
 
 template <class B>
 cudaError_t ring_optin() {
   cudaError_t e;
-#define LLMI_RING_OPT(DD, P)                                                                                        \
-  if ((e = cudaFuncSetAttribute(gemv_ring_kernel<B, RING_W, DD, P>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                int(RING_MAX_SMEM))) != cudaSuccess)                                                \
+#define LLMI_RING_OPT(WW, DD, P)                                                                                \
+  if ((e = cudaFuncSetAttribute(gemv_ring_kernel<B, WW, DD, P>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                int(RING_MAX_SMEM))) != cudaSuccess)                                            \
     return e
-  LLMI_RING_OPT(2, false); LLMI_RING_OPT(3, false); LLMI_RING_OPT(4, false);
-  LLMI_RING_OPT(2, true); LLMI_RING_OPT(3, true); LLMI_RING_OPT(4, true);
+  LLMI_RING_OPT(8, 2, false); LLMI_RING_OPT(8, 3, false); LLMI_RING_OPT(8, 4, false);
+  LLMI_RING_OPT(8, 2, true); LLMI_RING_OPT(8, 3, true); LLMI_RING_OPT(8, 4, true);
+  LLMI_RING_OPT(16, 2, false); LLMI_RING_OPT(16, 3, false);
+  LLMI_RING_OPT(16, 2, true); LLMI_RING_OPT(16, 3, true);
 #undef LLMI_RING_OPT
   return cudaSuccess;
 }
@@ -689,7 +695,7 @@ cudaError_t launch_batch(const GemvArgs* args, int n, cudaStream_t s, const Gemv
     uint32_t rc = 0, rt = 0;
     int rd = 0;
     size_t rs = 0;
-    if (ring_plan<B>(args, n, rc, rd, rt, rs) && (g_ring_mode == 2 || ring_wanted(rt, rc)))
+    if ((g_ring_mode == 2 || ring_wanted<B>(args, n)) && ring_plan<B>(args, n, rc, rd, rt, rs))
       return launch_ring<B>(args, n, s, ll, rc, rd, rt, rs);
   }
   GemvBatch b;
@@ -1013,7 +1019,8 @@ uint32_t llmi_gemv_chunks(const llmi_weight_s& w) {
   return (u + c - 1) / c;
 }
 
-void llmi_gemv_set_ring(int mode, int ctas_per_sm, int depth) {
+void llmi_gemv_set_ring(int mode, int ctas_per_sm, int depth, int warps) {
+  g_ring_w = warps == 8 ? 8 : 16;
   if (const char* e = getenv("LLMI_RING_PF")) g_ring_pf = std::max(0, atoi(e));  // items per CTA prefetched to L2 (A/B)
   g_ring_mode = mode;
   g_ring_cps = ctas_per_sm;

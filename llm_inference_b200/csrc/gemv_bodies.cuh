@@ -44,17 +44,23 @@ __device__ __forceinline__ float h2f(uint16_t h) { return __half2float(__ushort_
 
 // Q4_0 block (ops.cpp:373-396): byte j of w holds element j (low nibble) and
 // element j+16 (high nibble); xa = q8 elements 0..15, xb = 16..31.
+// The high nibbles stay in place: (w & 0xf0f0f0f0) as UNSIGNED bytes dotted with the signed q8 bytes is 16 x the
+// high-half dot, an exact multiple of 16 (no shift per word; the mat-vec kernels are issue-bound).
+__device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c) {  // unsigned x signed: no such __dp4a overload
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
 __device__ __forceinline__ int q4_0_block_dot(const uint4 w, const int4 xa, const int4 xb, const int xsum) {
-  int dp = 0;
-  dp = __dp4a(int(w.x & 0x0f0f0f0fu), xa.x, dp);
-  dp = __dp4a(int(w.y & 0x0f0f0f0fu), xa.y, dp);
-  dp = __dp4a(int(w.z & 0x0f0f0f0fu), xa.z, dp);
-  dp = __dp4a(int(w.w & 0x0f0f0f0fu), xa.w, dp);
-  dp = __dp4a(int((w.x >> 4) & 0x0f0f0f0fu), xb.x, dp);
-  dp = __dp4a(int((w.y >> 4) & 0x0f0f0f0fu), xb.y, dp);
-  dp = __dp4a(int((w.z >> 4) & 0x0f0f0f0fu), xb.z, dp);
-  dp = __dp4a(int((w.w >> 4) & 0x0f0f0f0fu), xb.w, dp);
-  return dp - 8 * xsum;  // sum (nib-8)*q == sum nib*q - 8*sum q
+  int lo = __dp4a(int(w.x & 0x0f0f0f0fu), xa.x, 0);
+  lo = __dp4a(int(w.y & 0x0f0f0f0fu), xa.y, lo);
+  lo = __dp4a(int(w.z & 0x0f0f0f0fu), xa.z, lo);
+  lo = __dp4a(int(w.w & 0x0f0f0f0fu), xa.w, lo);
+  int hi = dp4a_us(w.x & 0xf0f0f0f0u, xb.x, 0);
+  hi = dp4a_us(w.y & 0xf0f0f0f0u, xb.y, hi);
+  hi = dp4a_us(w.z & 0xf0f0f0f0u, xb.z, hi);
+  hi = dp4a_us(w.w & 0xf0f0f0f0u, xb.w, hi);
+  return lo + (hi >> 4) - 8 * xsum;  // sum (nib-8)*q == sum nib*q - 8*sum q
 }
 
 // Q8_0 block (ops.cpp:816-819)

@@ -149,12 +149,6 @@ __device__ __forceinline__ float ring_fix_take(uint2* p) {
   return __uint_as_float(v);
 }
 
-// unsigned bytes x signed bytes (there is no mixed-sign __dp4a overload)
-__device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c) {
-  int d;
-  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-  return d;
-}
 // shared-memory accesses by 32-bit shared address (no generic-address arithmetic in the item loop)
 __device__ __forceinline__ uint4 lds128(uint32_t a) {
   uint4 v;

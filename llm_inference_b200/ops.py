@@ -203,9 +203,9 @@ def set_gemv_shape(warps: int = 0, slabs_per_cta: int = 0) -> None:
     _lib.check(_lib.load().llmi_set_gemv_shape(warps, slabs_per_cta))
 
 
-def set_gemv_ring(mode: int = 0, ctas_per_sm: int = 0, depth: int = 0) -> None:
-    """Select the persistent bulk-copy-fed mat-vec kernel: 0 heuristic, 1 never, 2 wherever it fits.  Same bits."""
-    _lib.check(_lib.load().llmi_set_gemv_ring(mode, ctas_per_sm, depth))
+def set_gemv_ring(mode: int = 0, ctas_per_sm: int = 0, depth: int = 0, warps: int = 0) -> None:
+    """Select the persistent ring mat-vec kernel: 0 heuristic, 1 never, 2 wherever it fits.  Same bits."""
+    _lib.check(_lib.load().llmi_set_gemv_ring(mode, ctas_per_sm, depth, warps))
 
 
 def device_sync() -> None:

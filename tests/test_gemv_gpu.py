@@ -31,7 +31,7 @@ def _weights(t, n, k, seed):
     return synth.random_blocks(t, n, k, seed=seed)
 
 
-def _run(ops, t, w, x, n, k, shape=(0, 0), row_range=None, ring=(0, 0, 0)):
+def _run(ops, t, w, x, n, k, shape=(0, 0), row_range=None, ring=(0, 0, 0, 0)):
     ops.set_gemv_shape(*shape)
     ops.set_gemv_ring(*ring)
     rb, re = row_range or (0, n)
@@ -49,7 +49,7 @@ def _run(ops, t, w, x, n, k, shape=(0, 0), row_range=None, ring=(0, 0, 0)):
     for h in (dw, dx, do, act):
         h.close()
     ops.set_gemv_shape(0, 0)
-    ops.set_gemv_ring(0, 0, 0)
+    ops.set_gemv_ring(0, 0, 0, 0)
     return o, extra
 
 
@@ -148,15 +148,15 @@ def test_persistent_ring_kernel_is_bitwise_the_slab_kernel(gpu_ops, port, t, k, 
     every grid size and ring depth, including slabs split over two and over three CTAs (K = 21504: 42 chunks)."""
     w = _weights(t, n, k, seed=11 + t + n)
     x = np.random.default_rng(t + k).standard_normal(k).astype(np.float32)
-    base, _ = _run(gpu_ops, t, w, x, n, k, ring=(1, 0, 0))
+    base, _ = _run(gpu_ops, t, w, x, n, k, ring=(1, 0, 0, 0))
     _check(base, port.mat_vec_mul(t, w, x, n, k), "slab kernel")
-    for ring in ((2, 0, 0), (2, 1, 2), (2, 3, 2), (2, 4, 4), (2, 2, 3)):
+    for ring in ((2, 0, 0, 0), (2, 1, 2, 8), (2, 3, 2, 8), (2, 4, 4, 8), (2, 2, 3, 16), (2, 1, 2, 16)):
         for _ in range(2):  # twice: the hand-over words must be back to zero after a launch
             o, _e = _run(gpu_ops, t, w, x, n, k, ring=ring)
             assert np.array_equal(o.view(np.uint32), base.view(np.uint32)), f"ring={ring}"
     # a row shard (ragged slab count) through the ring kernel
     rb, re = 8 * ((n // 8) // 3), n
-    o, _e = _run(gpu_ops, t, w, x, n, k, row_range=(rb, re), ring=(2, 2, 3))
+    o, _e = _run(gpu_ops, t, w, x, n, k, row_range=(rb, re), ring=(2, 2, 3, 8))
     assert np.array_equal(o[rb:re].view(np.uint32), base[rb:re].view(np.uint32))
 
 
@@ -172,9 +172,9 @@ def test_persistent_ring_kernel_batched_launch(gpu_ops):
         outs = {m: [ops.DeviceVector(n, np.full(n, np.nan, np.float32)) for n in shapes] for m in (1, 2)}
         act.prepare(dws[0], dx)
         for m in (1, 2):
-            ops.set_gemv_ring(m, 0, 0)
+            ops.set_gemv_ring(m, 0, 0, 0)
             ops.gemv_batch(dws, act, outs[m])
-        ops.set_gemv_ring(0, 0, 0)
+        ops.set_gemv_ring(0, 0, 0, 0)
         ops.device_sync()
         for a, b in zip(outs[1], outs[2]):
             assert np.array_equal(a.get().view(np.uint32), b.get().view(np.uint32))

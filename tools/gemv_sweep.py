@@ -27,7 +27,7 @@ def peak_gbs() -> float:
     return json.loads(p.read_text())["hbm_gbs"] if p.exists() else 6650.0
 
 
-def time_case(t, k, n, shape, iters=20, with_quant=False, ring=(1, 0, 0)):
+def time_case(t, k, n, shape, iters=20, with_quant=False, ring=(1, 0, 0, 0)):
     wbytes = n * synth.row_bytes(t, k)
     copies = max(2, min(64, -(-2 * L2_BYTES // wbytes)))
     raw = synth.random_blocks(t, n, k, seed=1)
@@ -62,7 +62,7 @@ def time_case(t, k, n, shape, iters=20, with_quant=False, ring=(1, 0, 0)):
     for h in ws + [x, o, act]:
         h.close()
     ops.set_gemv_shape(0, 0)
-    ops.set_gemv_ring(0, 0, 0)
+    ops.set_gemv_ring(0, 0, 0, 0)
     return us, copies
 
 
@@ -71,7 +71,7 @@ def main():
     ap.add_argument("--shapes", default="0x0", help="comma list of WxS, 0x0 = heuristic")
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--with-quant", action="store_true")
-    ap.add_argument("--rings", default="", help="comma list of CPSxDEPTH for the persistent ring kernel (e.g. 2x3,3x2)")
+    ap.add_argument("--rings", default="", help="comma list of CPSxDEPTHxWARPS for the persistent ring kernel (e.g. 2x2x16,3x2x8)")
     ap.add_argument("--fmt", default="", help="only this format (e.g. Q4_0)")
     a = ap.parse_args()
     ops.init_ops(1, 0)
@@ -88,7 +88,7 @@ def main():
     if a.quick:
         cases = [(Q4_0, 1152, 6912), (Q4_0, 2560, 10240), (Q4_0, 10240, 2560), (Q4_0, 5376, 21504), (Q4_0, 21504, 5376),
                  (Q4_0, 5376, 4096), (F16, 1152, 262144), (Q8_0, 3840, 15360), (Q4_K, 2560, 10240), (Q6_K, 10240, 2560)]
-    variants = [("slab " + sh, tuple(int(v) for v in sh.split("x")), (1, 0, 0)) for sh in a.shapes.split(",") if sh]
+    variants = [("slab " + sh, tuple(int(v) for v in sh.split("x")), (1, 0, 0, 0)) for sh in a.shapes.split(",") if sh]
     variants += [("ring " + rg, (0, 0), (2,) + tuple(int(v) for v in rg.split("x"))) for rg in a.rings.split(",") if rg]
     for t, k, n in cases:
         if a.fmt and synth.TYPE_NAMES[t] != a.fmt:
