@@ -150,6 +150,13 @@ int llmi_set_gemv_ring(int mode, int ctas_per_sm, int depth, int warps);
  * the per-block fp32 scale-and-accumulate as its epilogue). */
 int llmi_gemm_tokens(llmi_weight_t w, const float* x_dev, uint32_t n_tokens, float* out_dev, llmi_stream_t stream);
 
+/* Prefill mode of llmi_gemm_tokens and of the model's prompt path.  0 (default) = exact: every (token, row) bit-identical
+ * to llmi_mat_vec_mul_dev, the parity gate.  1 = fast: batches of >= 64 tokens go through a dequantize-to-bf16
+ * tcgen05.mma (kind::f16, fp32 accumulation in tensor memory) GEMM — every format, tensor-core throughput, NOT
+ * bit-exact: |o - o_exact| <= 2e-2 * max|o_exact| per call (tests state the bar); greedy-token agreement with the exact
+ * path is reported by bench.py.  Env: LLMI_PREFILL=fast (read by llmi_init and every llmi_model_load). */
+int llmi_set_prefill_mode(int mode);
+
 /* Per-block integer dot products (must be bit-exact with the reference):
  * Q4_0/Q8_0: rows*(K/32) int32; Q4_K: rows*(K/32); Q6_K: rows*(K/128).
  * dots_host is indexed [local_row][block]. */

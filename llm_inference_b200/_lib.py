@@ -44,6 +44,7 @@ SIGNATURES = {
     "llmi_mat_vec_mul_dev": (_int, [_vp, _vp, _vp, _vp, _vp]),
     "llmi_set_gemv_shape": (_int, [_int, _int]),
     "llmi_set_gemv_ring": (_int, [_int, _int, _int, _int]),
+    "llmi_set_prefill_mode": (_int, [_int]),
     "llmi_debug_block_dots": (_int, [_vp, _vp, _vp]),
     "llmi_host_mat_vec_mul": (_int, [_vp, _vp, _u64, _vp, _u64]),
     "llmi_host_quantize_row_q8_0": (_int, [_vp, _u64, _vp]),

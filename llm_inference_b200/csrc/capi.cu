@@ -490,6 +490,12 @@ int llmi_set_gemv_ring(int mode, int ctas_per_sm, int depth, int warps) {
   return LLMI_OK;
 }
 
+int llmi_set_prefill_mode(int mode) {
+  if (mode != 0 && mode != 1) return llmi_fail(LLMI_ERR_ARG, "llmi_set_prefill_mode: 0 = exact (default), 1 = fast (bf16 tensor cores)");
+  llmi_gemv_set_prefill_fast(mode);
+  return LLMI_OK;
+}
+
 int llmi_gemv(llmi_weight_t w, llmi_act_t a, float* out, llmi_stream_t s) {
   LLMI_NEED_INIT();
   if (!w || !a || !out) return llmi_fail(LLMI_ERR_ARG, "llmi_gemv: null pointer");

@@ -23,11 +23,13 @@
 //     sums; the fp32 scale product and accumulation follow the reference's
 //     formulas (summation ORDER differs: that is the documented 1e-5 bound).
 #include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
 #include <algorithm>
 #include <map>
 #include <mutex>
+#include <string>
 #include <type_traits>
 
 #include "launch.cuh"
@@ -488,6 +490,7 @@ __global__ void toklane_reduce_kernel(const GemvBatch batch) {
 
 #include "umma_prefill.cuh"
 #include "gemv_ring.cuh"
+#include "gemm_bf16.cuh"
 
 // --------------------------------------------------------------- debug dump
 // One thread per (local row, block): recomputes the integer block dot with the
@@ -909,8 +912,86 @@ cudaError_t launch_umma(const GemvArgs* args, int n, cudaStream_t s) {
   return llmi_launch(toklane_reduce_kernel, dim3(rb, n), dim3(256), 0, s, b);
 }
 
+// ---- throughput prefill (gemm_bf16.cuh): opt-in, not the parity path ---------------------------------------------
+bool g_prefill_fast = false;  // LLMI_PREFILL=fast / llmi_set_prefill_mode(1)
+static uint8_t* g_fast_w = nullptr;  // grow-only scratch: dequantized weights / packed activations of one launch
+static uint8_t* g_fast_x = nullptr;
+static size_t g_fast_w_bytes = 0, g_fast_x_bytes = 0;
+
+template <class B>
+constexpr uint32_t body_type() {
+  return std::is_same<B, BodyQ4_0>::value   ? LLMI_Q4_0
+         : std::is_same<B, BodyQ8_0>::value ? LLMI_Q8_0
+         : std::is_same<B, BodyQ5_0>::value ? LLMI_Q5_0
+         : std::is_same<B, BodyQ4_K>::value ? LLMI_Q4_K
+         : std::is_same<B, BodyQ6_K>::value ? LLMI_Q6_K
+         : std::is_same<B, BodyHalf<false>>::value ? LLMI_F16 : LLMI_BF16;
+}
+
+// Every matrix of the batch: dequantize -> (activations packed once) -> tcgen05 bf16 GEMM.
+template <class B>
+cudaError_t launch_fast(const GemvArgs* args, int n, cudaStream_t s) {
+  const uint32_t type = body_type<B>(), K = args[0].n_cols, n_tok = args[0].n_tok;
+  const uint32_t nkb = K / fastmm::KB;
+  const uint32_t tnf = n_tok > 128 ? 256u : 128u, n_tt = (n_tok + tnf - 1) / tnf;
+  size_t w_need = 0;
+  for (int i = 0; i < n; ++i) {
+    const size_t tiles = (size_t(args[i].n_slabs) * LLMI_SLAB + fastmm::TM - 1) / fastmm::TM;
+    w_need = std::max(w_need, tiles * nkb * fastmm::A_BYTES);
+  }
+  const size_t x_need = size_t(n_tt) * nkb * tnf * fastmm::KB * 2;
+  if (w_need > g_fast_w_bytes || x_need > g_fast_x_bytes) {
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return e;
+    if (w_need > g_fast_w_bytes) {
+      if (g_fast_w) cudaFree(g_fast_w);
+      g_fast_w = nullptr;
+      g_fast_w_bytes = 0;
+      if ((e = cudaMalloc(&g_fast_w, w_need)) != cudaSuccess) return e;
+      g_fast_w_bytes = w_need;
+    }
+    if (x_need > g_fast_x_bytes) {
+      if (g_fast_x) cudaFree(g_fast_x);
+      g_fast_x = nullptr;
+      g_fast_x_bytes = 0;
+      if ((e = cudaMalloc(&g_fast_x, x_need)) != cudaSuccess) return e;
+      g_fast_x_bytes = x_need;
+    }
+  }
+  const int kind = llmi_act_kind_for(type);
+  {
+    const uint64_t items = uint64_t(n_tt) * nkb * tnf * 8;
+    const unsigned blocks = unsigned(std::min<uint64_t>((items + 255) / 256, uint64_t(g_sm_count) * 16));
+    cudaError_t e = llmi_launch(fast_pack_act_kernel, dim3(blocks), dim3(256), 0, s, args[0].act, args[0].act_stride, kind, K,
+                                n_tok, tnf, n_tt, nkb, reinterpret_cast<uint4*>(g_fast_x));
+    if (e != cudaSuccess) return e;
+  }
+  for (int i = 0; i < n; ++i) {
+    const uint32_t tiles = uint32_t((size_t(args[i].n_slabs) * LLMI_SLAB + fastmm::TM - 1) / fastmm::TM);
+    if (tiles == 0) continue;
+    const uint64_t items = uint64_t(tiles) * nkb * 1024;
+    const unsigned blocks = unsigned(std::min<uint64_t>((items + 255) / 256, uint64_t(g_sm_count) * 16));
+    cudaError_t e = llmi_launch(fast_dequant_kernel, dim3(blocks), dim3(256), 0, s, args[i], type, tiles, nkb,
+                                reinterpret_cast<uint4*>(g_fast_w));
+    if (e != cudaSuccess) return e;
+    if (tnf == 256)
+      e = llmi_launch(gemm_bf16_kernel<256>, dim3(tiles, n_tt), dim3(192), fastmm::Cfg<256>::SMEM, s, (const uint8_t*)g_fast_w,
+                      (const uint8_t*)g_fast_x, args[i].out, args[i].out_stride, args[i].n_local, n_tok, nkb);
+    else
+      e = llmi_launch(gemm_bf16_kernel<128>, dim3(tiles, n_tt), dim3(192), fastmm::Cfg<128>::SMEM, s, (const uint8_t*)g_fast_w,
+                      (const uint8_t*)g_fast_x, args[i].out, args[i].out_stride, args[i].n_local, n_tok, nkb);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
 template <class B>
 cudaError_t launch_tokens(const GemvArgs* args, int n, cudaStream_t s) {
+  if (g_prefill_fast && args[0].n_tok >= 64 && args[0].n_cols % fastmm::KB == 0) {
+    bool same = true;  // one activation, one K
+    for (int i = 1; i < n; ++i) same = same && args[i].act == args[0].act && args[i].n_cols == args[0].n_cols;
+    if (same) return launch_fast<B>(args, n, s);
+  }
   if (g_umma && args[0].n_tok >= g_umma_min_tokens && args[0].nb >= uint32_t(umma::SB)) {  // K >= one stage (256)
     if (std::is_same<B, BodyQ4_0>::value) return launch_umma<false>(args, n, s);
     if (std::is_same<B, BodyQ8_0>::value) return launch_umma<true>(args, n, s);
@@ -1027,6 +1108,9 @@ void llmi_gemv_set_ring(int mode, int ctas_per_sm, int depth, int warps) {
   g_ring_depth = depth;
 }
 
+void llmi_gemv_set_prefill_fast(int on) { g_prefill_fast = on != 0; }
+int llmi_gemv_prefill_fast() { return g_prefill_fast ? 1 : 0; }
+
 void llmi_gemv_set_shape(int warps, int slabs_per_cta) {
   g_warps = warps;
   g_slabs_per_cta = slabs_per_cta;
@@ -1039,6 +1123,10 @@ void llmi_gemv_shutdown() {
     for (auto& kv : g_fix) cudaFree(kv.second);
     g_fix.clear();
   }
+  if (g_fast_w) cudaFree(g_fast_w);
+  if (g_fast_x) cudaFree(g_fast_x);
+  g_fast_w = g_fast_x = nullptr;
+  g_fast_w_bytes = g_fast_x_bytes = 0;
   if (g_part) cudaFree(g_part);
   if (g_bq) cudaFree(g_bq);
   if (g_bd) cudaFree(g_bd);
@@ -1054,6 +1142,8 @@ void llmi_gemv_read_env() {
   g_umma = !(e && e[0] == '1');
   e = getenv("LLMI_UMMA_MIN_TOKENS");
   g_umma_min_tokens = e ? uint32_t(std::max(32, atoi(e))) : 128u;
+  e = getenv("LLMI_PREFILL");
+  if (e) g_prefill_fast = std::string(e) == "fast";
 }
 
 cudaError_t llmi_gemv_init() {
@@ -1067,6 +1157,10 @@ cudaError_t llmi_gemv_init() {
                                  int(umma::Cfg<false>::SMEM_BYTES))) != cudaSuccess) return e0;
   if ((e0 = cudaFuncSetAttribute(gemm_umma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  int(umma::Cfg<true>::SMEM_BYTES))) != cudaSuccess) return e0;
+  if ((e0 = cudaFuncSetAttribute(gemm_bf16_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 int(fastmm::Cfg<128>::SMEM))) != cudaSuccess) return e0;
+  if ((e0 = cudaFuncSetAttribute(gemm_bf16_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 int(fastmm::Cfg<256>::SMEM))) != cudaSuccess) return e0;
   if ((e0 = cudaFuncSetAttribute(gemm_toklane_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  int(tl_smem(8)))) != cudaSuccess) return e0;
   if ((e0 = cudaFuncSetAttribute(gemm_toklane_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,

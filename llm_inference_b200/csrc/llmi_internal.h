@@ -179,6 +179,9 @@ void llmi_gemv_set_shape(int warps, int slabs_per_cta);  // 0 = heuristic
 // persistent bulk-copy-fed kernel (gemv_ring.cuh): mode 0 heuristic / 1 never / 2 wherever it fits; CTAs per SM and
 // ring slots per warp (0 = default)
 void llmi_gemv_set_ring(int mode, int ctas_per_sm, int depth, int warps);
+// throughput prefill (gemm_bf16.cuh): token batches of >= 64 go through the dequantize-to-bf16 tcgen05 GEMM (not bit-exact)
+void llmi_gemv_set_prefill_fast(int on);
+int llmi_gemv_prefill_fast();
 cudaError_t llmi_launch_gemv_argmax(const llmi_weight_s& w, const llmi_act_s& a, float* out, unsigned long long* key,
                                     float softcap, cudaStream_t s, const GemvLL* ll = nullptr);
 cudaError_t llmi_launch_block_dots(const llmi_weight_s& w, const llmi_act_s& a, int32_t* dots_dev, cudaStream_t s);

@@ -208,6 +208,11 @@ def set_gemv_ring(mode: int = 0, ctas_per_sm: int = 0, depth: int = 0, warps: in
     _lib.check(_lib.load().llmi_set_gemv_ring(mode, ctas_per_sm, depth, warps))
 
 
+def set_prefill_mode(fast: bool) -> None:
+    """False (default): exact token-batched mat-vec.  True: dequantize-to-bf16 tcgen05 GEMM (tolerance, not bit-exact)."""
+    _lib.check(_lib.load().llmi_set_prefill_mode(1 if fast else 0))
+
+
 def device_sync() -> None:
     _lib.check(_lib.load().llmi_device_sync())
 
@@ -311,6 +316,6 @@ def registry_clear() -> None:
 __all__ = [
     "init_ops", "mat_vec_mul", "mat_vec_mul_q4_0", "mat_vec_mul_q4_k", "mat_vec_mul_q6_k", "mat_vec_mul_q8_0",
     "mat_vec_mul_q5_0", "mat_vec_mul_bf16", "mat_vec_mul_fp16", "quantize_row_q8_0", "quantize_row_q8_k",
-    "DeviceWeight", "DeviceVector", "TorchVector", "Activation", "gemv", "gemv_batch", "mat_vec_mul_dev", "block_dots", "set_gemv_shape", "set_gemv_ring",
+    "DeviceWeight", "DeviceVector", "TorchVector", "Activation", "gemv", "gemv_batch", "mat_vec_mul_dev", "block_dots", "set_gemv_shape", "set_gemv_ring", "set_prefill_mode",
     "device_sync", "registry_clear", "row_bytes",
 ]

@@ -438,3 +438,35 @@ def test_tensor_core_prefill_direct_store_is_bitwise_single_calls(gpu_ops, t):
         assert np.array_equal(got[i].view(np.uint32), o1.get().view(np.uint32)), (t, i)
     for v in (xs, out, one, o1, act, w):
         v.close()
+
+
+@pytest.mark.parametrize("t", [Q4_0, Q8_0, Q4_K, Q6_K, Q5_0, F16, BF16])
+def test_fast_prefill_gemm_is_within_its_stated_tolerance(gpu_ops, t):
+    """llmi_set_prefill_mode(1): the dequantize-to-bf16 tcgen05 GEMM (gemm_bf16.cuh).  Not the parity path — the bar it
+    states is |o - o_exact| <= 2e-2 * max|o_exact| per call against the exact token-batched mat-vec (bf16 rounds both
+    operands to 8 mantissa bits; measured ~2e-3); ragged row and token tiles, one and several token tiles."""
+    ops = gpu_ops
+    kq = t in (Q4_K, Q6_K)
+    try:
+        for k, n, m in ((1280 if kq else 1152, 203, 131), (2560, 520, 300), (512, 136, 64)):
+            w = ops.DeviceWeight(_weights(t, n, k, seed=5 * k + n), t, k, n)
+            x = np.random.default_rng(m + k).standard_normal((m, k)).astype(np.float32)
+            xs, out = ops.DeviceVector(m * k, x), ops.DeviceVector(m * n, np.full(m * n, np.nan, np.float32))
+            ops.set_prefill_mode(False)
+            ops.gemm_tokens(w, xs, m, out)
+            ops.device_sync()
+            exact = out.get().reshape(m, n).copy()
+            out2 = ops.DeviceVector(m * n, np.full(m * n, np.nan, np.float32))
+            ops.set_prefill_mode(True)
+            ops.gemm_tokens(w, xs, m, out2)
+            ops.device_sync()
+            fast = out2.get().reshape(m, n)
+            assert not np.isnan(fast).any()
+            scale = float(np.abs(exact).max())
+            err = float(np.abs(fast - exact).max())
+            assert err <= 2e-2 * scale, (synth.TYPE_NAMES[t], k, n, m, err / scale)
+            assert err > 0 or t in (F16, BF16)  # it IS another arithmetic: a bit-equal result would mean the exact path ran
+            for h in (w, xs, out, out2):
+                h.close()
+    finally:
+        ops.set_prefill_mode(False)
