@@ -315,6 +315,120 @@ __global__ void __launch_bounds__(1024) attention_kernel(AttnArgs a, uint32_t nb
   TL_MARK(2);
 }
 
+// ---- throughput prefill (opt-in, llmi_set_prefill_mode(1)): attention of a token batch without the reference's
+// position-by-position fp16 recurrence ------------------------------------------------------------------------------
+// attention_kernel<D, 2> reproduces model.cpp:476-550 operation for operation — an fp16 accumulator rounded after
+// every cached position — one CTA per (head, token) walking the whole context: 1.1 of the 1.33 s of a 2048-token
+// gemma-3-27b prompt once the mat-vecs run on the tensor cores.  This kernel computes the same softmax(q.K)V with an
+// fp32 online softmax: CTA = one KV head x QB consecutive tokens x the G query heads that share the KV head (16
+// warps, one per (head, token)); K / V tiles of 32 positions go through shared memory once for all of them; a lane
+// owns a POSITION for the scores (q broadcast from shared memory, K rows padded to D + 1 words: conflict-free) and
+// a run of D/32 ELEMENTS for the value accumulation.  Inputs are what the exact prologue (MODE 1) left: f16(q),
+// f16(k) as double high words, f16 values; the output feeds the generic quantizer.  Not bit-exact (the reference's
+// fp16 recurrence is itself ~1e-3 from the arithmetic it approximates); covered by the fast mode's stated tolerance.
+__device__ __forceinline__ float double_hi_to_float(uint32_t hi) {  // hi = high word of double(x), x an f16 value
+  const uint32_t e = (hi >> 20) & 0x7ffu;
+  return e == 0 ? 0.0f : __uint_as_float((hi & 0x80000000u) | ((e - 896u) << 23) | ((hi & 0xfffffu) << 3));
+}
+constexpr int FA_WARPS = 16, FA_TILE = 32;
+template <int D>
+__global__ void __launch_bounds__(FA_WARPS * 32) fast_attention_kernel(AttnArgs a, uint32_t n_tok, uint32_t qb_tokens) {
+  extern __shared__ __align__(16) uint8_t fa_smem[];
+  constexpr int KS = D + 1, EPL = D / 32;  // padded K row (words); elements per lane
+  float* kt = reinterpret_cast<float*>(fa_smem);                                   // [32][D + 1]
+  __half* vt = reinterpret_cast<__half*>(kt + FA_TILE * KS + 3);                   // [32][D] (8-byte aligned below)
+  vt = reinterpret_cast<__half*>((reinterpret_cast<uintptr_t>(vt) + 15) & ~uintptr_t(15));
+  float* qs = reinterpret_cast<float*>(vt + FA_TILE * D);                          // [FA_WARPS][D]
+  pdl_trigger();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t hkv = blockIdx.x, G = a.H / a.HK;
+  const uint32_t g = warp % G, tq = warp / G;
+  const uint32_t tok = blockIdx.y * qb_tokens + tq, h = hkv * G + g;
+  const bool live = tq < qb_tokens && tok < n_tok;
+  pdl_wait();
+  const int pos0 = *a.pos;  // position of the batch's first token
+  const int P = pos0 + int(tok);                                   // this warp attends to positions 0..P
+  const int P_max = pos0 + int(min(n_tok, (blockIdx.y + 1) * qb_tokens)) - 1;  // ... and the CTA's last token to 0..P_max
+  if (live) {
+    const uint32_t* q = a.qbuf + (size_t(tok) * a.H + h) * D;
+    for (int i = lane; i < D; i += 32) qs[warp * D + i] = double_hi_to_float(q[i]);
+  }
+  float m = -INFINITY, l = 0.0f, acc[EPL];
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) acc[e] = 0.0f;
+  const uint32_t* kc = a.kcache + size_t(hkv) * a.t_max * D;
+  const __half* vc = a.vcache + size_t(hkv) * a.t_max * D;
+  for (int t0 = 0; t0 <= P_max; t0 += FA_TILE) {
+    const int nt = min(FA_TILE, P_max + 1 - t0);
+    __syncthreads();  // the previous tile has been consumed (and qs is written)
+    for (int i = threadIdx.x; i < nt * D; i += FA_WARPS * 32) {
+      const int r = i / D, c = i - r * D;
+      kt[r * KS + c] = double_hi_to_float(kc[size_t(t0 + r) * D + c]);
+    }
+    for (int i = threadIdx.x; i < nt * D / 8; i += FA_WARPS * 32)
+      reinterpret_cast<uint4*>(vt)[i] = reinterpret_cast<const uint4*>(vc + size_t(t0) * D)[i];
+    __syncthreads();
+    if (!live || t0 > P) continue;
+    // scores: lane = position t0 + lane
+    float sc = 0.0f;
+    {
+      const float* kr = kt + min(lane, nt - 1) * KS;
+      const float4* q4 = reinterpret_cast<const float4*>(qs + warp * D);
+#pragma unroll 8
+      for (int i = 0; i < D / 4; ++i) {
+        const float4 qv = q4[i];
+        sc = fmaf(qv.x, kr[4 * i], sc);
+        sc = fmaf(qv.y, kr[4 * i + 1], sc);
+        sc = fmaf(qv.z, kr[4 * i + 2], sc);
+        sc = fmaf(qv.w, kr[4 * i + 3], sc);
+      }
+    }
+    if (a.softcap > 0.0f) sc = a.softcap * tanhf(sc / a.softcap);
+    const bool ok = t0 + lane <= P;
+    float tm = ok ? sc : -INFINITY;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) tm = fmaxf(tm, __shfl_xor_sync(0xffffffffu, tm, o));
+    const float m_new = fmaxf(m, tm);
+    const float p = ok ? __expf(sc - m_new) : 0.0f;
+    const float corr = __expf(m - m_new);  // m = -inf on the first tile: 0
+    float ps = p;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o);
+    l = l * corr + ps;
+    m = m_new;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) acc[e] *= corr;
+    // values: lane = elements EPL * lane .. + EPL - 1
+    const int jn = min(nt, P - t0 + 1);
+    for (int j = 0; j < jn; ++j) {
+      const float pj = __shfl_sync(0xffffffffu, p, j);
+      const __half* vr = vt + j * D + lane * EPL;
+      if (EPL == 4) {
+        const uint2 w = *reinterpret_cast<const uint2*>(vr);
+        const float2 v0 = __half22float2(*reinterpret_cast<const __half2*>(&w.x));
+        const float2 v1 = __half22float2(*reinterpret_cast<const __half2*>(&w.y));
+        acc[0] = fmaf(pj, v0.x, acc[0]);
+        acc[1] = fmaf(pj, v0.y, acc[1]);
+        acc[2] = fmaf(pj, v1.x, acc[2]);
+        acc[3] = fmaf(pj, v1.y, acc[3]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < EPL; e += 2) {
+          const float2 v = __half22float2(*reinterpret_cast<const __half2*>(vr + e));
+          acc[e] = fmaf(pj, v.x, acc[e]);
+          acc[e + 1] = fmaf(pj, v.y, acc[e + 1]);
+        }
+      }
+    }
+  }
+  if (live) {
+    const float inv = l > 0.0f ? 1.0f / l : 0.0f;
+    float* o = a.out + size_t(tok) * a.H * D + size_t(h) * D + lane * EPL;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) o[e] = acc[e] * inv;
+  }
+}
+
 // RoPE factors for every (position, pair): ops.cpp:80-83 —
 //   freq = 1.0f / powf(base, float(2i)/n_rot); val = float(pos) * freq / scale; cosf(val), sinf(val)
 __global__ void rope_table_kernel(float2* table, uint32_t t_max, uint32_t D, float base, float scale) {
@@ -544,6 +658,21 @@ static cudaError_t attention_launch(const AttnArgs& a, uint32_t n_tok, cudaStrea
   if (!a.qbuf) return cudaErrorInvalidValue;
   cudaError_t e = llmi_launch(attention_kernel<D, 1>, dim3(a.H, n_tok), dim3(1024), 0, s, a, nbuf);
   if (e != cudaSuccess) return e;
+  if (llmi_gemv_prefill_fast() && D >= 64 && D <= 256 && FA_WARPS % (a.H / a.HK) == 0) {  // throughput prefill
+    const uint32_t qb = FA_WARPS / (a.H / a.HK);
+    const size_t fsm = size_t(FA_TILE) * (D + 1) * 4 + 32 + size_t(FA_TILE) * D * 2 + size_t(FA_WARPS) * D * 4;
+    static bool optin = false;
+    if (!optin) {
+      if ((e = cudaFuncSetAttribute(fast_attention_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fsm))) != cudaSuccess)
+        return e;
+      optin = true;
+    }
+    if ((e = llmi_launch(fast_attention_kernel<D>, dim3(a.HK, (n_tok + qb - 1) / qb), dim3(FA_WARPS * 32), fsm, s, a, n_tok,
+                         qb)) != cudaSuccess)
+      return e;
+    if (a.act_kind == ACT_NONE) return cudaSuccess;
+    return llmi_launch_act(a.out, a.H * a.D, a.act_kind, a.act_buf, s, n_tok, a.act_stride);
+  }
   return llmi_launch(attention_kernel<D, 2>, dim3(a.H, n_tok), dim3(1024), smem, s, a, nbuf);
 }
 
