@@ -575,7 +575,7 @@ void pick_shape(const GemvArgs& a, uint64_t slabs_in_launch, int& W, uint32_t& S
 // ---- persistent bulk-copy-fed kernel (gemv_ring.cuh) --------------------------------------------------------
 // g_ring_mode: 0 = heuristic (ring_wanted), 1 = never, 2 = wherever it fits.  g_ring_cps / g_ring_depth: CTAs per SM
 // and ring slots per warp (0 = default).  Results never depend on any of them.
-int g_ring_mode = 0, g_ring_cps = 0, g_ring_depth = 0, g_ring_pf = 0, g_ring_w = 16;  // g_ring_w: warps per CTA, 8 or 16
+int g_ring_mode = 0, g_ring_cps = 0, g_ring_depth = 0, g_ring_w = 16;  // g_ring_w: warps per CTA, 8 or 16
 constexpr uint32_t RING_MAX_CTAS = 148 * 4, RING_MAX_CHUNKS = 64, RING_MAX_PART_ITEMS = 768;
 constexpr size_t RING_MAX_SMEM = 112 * 1024;
 
@@ -648,7 +648,6 @@ cudaError_t launch_ring(const GemvArgs* args, int n, cudaStream_t s, const GemvL
   b.n = n;
   b.total = total;
   b.part_items = uint32_t((uint64_t(total) + ctas - 1) / ctas);
-  b.pf_items = uint32_t(g_ring_pf);
   uint32_t slabs = 0;
   for (int i = 0; i < GEMV_MAX_BATCH; ++i) {
     b.a[i] = args[i < n ? i : 0];
@@ -1102,7 +1101,6 @@ uint32_t llmi_gemv_chunks(const llmi_weight_s& w) {
 
 void llmi_gemv_set_ring(int mode, int ctas_per_sm, int depth, int warps) {
   g_ring_w = warps == 8 ? 8 : 16;
-  if (const char* e = getenv("LLMI_RING_PF")) g_ring_pf = std::max(0, atoi(e));  // items per CTA prefetched to L2 (A/B)
   g_ring_mode = mode;
   g_ring_cps = ctas_per_sm;
   g_ring_depth = depth;

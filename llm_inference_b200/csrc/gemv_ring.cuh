@@ -19,8 +19,10 @@
 //   * a slab whose K-chunks straddle two (or more) CTAs is summed by the CTA that holds its LAST chunk; the others
 //     process those chunks FIRST and hand their chunk partials over as flagged 64-bit words {value, 1} in a small
 //     scratch buffer (single-copy atomic: no fence).  The owner adds all J partials left to right — the canonical
-//     order — and clears the words it consumed.  Publishing happens after griddepcontrol.wait and consuming before
-//     the kernel ends, so launches of one stream never overlap in the buffer.
+//     order — and clears the words it consumed.  A CTA therefore only waits for CTAs with a smaller index, which
+//     start first and wait for nobody behind them: no cooperative launch is needed for forward progress.  Publishing
+//     happens after griddepcontrol.wait and consuming before the kernel ends, so launches of one stream never overlap
+//     in the buffer.
 #pragma once
 // (included inside gemv.cu's anonymous namespace, like umma_prefill.cuh)
 
@@ -129,7 +131,6 @@ struct RingBatch {
   int n;
   uint32_t total;   // work items of the launch = (slabs of all matrices) x chunks
   uint32_t part_items;  // capacity of the chunk-partial array of a CTA (items)
-  uint32_t pf_items;    // items behind the rings that every CTA sends to L2 before it waits for its predecessor
   uint2* fix;       // [gridDim.x][chunks][8] flagged chunk partials of slabs split across CTAs; all zero between launches
   LLPeers peers;
   LLTag tag;
@@ -279,18 +280,24 @@ __global__ void __launch_bounds__(W * 32) gemv_ring_kernel(const RingBatch batch
   uint8_t* sm_act = smem + act_off;
   float* part = reinterpret_cast<float*>(sm_act + ((a0.act_bytes + 127u) & ~127u));
   if (threadIdx.x == 0) mbar_init(&bars[0], 1);
-  // This CTA's items [g0, g1), in order.  A slab belongs to the CTA that holds its FIRST chunk: the chunks of a
-  // leading slab that began in an earlier CTA come first in the sequence and are handed to that CTA right away;
-  // the missing trailing chunks of this CTA's last slab are collected at the very end.
+  // This CTA's items [g0, g1).  A slab belongs to the CTA that holds its LAST chunk, so a CTA only ever waits for CTAs
+  // with a SMALLER index — which the hardware starts first and which wait for nobody behind them: forward progress
+  // does not depend on the whole grid being resident (the look-back argument of single-pass scans).  The chunks of a
+  // trailing slab this CTA does not own go FIRST in its sequence and are handed over as soon as they are computed;
+  // sequence position i -> item: i < n_tail ? tail0 + i : g0 + (i - n_tail).
   const uint32_t g0 = uint32_t(uint64_t(batch.total) * blockIdx.x / gridDim.x);
   const uint32_t g1 = uint32_t(uint64_t(batch.total) * (blockIdx.x + 1) / gridDim.x);
   const uint32_t n_my = g1 - g0;
-  const uint32_t S0 = g0 / J, j0 = g0 - S0 * J;
-  uint32_t n_lead = 0, lead_owner = 0;
-  if (j0 != 0 && n_my) {
-    n_lead = min(g1, (S0 + 1) * J) - g0;
-    lead_owner = uint32_t((uint64_t(S0 * J + 1) * gridDim.x - 1) / batch.total);  // the CTA whose range holds item S0 * J
+  uint32_t n_tail = 0, tail0 = g1, owner = 0;
+  if (n_my) {
+    const uint32_t sb = (g1 - 1) / J, last = sb * J + J - 1;  // last chunk of the last slab touched
+    if (last >= g1) {
+      tail0 = max(g0, sb * J);
+      n_tail = g1 - tail0;
+      owner = uint32_t((uint64_t(last + 1) * gridDim.x - 1) / batch.total);  // the CTA whose range holds item `last`
+    }
   }
+  auto item_of = [&](uint32_t i) -> uint32_t { return i < n_tail ? tail0 + i : g0 + (i - n_tail); };
   __syncthreads();
   // all lanes: asynchronous copies of the item under cursor c (if any) into slot s; always one commit group
   auto fill = [&](const RingCursor& c, bool live, int s) {
@@ -315,32 +322,23 @@ __global__ void __launch_bounds__(W * 32) gemv_ring_kernel(const RingBatch batch
   RingCursor cf, cc;  // fill cursor (runs D rounds ahead) and consume cursor
   uint32_t i_f = warp;
   if (uint32_t(warp) < n_my) {
-    cf.init(batch, g0 + warp, J);
+    cf.init(batch, item_of(warp), J);
     cc = cf;
   }
+  // sequence position i_old -> i_old + W: one step of the cursor, except across the jump from the tail items back to g0
+  auto step = [&](RingCursor& c, uint32_t i_new) {
+    if (i_new - W < n_tail && i_new >= n_tail) c.init(batch, item_of(i_new), J);
+    else c.template advance<W>(batch, J);
+  };
 #pragma unroll
   for (int s = 0; s < D; ++s) {
     fill(cf, i_f < n_my, s);
     i_f += W;
-    if (i_f < n_my) cf.template advance<W>(batch, J);
+    if (i_f < n_my) step(cf, i_f);
   }
-  // Still nothing here depends on the predecessor: the items BEHIND the rings go to L2 (cp.async.bulk.prefetch.L2, one
-  // instruction per plane of an item, no destination, no completion to wait for).  In the decode step the predecessor
-  // is a glue kernel with a handful of CTAs and an idle HBM pipe; what it leaves of its run time is spent here.
-  if (batch.pf_items && warp == W - 1) {
-    const uint32_t first = uint32_t(W) * D, last = min(n_my, first + batch.pf_items);
-    for (uint32_t i = first + lane; i < last; i += 32) {
-      const uint32_t g = g0 + i, S = g / J, j = g - S * J;
-      int mi = 0;
-      while (mi + 1 < batch.n && S >= batch.slab_end[mi]) ++mi;
-      const GemvArgs& a = batch.a[mi];
-      const uint32_t c0 = j * F::CELLS, nc = min(F::CELLS, nb - c0);
-      const size_t cell = size_t(S - (mi ? batch.slab_end[mi - 1] : 0u)) * nb + c0;
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.q + cell * F::QB), "r"(nc * F::QB) : "memory");
-      if (F::DB) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.d + cell * F::DB), "r"(nc * F::DB) : "memory");
-      if (F::XB) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.x + cell * F::XB), "r"(nc * F::XB) : "memory");
-    }
-  }
+  // (An L2 prefetch of the items BEHIND the rings — cp.async.bulk.prefetch.L2 per item plane, issued here — was
+  // measured and removed: the decode step got slower, 4.92 -> 5.13 / 5.42 ms at 32 / 96 items per CTA,
+  // profiles/r02_ab_ring_prefetch.txt.)
   // the activation vector is the predecessor's output
   pdl_wait();
   TL_MARK(1);
@@ -366,40 +364,40 @@ __global__ void __launch_bounds__(W * 32) gemv_ring_kernel(const RingBatch batch
     // (the shuffles of the item's reduction are past every lane's reads of the slot: it can be refilled)
     fill(cf, i_f < n_my, s);
     i_f += W;
-    if (i_f < n_my) cf.template advance<W>(batch, J);
+    if (i_f < n_my) step(cf, i_f);
     if (lane < LLMI_SLAB) {
-      part[i * LLMI_SLAB + lane] = v;
-      if (i < n_lead) ring_fix_store(batch.fix + (size_t(lead_owner) * J + j) * LLMI_SLAB + lane, v);
+      part[(cc.S * J + j - g0) * LLMI_SLAB + lane] = v;
+      if (i < n_tail) ring_fix_store(batch.fix + (size_t(owner) * J + j) * LLMI_SLAB + lane, v);
     }
-    if (i + W < n_my) cc.template advance<W>(batch, J);
+    if (i + W < n_my) step(cc, i + W);
     s = s + 1 == D ? 0 : s + 1;
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   TL_MARK(4);
-  // the trailing chunks of this CTA's last slab were computed by later CTAs (at the START of their sequences): every
+  // the leading chunks of this CTA's first slab may have been computed by earlier CTAs (FIRST in their sequences): every
   // missing (chunk, row) word is fetched by its own thread — one round trip for all of them — into the partials array
-  const uint32_t Sa = j0 ? S0 + 1 : S0;  // first owned slab
-  const bool owns = n_my && Sa * J < g1;
-  if (owns) {
-    const uint32_t Sl = (g1 - 1) / J, have = g1 - Sl * J;  // last owned slab, its chunks computed here
-    if (have < J) {
-      uint2* fp = batch.fix + size_t(blockIdx.x) * J * LLMI_SLAB;
-      for (uint32_t idx = threadIdx.x; idx < (J - have) * LLMI_SLAB; idx += W * 32)
-        part[(n_my + idx / LLMI_SLAB) * LLMI_SLAB + idx % LLMI_SLAB] = ring_fix_take(fp + have * LLMI_SLAB + idx);
-    }
+  // behind this CTA's own items
+  const uint32_t Sa = g0 / J, lead = g0 - Sa * J;  // first slab touched, its chunks computed elsewhere
+  const bool owns = n_my > n_tail;                 // the items in front of tail0 end on a slab boundary
+  if (owns && lead) {
+    uint2* fp = batch.fix + size_t(blockIdx.x) * J * LLMI_SLAB;
+    for (uint32_t idx = threadIdx.x; idx < lead * LLMI_SLAB; idx += W * 32) part[n_my * LLMI_SLAB + idx] = ring_fix_take(fp + idx);
   }
   __syncthreads();
   TL_MARK(5);
-  // rows of the slabs this CTA owns (first chunk in [g0, g1)): chunk partials left to right, the canonical order
+  // rows of the slabs this CTA owns: chunk partials left to right, the canonical order
   unsigned long long best = 0;
   const uint32_t tag = PUSH ? ll_tag(batch.tag) : 0u;
   if (owns) {
-    const uint32_t n_own = (g1 - 1) / J - Sa + 1;
+    const uint32_t n_own = (tail0 - 1) / J - Sa + 1;
     for (uint32_t idx = threadIdx.x; idx < n_own * LLMI_SLAB; idx += W * 32) {
       const uint32_t S = Sa + idx / LLMI_SLAB, rr = idx % LLMI_SLAB;
-      const float* p = part + size_t(S * J - g0) * LLMI_SLAB + rr;
-      float sum = p[0];
-      for (uint32_t j = 1; j < J; ++j) sum += p[j * LLMI_SLAB];
+      const uint32_t nl = S == Sa ? lead : 0u;  // chunks of this slab that sit in the collected region
+      const float* pl = part + size_t(n_my) * LLMI_SLAB + rr;
+      const float* p = part + (ptrdiff_t(S * J) - ptrdiff_t(g0)) * LLMI_SLAB + rr;  // dereferenced from chunk nl on
+      float sum = nl ? pl[0] : p[0];
+      for (uint32_t j = 1; j < nl; ++j) sum += pl[j * LLMI_SLAB];
+      for (uint32_t j = nl ? nl : 1u; j < J; ++j) sum += p[j * LLMI_SLAB];
       int mi = 0;
       while (mi + 1 < batch.n && S >= batch.slab_end[mi]) ++mi;
       const GemvArgs& a = batch.a[mi];
