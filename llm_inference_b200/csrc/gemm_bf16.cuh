@@ -159,7 +159,10 @@ __global__ void fast_pack_act_kernel(const uint8_t* __restrict__ act, uint32_t a
   }
 }
 
-// grid = (row tiles, token tiles); A / Bt: the operand-order buffers of the two kernels above
+// grid = (token tiles, row tiles) — the token tiles of one row tile run side by side, so its dequantized weights are
+// read from DRAM once and from L2 by the others (with the tiles the other way round the 21504 x 5376 matrix was read
+// once per token tile: 945 MB of DRAM reads for 231 MB of weights, profiles/r02_ncu_gemm_bf16_gate27b.csv);
+// A / Bt: the operand-order buffers of the two kernels above
 template <int TNF>
 __global__ void __launch_bounds__(192, 1)
 gemm_bf16_kernel(const uint8_t* __restrict__ A, const uint8_t* __restrict__ Bt, float* __restrict__ out, uint32_t out_stride,
@@ -170,7 +173,7 @@ gemm_bf16_kernel(const uint8_t* __restrict__ A, const uint8_t* __restrict__ Bt, 
   __shared__ __align__(8) uint64_t full[NST], empty[NST], acc_full;
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rt = blockIdx.x, tt = blockIdx.y;
+  const uint32_t rt = blockIdx.y, tt = blockIdx.x;
   pdl_trigger();
   uint8_t* smem = fsm_raw + ((1024u - (smem_u32(fsm_raw) & 1023u)) & 1023u);
   if (threadIdx.x == 0) {

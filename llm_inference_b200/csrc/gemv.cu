@@ -974,10 +974,10 @@ cudaError_t launch_fast(const GemvArgs* args, int n, cudaStream_t s) {
                                 reinterpret_cast<uint4*>(g_fast_w));
     if (e != cudaSuccess) return e;
     if (tnf == 256)
-      e = llmi_launch(gemm_bf16_kernel<256>, dim3(tiles, n_tt), dim3(192), fastmm::Cfg<256>::SMEM, s, (const uint8_t*)g_fast_w,
+      e = llmi_launch(gemm_bf16_kernel<256>, dim3(n_tt, tiles), dim3(192), fastmm::Cfg<256>::SMEM, s, (const uint8_t*)g_fast_w,
                       (const uint8_t*)g_fast_x, args[i].out, args[i].out_stride, args[i].n_local, n_tok, nkb);
     else
-      e = llmi_launch(gemm_bf16_kernel<128>, dim3(tiles, n_tt), dim3(192), fastmm::Cfg<128>::SMEM, s, (const uint8_t*)g_fast_w,
+      e = llmi_launch(gemm_bf16_kernel<128>, dim3(n_tt, tiles), dim3(192), fastmm::Cfg<128>::SMEM, s, (const uint8_t*)g_fast_w,
                       (const uint8_t*)g_fast_x, args[i].out, args[i].out_stride, args[i].n_local, n_tok, nkb);
     if (e != cudaSuccess) return e;
   }
@@ -1140,7 +1140,7 @@ void llmi_gemv_read_env() {
   g_umma = !(e && e[0] == '1');
   e = getenv("LLMI_UMMA_MIN_TOKENS");
   g_umma_min_tokens = e ? uint32_t(std::max(32, atoi(e))) : 128u;
-  e = getenv("LLMI_PREFILL");
+  e = getenv("LLMI_PREFILL");  // "fast" / anything else = exact; unset: whatever llmi_set_prefill_mode last said
   if (e) g_prefill_fast = std::string(e) == "fast";
 }
 

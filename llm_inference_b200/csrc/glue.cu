@@ -330,50 +330,64 @@ __device__ __forceinline__ float double_hi_to_float(uint32_t hi) {  // hi = high
   const uint32_t e = (hi >> 20) & 0x7ffu;
   return e == 0 ? 0.0f : __uint_as_float((hi & 0x80000000u) | ((e - 896u) << 23) | ((hi & 0xfffffu) << 3));
 }
-constexpr int FA_WARPS = 16, FA_TILE = 32;
+// FA_QPW = queries (consecutive tokens) per warp.  4 was measured and is slower (gemma-3-27b 2048-token prompt 426 -> 470 ms,
+// 1b 69 -> 91 ms): the kernel is bound by the per-warp score / value loops, not by the tile loads, and fewer, fatter
+// CTAs lose more in parallelism than they save in tile traffic.
+constexpr int FA_WARPS = 16, FA_TILE = 32, FA_QPW = 1;  // warps per CTA, positions per tile, queries per warp
 template <int D>
 __global__ void __launch_bounds__(FA_WARPS * 32) fast_attention_kernel(AttnArgs a, uint32_t n_tok, uint32_t qb_tokens) {
   extern __shared__ __align__(16) uint8_t fa_smem[];
   constexpr int KS = D + 1, EPL = D / 32;  // padded K row (words); elements per lane
   float* kt = reinterpret_cast<float*>(fa_smem);                                   // [32][D + 1]
-  __half* vt = reinterpret_cast<__half*>(kt + FA_TILE * KS + 3);                   // [32][D] (8-byte aligned below)
-  vt = reinterpret_cast<__half*>((reinterpret_cast<uintptr_t>(vt) + 15) & ~uintptr_t(15));
-  float* qs = reinterpret_cast<float*>(vt + FA_TILE * D);                          // [FA_WARPS][D]
+  __half* vt = reinterpret_cast<__half*>((reinterpret_cast<uintptr_t>(kt + FA_TILE * KS) + 15) & ~uintptr_t(15));  // [32][D]
+  float* qs = reinterpret_cast<float*>(vt + FA_TILE * D);                          // [FA_WARPS][FA_QPW][D]
   pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t hkv = blockIdx.x, G = a.H / a.HK;
-  const uint32_t g = warp % G, tq = warp / G;
-  const uint32_t tok = blockIdx.y * qb_tokens + tq, h = hkv * G + g;
-  const bool live = tq < qb_tokens && tok < n_tok;
+  const uint32_t g = warp % G, tw = warp / G;  // query head within the KV group; this warp's run of FA_QPW tokens
+  const uint32_t h = hkv * G + g;
+  const uint32_t tok0 = blockIdx.y * qb_tokens + tw * FA_QPW;
   pdl_wait();
   const int pos0 = *a.pos;  // position of the batch's first token
-  const int P = pos0 + int(tok);                                   // this warp attends to positions 0..P
-  const int P_max = pos0 + int(min(n_tok, (blockIdx.y + 1) * qb_tokens)) - 1;  // ... and the CTA's last token to 0..P_max
-  if (live) {
-    const uint32_t* q = a.qbuf + (size_t(tok) * a.H + h) * D;
-    for (int i = lane; i < D; i += 32) qs[warp * D + i] = double_hi_to_float(q[i]);
-  }
-  float m = -INFINITY, l = 0.0f, acc[EPL];
+  const int P_max = pos0 + int(min(n_tok, (blockIdx.y + 1) * qb_tokens)) - 1;  // the CTA's last token attends to 0..P_max
+  int P[FA_QPW];      // query qi attends to positions 0..P[qi]; -1: no such token
+  float m[FA_QPW], l[FA_QPW], acc[FA_QPW][EPL];
 #pragma unroll
-  for (int e = 0; e < EPL; ++e) acc[e] = 0.0f;
+  for (int qi = 0; qi < FA_QPW; ++qi) {
+    const uint32_t tok = tok0 + qi;
+    P[qi] = tok < n_tok ? pos0 + int(tok) : -1;
+    m[qi] = -INFINITY;
+    l[qi] = 0.0f;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) acc[qi][e] = 0.0f;
+    if (P[qi] >= 0) {
+      const uint32_t* q = a.qbuf + (size_t(tok) * a.H + h) * D;
+      for (int i = lane; i < D; i += 32) qs[(warp * FA_QPW + qi) * D + i] = double_hi_to_float(q[i]);
+    }
+  }
   const uint32_t* kc = a.kcache + size_t(hkv) * a.t_max * D;
   const __half* vc = a.vcache + size_t(hkv) * a.t_max * D;
   for (int t0 = 0; t0 <= P_max; t0 += FA_TILE) {
     const int nt = min(FA_TILE, P_max + 1 - t0);
     __syncthreads();  // the previous tile has been consumed (and qs is written)
-    for (int i = threadIdx.x; i < nt * D; i += FA_WARPS * 32) {
-      const int r = i / D, c = i - r * D;
-      kt[r * KS + c] = double_hi_to_float(kc[size_t(t0 + r) * D + c]);
+    for (int i = threadIdx.x; i < nt * D / 4; i += FA_WARPS * 32) {
+      const int r = (i * 4) / D, c = i * 4 - r * D;
+      const uint4 w = *reinterpret_cast<const uint4*>(kc + size_t(t0 + r) * D + c);
+      float* dst = kt + r * KS + c;
+      dst[0] = double_hi_to_float(w.x);
+      dst[1] = double_hi_to_float(w.y);
+      dst[2] = double_hi_to_float(w.z);
+      dst[3] = double_hi_to_float(w.w);
     }
     for (int i = threadIdx.x; i < nt * D / 8; i += FA_WARPS * 32)
       reinterpret_cast<uint4*>(vt)[i] = reinterpret_cast<const uint4*>(vc + size_t(t0) * D)[i];
     __syncthreads();
-    if (!live || t0 > P) continue;
-    // scores: lane = position t0 + lane
-    float sc = 0.0f;
-    {
-      const float* kr = kt + min(lane, nt - 1) * KS;
-      const float4* q4 = reinterpret_cast<const float4*>(qs + warp * D);
+    const float* kr = kt + min(lane, nt - 1) * KS;  // scores: lane = position t0 + lane
+#pragma unroll
+    for (int qi = 0; qi < FA_QPW; ++qi) {
+      if (t0 > P[qi]) continue;  // warp-uniform
+      float sc = 0.0f;
+      const float4* q4 = reinterpret_cast<const float4*>(qs + (warp * FA_QPW + qi) * D);
 #pragma unroll 8
       for (int i = 0; i < D / 4; ++i) {
         const float4 qv = q4[i];
@@ -382,50 +396,42 @@ __global__ void __launch_bounds__(FA_WARPS * 32) fast_attention_kernel(AttnArgs 
         sc = fmaf(qv.z, kr[4 * i + 2], sc);
         sc = fmaf(qv.w, kr[4 * i + 3], sc);
       }
-    }
-    if (a.softcap > 0.0f) sc = a.softcap * tanhf(sc / a.softcap);
-    const bool ok = t0 + lane <= P;
-    float tm = ok ? sc : -INFINITY;
+      if (a.softcap > 0.0f) sc = a.softcap * tanhf(sc / a.softcap);
+      const bool ok = t0 + lane <= P[qi];
+      float tm = ok ? sc : -INFINITY;
 #pragma unroll
-    for (int o = 16; o; o >>= 1) tm = fmaxf(tm, __shfl_xor_sync(0xffffffffu, tm, o));
-    const float m_new = fmaxf(m, tm);
-    const float p = ok ? __expf(sc - m_new) : 0.0f;
-    const float corr = __expf(m - m_new);  // m = -inf on the first tile: 0
-    float ps = p;
+      for (int o = 16; o; o >>= 1) tm = fmaxf(tm, __shfl_xor_sync(0xffffffffu, tm, o));
+      const float m_new = fmaxf(m[qi], tm);
+      const float p = ok ? __expf(sc - m_new) : 0.0f;
+      const float corr = __expf(m[qi] - m_new);  // m = -inf on the first tile: 0
+      float ps = p;
 #pragma unroll
-    for (int o = 16; o; o >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o);
-    l = l * corr + ps;
-    m = m_new;
+      for (int o = 16; o; o >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o);
+      l[qi] = l[qi] * corr + ps;
+      m[qi] = m_new;
 #pragma unroll
-    for (int e = 0; e < EPL; ++e) acc[e] *= corr;
-    // values: lane = elements EPL * lane .. + EPL - 1
-    const int jn = min(nt, P - t0 + 1);
-    for (int j = 0; j < jn; ++j) {
-      const float pj = __shfl_sync(0xffffffffu, p, j);
-      const __half* vr = vt + j * D + lane * EPL;
-      if (EPL == 4) {
-        const uint2 w = *reinterpret_cast<const uint2*>(vr);
-        const float2 v0 = __half22float2(*reinterpret_cast<const __half2*>(&w.x));
-        const float2 v1 = __half22float2(*reinterpret_cast<const __half2*>(&w.y));
-        acc[0] = fmaf(pj, v0.x, acc[0]);
-        acc[1] = fmaf(pj, v0.y, acc[1]);
-        acc[2] = fmaf(pj, v1.x, acc[2]);
-        acc[3] = fmaf(pj, v1.y, acc[3]);
-      } else {
+      for (int e = 0; e < EPL; ++e) acc[qi][e] *= corr;
+      // values: lane = elements EPL * lane .. + EPL - 1
+      const int jn = min(nt, P[qi] - t0 + 1);
+      for (int j = 0; j < jn; ++j) {
+        const float pj = __shfl_sync(0xffffffffu, p, j);
+        const __half* vr = vt + j * D + lane * EPL;
 #pragma unroll
         for (int e = 0; e < EPL; e += 2) {
           const float2 v = __half22float2(*reinterpret_cast<const __half2*>(vr + e));
-          acc[e] = fmaf(pj, v.x, acc[e]);
-          acc[e + 1] = fmaf(pj, v.y, acc[e + 1]);
+          acc[qi][e] = fmaf(pj, v.x, acc[qi][e]);
+          acc[qi][e + 1] = fmaf(pj, v.y, acc[qi][e + 1]);
         }
       }
     }
   }
-  if (live) {
-    const float inv = l > 0.0f ? 1.0f / l : 0.0f;
-    float* o = a.out + size_t(tok) * a.H * D + size_t(h) * D + lane * EPL;
 #pragma unroll
-    for (int e = 0; e < EPL; ++e) o[e] = acc[e] * inv;
+  for (int qi = 0; qi < FA_QPW; ++qi) {
+    if (P[qi] < 0) continue;
+    const float inv = l[qi] > 0.0f ? 1.0f / l[qi] : 0.0f;
+    float* o = a.out + size_t(tok0 + qi) * a.H * D + size_t(h) * D + lane * EPL;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) o[e] = acc[qi][e] * inv;
   }
 }
 
@@ -659,8 +665,8 @@ static cudaError_t attention_launch(const AttnArgs& a, uint32_t n_tok, cudaStrea
   cudaError_t e = llmi_launch(attention_kernel<D, 1>, dim3(a.H, n_tok), dim3(1024), 0, s, a, nbuf);
   if (e != cudaSuccess) return e;
   if (llmi_gemv_prefill_fast() && D >= 64 && D <= 256 && FA_WARPS % (a.H / a.HK) == 0) {  // throughput prefill
-    const uint32_t qb = FA_WARPS / (a.H / a.HK);
-    const size_t fsm = size_t(FA_TILE) * (D + 1) * 4 + 32 + size_t(FA_TILE) * D * 2 + size_t(FA_WARPS) * D * 4;
+    const uint32_t qb = FA_WARPS / (a.H / a.HK) * FA_QPW;  // tokens per CTA
+    const size_t fsm = size_t(FA_TILE) * (D + 1) * 4 + 32 + size_t(FA_TILE) * D * 2 + size_t(FA_WARPS) * FA_QPW * D * 4;
     static bool optin = false;
     if (!optin) {
       if ((e = cudaFuncSetAttribute(fast_attention_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fsm))) != cudaSuccess)

@@ -39,6 +39,8 @@ for mode in ("exact", "fast"):
                  "logits": lg.copy()}
     m.close()
 os.environ.pop("LLMI_PREFILL", None)
+from llm_inference_b200 import ops  # noqa: E402
+ops.set_prefill_mode(False)
 le, lf = res["exact"].pop("logits"), res["fast"].pop("logits")
 agree = 0
 for a, b in zip([res["exact"]["first"]] + res["exact"]["tokens"], [res["fast"]["first"]] + res["fast"]["tokens"]):
