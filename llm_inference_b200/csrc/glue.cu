@@ -11,7 +11,10 @@
 
 #include <type_traits>
 
+#include <algorithm>
 #include <cstdlib>
+
+#include <mma.h>
 
 #include "glue.h"
 #include "launch.cuh"
@@ -435,6 +438,165 @@ __global__ void __launch_bounds__(FA_WARPS * 32) fast_attention_kernel(AttnArgs 
   }
 }
 
+// ---- the same attention on the tensor cores (f16 mma through nvcuda::wmma, fp32 accumulation) ---------------------------
+// The CUDA-core kernel above was 52 % of a 1024-token gemma-3-27b batch once the mat-vecs ran on tcgen05
+// (profiles/r02_notes.md).  Here a CTA of 4 warps owns 64 query rows = 64/G consecutive tokens x the G query heads of one
+// KV head, a warp 16 of them; K / V tiles of 64 positions go through shared memory as f16 (q and k ARE f16 values:
+// the exact prologue rounded them; fast_attn_prep_kernel turns their double-high-word storage into halves once per
+// batch).  Two passes over the KV tiles, so the opaque wmma accumulator layout never has to be rescaled: pass 1
+// S = Q.K^T -> row maxima; pass 2 S again, P = exp(S - max) (f16), row sums, O += P.V in D/16 accumulator fragments
+// that live across the tiles; O / sum -> out.  Same tolerance class as the kernel above (tests cover both).
+__global__ void fast_attn_prep_kernel(AttnArgs a, uint32_t n_tok, __half* __restrict__ qh, __half* __restrict__ kh) {
+  pdl_trigger();
+  pdl_wait();
+  const int T = *a.pos + int(n_tok);  // positions in the cache after this batch's prologue
+  const uint64_t nq = uint64_t(n_tok) * a.H * a.D, nk = uint64_t(a.HK) * a.t_max * a.D;
+  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < nq + nk; i += uint64_t(gridDim.x) * blockDim.x) {
+    if (i < nq) {
+      qh[i] = __float2half_rn(double_hi_to_float(a.qbuf[i]));
+    } else {
+      const uint64_t j = i - nq;
+      const uint32_t t = uint32_t((j / a.D) % a.t_max);
+      if (int(t) < T) kh[j] = __float2half_rn(double_hi_to_float(a.kcache[j]));
+    }
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(128) fast_attention_tc_kernel(AttnArgs a, uint32_t n_tok, const __half* __restrict__ qh,
+                                                                const __half* __restrict__ kh) {
+  using namespace nvcuda;
+  constexpr int LD = D + 8, SLD = 68, PLD = 72, OLD = D + 4;  // leading dimensions: halves, floats, halves, floats
+  extern __shared__ __align__(128) uint8_t fat_smem[];
+  __half* Qs = reinterpret_cast<__half*>(fat_smem);        // [64][LD]
+  __half* Ks = Qs + 64 * LD;                               // [64][LD]
+  __half* Vs = Ks + 64 * LD;                               // [64][LD]
+  float* Ss = reinterpret_cast<float*>(Vs + 64 * LD);      // [4 warps][16][SLD]
+  __half* Ps = reinterpret_cast<__half*>(Ss + 4 * 16 * SLD);  // [4 warps][16][PLD]
+  pdl_trigger();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t hkv = blockIdx.x, G = a.H / a.HK, TPB = 64 / G;
+  const uint32_t tokb = blockIdx.y * TPB;
+  pdl_wait();
+  const int pos0 = *a.pos;
+  const int n_here = int(min(TPB, n_tok - tokb));
+  const int P_max = pos0 + int(tokb) + n_here - 1;
+  for (int i = threadIdx.x; i < 64 * D / 8; i += 128) {  // row r = (token in block) * G + (head in group)
+    const int r = i / (D / 8), c = (i % (D / 8)) * 8;
+    const int tl = r / int(G), g = r % int(G);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (tl < n_here) v = *reinterpret_cast<const uint4*>(qh + (size_t(tokb + tl) * a.H + hkv * G + g) * D + c);
+    *reinterpret_cast<uint4*>(Qs + r * LD + c) = v;
+  }
+  const int rr = lane >> 1, hc = lane & 1;  // this lane's row of the warp tile and its half of the 64 columns
+  const int tl_row = (warp * 16 + rr) / int(G);
+  const int P_row = tl_row < n_here ? pos0 + int(tokb) + tl_row : -1;
+  float* Sw = Ss + warp * 16 * SLD;
+  __half* Pw = Ps + warp * 16 * PLD;
+  const __half* kbase = kh + size_t(hkv) * a.t_max * D;
+  const __half* vbase = a.vcache + size_t(hkv) * a.t_max * D;
+  auto load_tile = [&](const __half* base, __half* dst, int t0, int nt) {
+    for (int i = threadIdx.x; i < 64 * D / 8; i += 128) {
+      const int r = i / (D / 8), c = (i % (D / 8)) * 8;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (r < nt) v = *reinterpret_cast<const uint4*>(base + size_t(t0 + r) * D + c);
+      *reinterpret_cast<uint4*>(dst + r * LD + c) = v;
+    }
+  };
+  auto scores = [&]() {  // Sw[16][64] = Q_w (16 x D) . K^T (D x 64)
+    wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc[4];
+#pragma unroll
+    for (int n = 0; n < 4; ++n) wmma::fill_fragment(acc[n], 0.0f);
+#pragma unroll 4
+    for (int k = 0; k < D / 16; ++k) {
+      wmma::fragment<wmma::matrix_a, 16, 16, 16, __half, wmma::row_major> af;
+      wmma::load_matrix_sync(af, Qs + warp * 16 * LD + k * 16, LD);
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        wmma::fragment<wmma::matrix_b, 16, 16, 16, __half, wmma::col_major> bf;  // (k, n) = Ks[n][k]
+        wmma::load_matrix_sync(bf, Ks + n * 16 * LD + k * 16, LD);
+        wmma::mma_sync(acc[n], af, bf, acc[n]);
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < 4; ++n) wmma::store_matrix_sync(Sw + n * 16, acc[n], SLD, wmma::mem_row_major);
+    __syncwarp();
+  };
+  auto sval = [&](float sc) { return a.softcap > 0.0f ? a.softcap * tanhf(sc / a.softcap) : sc; };
+  // pass 1: row maxima
+  float m_row = -INFINITY;
+  for (int t0 = 0; t0 <= P_max; t0 += 64) {
+    const int nt = min(64, P_max + 1 - t0);
+    __syncthreads();
+    load_tile(kbase, Ks, t0, nt);
+    __syncthreads();
+    if (t0 > pos0 + int(tokb) + (warp * 16 + 15) / int(G)) continue;  // no row of this warp reaches the tile (warp-uniform)
+    scores();
+    float mx = -INFINITY;
+#pragma unroll 8
+    for (int c = 0; c < 32; ++c) {
+      const int col = hc * 32 + c;
+      if (t0 + col <= P_row) mx = fmaxf(mx, sval(Sw[rr * SLD + col]));
+    }
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    m_row = fmaxf(m_row, mx);
+    __syncwarp();
+  }
+  // pass 2: P = exp(S - max), row sums, O += P.V
+  wmma::fragment<wmma::accumulator, 16, 16, 16, float> oacc[D / 16];
+#pragma unroll
+  for (int n = 0; n < D / 16; ++n) wmma::fill_fragment(oacc[n], 0.0f);
+  float l_row = 0.0f;
+  for (int t0 = 0; t0 <= P_max; t0 += 64) {
+    const int nt = min(64, P_max + 1 - t0);
+    __syncthreads();
+    load_tile(kbase, Ks, t0, nt);
+    load_tile(vbase, Vs, t0, nt);
+    __syncthreads();
+    if (t0 > pos0 + int(tokb) + (warp * 16 + 15) / int(G)) continue;
+    scores();
+    float ls = 0.0f;
+#pragma unroll 8
+    for (int c = 0; c < 32; ++c) {
+      const int col = hc * 32 + c;
+      const float p = t0 + col <= P_row ? __expf(sval(Sw[rr * SLD + col]) - m_row) : 0.0f;
+      ls += p;
+      Pw[rr * PLD + col] = __float2half_rn(p);
+    }
+    ls += __shfl_xor_sync(0xffffffffu, ls, 1);
+    l_row += ls;
+    __syncwarp();
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      wmma::fragment<wmma::matrix_a, 16, 16, 16, __half, wmma::row_major> af;
+      wmma::load_matrix_sync(af, Pw + kk * 16, PLD);
+#pragma unroll
+      for (int n = 0; n < D / 16; ++n) {
+        wmma::fragment<wmma::matrix_b, 16, 16, 16, __half, wmma::row_major> bf;  // (k, n) = Vs[k][n]
+        wmma::load_matrix_sync(bf, Vs + kk * 16 * LD + n * 16, LD);
+        wmma::mma_sync(oacc[n], af, bf, oacc[n]);
+      }
+    }
+    __syncwarp();
+  }
+  __syncthreads();  // every warp is done with K / V: their space takes the fp32 output tiles
+  float* Ow = reinterpret_cast<float*>(Ks) + warp * 16 * OLD;
+#pragma unroll
+  for (int n = 0; n < D / 16; ++n) wmma::store_matrix_sync(Ow + n * 16, oacc[n], OLD, wmma::mem_row_major);
+  __syncwarp();
+  if (P_row >= 0) {
+    const float inv = l_row > 0.0f ? 1.0f / l_row : 0.0f;
+    const uint32_t g = uint32_t(warp * 16 + rr) % G;
+    float* o = a.out + size_t(tokb + tl_row) * a.H * D + size_t(hkv * G + g) * D + hc * (D / 2);
+    const float* src = Ow + rr * OLD + hc * (D / 2);
+#pragma unroll 4
+    for (int c = 0; c < D / 2; c += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(src + c);
+      *reinterpret_cast<float4*>(o + c) = make_float4(v.x * inv, v.y * inv, v.z * inv, v.w * inv);
+    }
+  }
+}
+
 // RoPE factors for every (position, pair): ops.cpp:80-83 —
 //   freq = 1.0f / powf(base, float(2i)/n_rot); val = float(pos) * freq / scale; cosf(val), sinf(val)
 __global__ void rope_table_kernel(float2* table, uint32_t t_max, uint32_t D, float base, float scale) {
@@ -664,7 +826,47 @@ static cudaError_t attention_launch(const AttnArgs& a, uint32_t n_tok, cudaStrea
   if (!a.qbuf) return cudaErrorInvalidValue;
   cudaError_t e = llmi_launch(attention_kernel<D, 1>, dim3(a.H, n_tok), dim3(1024), 0, s, a, nbuf);
   if (e != cudaSuccess) return e;
-  if (llmi_gemv_prefill_fast() && D >= 64 && D <= 256 && FA_WARPS % (a.H / a.HK) == 0) {  // throughput prefill
+  if constexpr (D <= 256)
+  if (llmi_gemv_prefill_fast() && D >= 64 && 64 % (a.H / a.HK) == 0 && !getenv("LLMI_FAST_ATTN_NO_TC")) {
+    // throughput prefill, tensor-core form (grow-only f16 scratch for q and K)
+    static __half *qh = nullptr, *kh = nullptr;
+    static size_t qh_n = 0, kh_n = 0;
+    const size_t nq = size_t(n_tok) * a.H * D, nk = size_t(a.HK) * a.t_max * D;
+    if (nq > qh_n || nk > kh_n) {
+      if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+      if (nq > qh_n) {
+        if (qh) cudaFree(qh);
+        qh = nullptr;
+        qh_n = 0;
+        if ((e = cudaMalloc(&qh, nq * 2)) != cudaSuccess) return e;
+        qh_n = nq;
+      }
+      if (nk > kh_n) {
+        if (kh) cudaFree(kh);
+        kh = nullptr;
+        kh_n = 0;
+        if ((e = cudaMalloc(&kh, nk * 2)) != cudaSuccess) return e;
+        kh_n = nk;
+      }
+    }
+    const unsigned pb = unsigned(std::min<size_t>((nq + nk + 255) / 256, 148 * 16));
+    if ((e = llmi_launch(fast_attn_prep_kernel, dim3(pb), dim3(256), 0, s, a, n_tok, qh, kh)) != cudaSuccess) return e;
+    constexpr int LD = D + 8;
+    const size_t fsm = size_t(3) * 64 * LD * 2 + size_t(4) * 16 * 68 * 4 + size_t(4) * 16 * 72 * 2;
+    static bool optin = false;
+    if (!optin) {
+      if ((e = cudaFuncSetAttribute(fast_attention_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fsm))) != cudaSuccess)
+        return e;
+      optin = true;
+    }
+    const uint32_t tpb = 64 / (a.H / a.HK);
+    if ((e = llmi_launch(fast_attention_tc_kernel<D>, dim3(a.HK, (n_tok + tpb - 1) / tpb), dim3(128), fsm, s, a, n_tok,
+                         (const __half*)qh, (const __half*)kh)) != cudaSuccess)
+      return e;
+    if (a.act_kind == ACT_NONE) return cudaSuccess;
+    return llmi_launch_act(a.out, a.H * a.D, a.act_kind, a.act_buf, s, n_tok, a.act_stride);
+  }
+  if (llmi_gemv_prefill_fast() && D >= 64 && D <= 256 && FA_WARPS % (a.H / a.HK) == 0) {  // CUDA-core form
     const uint32_t qb = FA_WARPS / (a.H / a.HK) * FA_QPW;  // tokens per CTA
     const size_t fsm = size_t(FA_TILE) * (D + 1) * 4 + 32 + size_t(FA_TILE) * D * 2 + size_t(FA_WARPS) * FA_QPW * D * 4;
     static bool optin = false;
