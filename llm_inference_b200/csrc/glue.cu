@@ -438,6 +438,63 @@ __global__ void __launch_bounds__(FA_WARPS * 32) fast_attention_kernel(AttnArgs 
   }
 }
 
+// The prologue of a token batch in the throughput mode: q/k RMSNorm, RoPE, q scaling, f16 rounding and the K/V append of
+// attention_body's MODE 1 — the same operations in the same order (two pair sums per lane, the xor-shuffle tree per 32
+// pairs, the 32-pair sums left to right), but one WARP per (token, head) instead of one 1024-thread CTA: MODE 1 was
+// 461 us per 1024-token gemma-3-27b layer batch, 10 % of the fast prompt (profiles/r02_notes.md).
+template <int D>
+__global__ void __launch_bounds__(256) fast_attn_prologue_kernel(AttnArgs a, uint32_t n_tok) {
+  constexpr int HALF = D / 2, NC = (HALF + 31) / 32;
+  pdl_trigger();
+  const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const uint32_t slots = a.H + a.HK, tok = gw / slots, slot = gw % slots;
+  pdl_wait();
+  if (tok >= n_tok) return;
+  const int pos = *a.pos + int(tok);
+  const bool is_q = slot < a.H;
+  const uint32_t head = is_q ? slot : slot - a.H;
+  const float* x = is_q ? a.q + (size_t(tok) * a.H + head) * D : a.k + (size_t(tok) * a.HK + head) * D;
+  const float* wn = is_q ? a.wq_norm : a.wk_norm;
+  float x0[NC], x1[NC];
+  float ss = 0.0f;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int i = int(lane) + 32 * c;
+    x0[c] = i < HALF ? x[i] : 0.0f;
+    x1[c] = i < HALF ? x[i + HALF] : 0.0f;
+    float sq = __fadd_rn(__fmul_rn(x0[c], x0[c]), __fmul_rn(x1[c], x1[c]));
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    ss += sq;
+  }
+  const float sc = rms_scale(ss, D, a.eps);
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int i = int(lane) + 32 * c;
+    if (i >= HALF) continue;
+    const float v0 = __fmul_rn(__fmul_rn(sc, x0[c]), wn[i]), v1 = __fmul_rn(__fmul_rn(sc, x1[c]), wn[i + HALF]);
+    const float2 csn = a.rope_table[size_t(pos) * HALF + i];
+    const float cs = csn.x, sn = csn.y;
+    if (is_q) {
+      const float qa = __fmul_rn(__fmaf_rn(v0, cs, -__fmul_rn(v1, sn)), a.attn_scale);
+      const float qb = __fmul_rn(__fmaf_rn(v0, sn, __fmul_rn(v1, cs)), a.attn_scale);
+      uint32_t* qd = a.qbuf + (size_t(tok) * a.H + head) * D;
+      qd[i] = f16_as_double_hi(__float2half_rn(qa));
+      qd[i + HALF] = f16_as_double_hi(__float2half_rn(qb));
+    } else {
+      const __half ka = __float2half_rn(__fmaf_rn(v0, cs, -__fmul_rn(v1, sn)));
+      const __half kb = __float2half_rn(__fmaf_rn(v0, sn, __fmul_rn(v1, cs)));
+      uint32_t* kd = a.kcache + (size_t(head) * a.t_max + pos) * D;
+      __half* vd = a.vcache + (size_t(head) * a.t_max + pos) * D;
+      const float* v = a.v + (size_t(tok) * a.HK + head) * D;
+      kd[i] = f16_as_double_hi(ka);
+      kd[i + HALF] = f16_as_double_hi(kb);
+      vd[i] = __float2half_rn(v[i]);
+      vd[i + HALF] = __float2half_rn(v[i + HALF]);
+    }
+  }
+}
+
 // ---- the same attention on the tensor cores (f16 mma through nvcuda::wmma, fp32 accumulation) ---------------------------
 // The CUDA-core kernel above was 52 % of a 1024-token gemma-3-27b batch once the mat-vecs ran on tcgen05
 // (profiles/r02_notes.md).  Here a CTA of 4 warps owns 64 query rows = 64/G consecutive tokens x the G query heads of one
@@ -824,7 +881,13 @@ static cudaError_t attention_launch(const AttnArgs& a, uint32_t n_tok, cudaStrea
   const uint32_t nbuf = attention_nbuf(a.t_max, a.D);
   if (n_tok <= 1 && !a.qbuf) return llmi_launch(attention_kernel<D, 0>, dim3(a.H), dim3(1024), smem, s, a, nbuf);
   if (!a.qbuf) return cudaErrorInvalidValue;
-  cudaError_t e = llmi_launch(attention_kernel<D, 1>, dim3(a.H, n_tok), dim3(1024), 0, s, a, nbuf);
+  cudaError_t e;
+  if (llmi_gemv_prefill_fast() && D <= 256 && !getenv("LLMI_FAST_ATTN_NO_TC")) {
+    const uint32_t warps = n_tok * (a.H + a.HK);
+    e = llmi_launch(fast_attn_prologue_kernel<D>, dim3((warps + 7) / 8), dim3(256), 0, s, a, n_tok);
+  } else {
+    e = llmi_launch(attention_kernel<D, 1>, dim3(a.H, n_tok), dim3(1024), 0, s, a, nbuf);
+  }
   if (e != cudaSuccess) return e;
   if constexpr (D <= 256)
   if (llmi_gemv_prefill_fast() && D >= 64 && 64 % (a.H / a.HK) == 0 && !getenv("LLMI_FAST_ATTN_NO_TC")) {

@@ -880,7 +880,7 @@ int load_impl(llmi_model_s* m, const uint8_t* image, uint64_t size, uint32_t t_m
   const size_t mx = std::max<size_t>({E, F, HD});
   m->batch = 256;  // >= 128 tokens per batch go through the tensor-core mat-vec (gemv.cu launch_tokens)
   // throughput prefill (gemm_bf16.cuh) dequantizes a matrix once per batch: larger batches amortize it
-  if (llmi_gemv_prefill_fast()) m->batch = 1024;
+  if (llmi_gemv_prefill_fast()) m->batch = 2048;
   if (const char* e = getenv("LLMI_PREFILL_BATCH")) m->batch = uint32_t(std::max(1, atoi(e)));
   if (m->batch > t_max) m->batch = t_max;
   const size_t B = m->batch;
