@@ -792,17 +792,19 @@ cudaError_t llmi_launch_embed(const EmbedArgs& a, const int32_t* token, float sc
                      ll ? *ll : LLCtx(), ll_off);
 }
 
-// LLMI_NORM_CLUSTER=0 keeps the single-CTA kernel (A/B); both produce the same bits.
-static int g_norm_cluster = -1;
+// LLMI_NORM_CLUSTER=0 keeps the single-CTA kernel (A/B, re-read by every llmi_model_load); both produce the same bits.
+static int g_norm_cluster = 1;
+void llmi_glue_read_env() {
+  const char* e = getenv("LLMI_NORM_CLUSTER");
+  g_norm_cluster = (e && e[0] == '0') ? 0 : 1;
+}
 cudaError_t llmi_launch_norm_act(const NormArgs& a, cudaStream_t s) {
   const int threads = a.n >= 2048 ? 1024 : 512;
-  if (g_norm_cluster < 0) {
-    const char* e = getenv("LLMI_NORM_CLUSTER");
-    g_norm_cluster = (e && e[0] == '0') ? 0 : 1;
-  }
   const uint32_t n_tok = a.n_tok ? a.n_tok : 1;
   const bool kind_ok = a.act_kind != ACT_Q8_K || a.xn_out != nullptr;
-  if (g_norm_cluster && kind_ok && a.n <= uint32_t(NORM_PER * threads)) {
+  // the cluster pays from ~2 elements per logical thread on: at E = 1152 (one element per thread) its barriers cost more than
+  // the single CTA's issue pressure (3.0 vs 3.6 us per launch on the step timeline), at E = 5376 it is 6.0 vs 3.8 us
+  if (g_norm_cluster && kind_ok && a.n >= 2048 && a.n <= uint32_t(NORM_PER * threads)) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(n_tok * NORM_CL);
     cfg.blockDim = dim3(threads / NORM_CL);

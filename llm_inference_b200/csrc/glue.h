@@ -71,6 +71,7 @@ struct AttnArgs {
 cudaError_t llmi_launch_embed(const EmbedArgs& a, const int32_t* token, float scale, float* h, cudaStream_t s,
                               uint32_t n_tok = 1, const LLCtx* ll = nullptr, uint32_t ll_off = 0);
 cudaError_t llmi_launch_norm_act(const NormArgs& a, cudaStream_t s);
+void llmi_glue_read_env();  // LLMI_NORM_CLUSTER (re-read by every llmi_model_load)
 cudaError_t llmi_launch_act(const float* x, uint32_t n, int kind, uint8_t* buf, cudaStream_t s, uint32_t n_tok = 1,
                             uint32_t act_stride = 0);
 cudaError_t llmi_launch_rope_table(float2* table, uint32_t t_max, uint32_t D, float base, float scale, cudaStream_t s);

@@ -1049,6 +1049,7 @@ int llmi_model_load_shard(const void* gguf_image, uint64_t size, uint32_t max_po
     return llmi_fail(LLMI_ERR_ARG, "llmi_model_load_shard: need 1 <= world <= 8 and 0 <= rank < world");
   if (max_positions == 0) max_positions = 4096;
   llmi_gemv_read_env();
+  llmi_glue_read_env();
   std::unique_ptr<llmi_model_s> m(new llmi_model_s());
   int rc;
   try {

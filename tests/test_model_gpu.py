@@ -154,6 +154,35 @@ def test_batched_prefill_is_bitwise_the_token_by_token_path(gpu_ops, monkeypatch
     assert outs["batched"][1] < outs["single"][1] / 4  # 3 batches of launches instead of 37 tokens' worth
 
 
+@pytest.mark.parametrize("wt,et", [(synth.Q4_0, synth.F16), ("q4_k_m", synth.Q6_K)])
+def test_cluster_norm_is_bitwise_the_single_cta_norm(gpu_ops, monkeypatch, wt, et):
+    """norm_act_cluster_kernel (8 CTAs, distributed shared memory; used from E = 2048 on) spreads the single-CTA kernel's
+    1024 logical threads over a cluster with the same per-thread sums, shuffle trees and left-to-right warp sums: logits
+    of a prompt (batched: one cluster per token) and of the decode steps after it must be bit-identical, for the Q8_0
+    (registers) and the Q8_K (through the fp32 copy) activation emitters."""
+    from llm_inference_b200.model import Model
+    dims = synth.GemmaDims("wide", 2, 2560, 1024, 4, 2, 256, 640)
+    img = synth.build_gemma3_gguf(dims, wt, et, seed=31)
+    prompt = (np.arange(19, dtype=np.int32) * 11 + 5) % dims.vocab
+    outs = {}
+    for mode in ("cluster", "single"):
+        monkeypatch.delenv("LLMI_NORM_CLUSTER", raising=False)
+        if mode == "single":
+            monkeypatch.setenv("LLMI_NORM_CLUSTER", "0")
+        m = Model(img, max_positions=48)
+        lg = [m.forward(prompt, 0)]
+        pos = len(prompt)
+        for _ in range(3):
+            lg.append(m.forward([int(lg[-1].argmax())], pos))
+            pos += 1
+        toks, _ = m.decode_greedy(int(lg[-1].argmax()), pos, 6)
+        outs[mode] = (np.stack(lg), toks)
+        m.close()
+    monkeypatch.delenv("LLMI_NORM_CLUSTER", raising=False)
+    assert np.array_equal(outs["cluster"][0].view(np.uint32), outs["single"][0].view(np.uint32))
+    assert np.array_equal(outs["cluster"][1], outs["single"][1])
+
+
 @pytest.mark.parametrize("wt,et,hd", [(synth.Q4_0, synth.F16, 128), ("q4_k_m", synth.Q6_K, 256), (synth.Q8_0, synth.Q8_0, 64)])
 def test_throughput_prefill_mode_stays_within_its_tolerance(gpu_ops, monkeypatch, wt, et, hd):
     """LLMI_PREFILL=fast (opt-in): prompts of >= 64 tokens go through the dequantize-to-bf16 tcgen05 GEMM and the fp32
