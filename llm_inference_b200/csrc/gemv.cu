@@ -1215,14 +1215,12 @@ GemvArgs llmi_gemv_args(const llmi_weight_s& w) {
   return make_args(w, none, nullptr);
 }
 
-// Set by llmi_launch_gemv_argmax for the duration of one launch.
-static unsigned long long* g_argmax_key = nullptr;
-static float g_argmax_softcap = 0.0f;
-
 // One launch for up to GEMV_MAX_BATCH matrices of the SAME format consuming the
 // same prepared activation (q/k/v, gate/up): the grid is the union of their CTAs.
-cudaError_t llmi_launch_gemv_batch(const llmi_weight_s* const* ws, float* const* outs, int n, const llmi_act_s& a,
-                                   cudaStream_t s, const GemvLL* ll) {
+// key / softcap: the optional fused epilogue of the logits mat-vec (llmi_launch_gemv_argmax).
+static cudaError_t launch_gemv_batch_impl(const llmi_weight_s* const* ws, float* const* outs, int n, const llmi_act_s& a,
+                                          cudaStream_t s, const GemvLL* ll, unsigned long long* g_argmax_key,
+                                          float g_argmax_softcap) {
   if (n < 1 || n > GEMV_MAX_BATCH) return cudaErrorInvalidValue;
   GemvArgs args[GEMV_MAX_BATCH];
   int m = 0;
@@ -1247,6 +1245,11 @@ cudaError_t llmi_launch_gemv_batch(const llmi_weight_s* const* ws, float* const*
     case LLMI_BF16: return launch_batch<BF16>(args, m, s, ll);
     default: return cudaErrorInvalidValue;
   }
+}
+
+cudaError_t llmi_launch_gemv_batch(const llmi_weight_s* const* ws, float* const* outs, int n, const llmi_act_s& a,
+                                   cudaStream_t s, const GemvLL* ll) {
+  return launch_gemv_batch_impl(ws, outs, n, a, s, ll, nullptr, 0.0f);
 }
 
 // Bytes [offset, offset + budget) of the concatenation of up to two matrices, taken as the same fraction window of
@@ -1384,14 +1387,9 @@ cudaError_t llmi_launch_gemv(const llmi_weight_s& w, const llmi_act_s& a, float*
 // zeroes *key before and decodes it after (finish_token_kernel, glue.cu).
 cudaError_t llmi_launch_gemv_argmax(const llmi_weight_s& w, const llmi_act_s& a, float* out,
                                     unsigned long long* key, float softcap, cudaStream_t s, const GemvLL* ll) {
-  g_argmax_key = key;
-  g_argmax_softcap = softcap;
   const llmi_weight_s* ws[1] = {&w};
   float* outs[1] = {out};
-  const cudaError_t e = llmi_launch_gemv_batch(ws, outs, 1, a, s, ll);
-  g_argmax_key = nullptr;
-  g_argmax_softcap = 0.0f;
-  return e;
+  return launch_gemv_batch_impl(ws, outs, 1, a, s, ll, key, softcap);
 }
 
 cudaError_t llmi_launch_block_dots(const llmi_weight_s& w, const llmi_act_s& a, int32_t* dots_dev, cudaStream_t s) {
