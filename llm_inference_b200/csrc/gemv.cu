@@ -648,6 +648,8 @@ cudaError_t launch_ring(const GemvArgs* args, int n, cudaStream_t s, const GemvL
   b.n = n;
   b.total = total;
   b.part_items = uint32_t((uint64_t(total) + ctas - 1) / ctas);
+  static const bool late = getenv("LLMI_RING_LATE") && getenv("LLMI_RING_LATE")[0] == '1';
+  b.late_fill = late ? 1u : 0u;
   uint32_t slabs = 0;
   for (int i = 0; i < GEMV_MAX_BATCH; ++i) {
     b.a[i] = args[i < n ? i : 0];

@@ -131,6 +131,7 @@ struct RingBatch {
   int n;
   uint32_t total;   // work items of the launch = (slabs of all matrices) x chunks
   uint32_t part_items;  // capacity of the chunk-partial array of a CTA (items)
+  uint32_t late_fill;   // 1: do not touch HBM before griddepcontrol.wait (A/B knob)
   uint2* fix;       // [gridDim.x][chunks][8] flagged chunk partials of slabs split across CTAs; all zero between launches
   LLPeers peers;
   LLTag tag;
@@ -330,6 +331,7 @@ __global__ void __launch_bounds__(W * 32) gemv_ring_kernel(const RingBatch batch
     if (i_new - W < n_tail && i_new >= n_tail) c.init(batch, item_of(i_new), J);
     else c.template advance<W>(batch, J);
   };
+  if (batch.late_fill) pdl_wait();  // A/B knob (LLMI_RING_LATE=1): rings filled only once the predecessor has finished
 #pragma unroll
   for (int s = 0; s < D; ++s) {
     fill(cf, i_f < n_my, s);
