@@ -159,6 +159,39 @@ __global__ void fast_pack_act_kernel(const uint8_t* __restrict__ act, uint32_t a
   }
 }
 
+// hidden = gelu_tanh(gate) * up of a token batch, straight into the down-projection's bf16 operand order — in this mode
+// the GEGLU stage neither quantizes (geglu_act_kernel: 11 % of a fast prompt, most of it the Q8_0 quantizer's shuffles
+// and IEEE divisions) nor takes the detour through fast_pack_act_kernel.  The reference's formula (model.cpp:887-901).
+__global__ void fast_geglu_pack_kernel(const float* __restrict__ gate, const float* __restrict__ up, uint32_t n_cols, uint32_t n_tok,
+                                       uint32_t tnf, uint32_t n_ttiles, uint32_t nkb, uint4* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
+  const uint32_t per_stage = tnf * 8;
+  const uint64_t total = uint64_t(n_ttiles) * nkb * per_stage;
+  for (uint64_t o = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; o < total; o += uint64_t(gridDim.x) * blockDim.x) {
+    const uint32_t in = uint32_t(o % per_stage);
+    const uint64_t tb = o / per_stage;
+    const uint32_t kb = uint32_t(tb % nkb), tt = uint32_t(tb / nkb);
+    const uint32_t t = in & 7, tg = (in >> 3) % (tnf / 8), kc = in / tnf;
+    const uint32_t tok = tt * tnf + tg * 8 + t, k0 = (kb * 8 + kc) * 8;
+    float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (tok < n_tok) {
+      const float4* g4 = reinterpret_cast<const float4*>(gate + size_t(tok) * n_cols + k0);
+      const float4* u4 = reinterpret_cast<const float4*>(up + size_t(tok) * n_cols + k0);
+      const float4 ga = g4[0], gb = g4[1], ua = u4[0], ub = u4[1];
+      const float gs[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w}, us[8] = {ua.x, ua.y, ua.z, ua.w, ub.x, ub.y, ub.z, ub.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float x = gs[i];
+        const float inner = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+        const float th = 1.0f - 2.0f / (__expf(2.0f * inner) + 1.0f);  // tanh; exp overflow -> 1, underflow -> -1
+        v[i] = 0.5f * x * (1.0f + th) * us[i];
+      }
+    }
+    out[o] = fastmm::pack8(v);
+  }
+}
+
 // grid = (token tiles, row tiles) — the token tiles of one row tile run side by side, so its dequantized weights are
 // read from DRAM once and from L2 by the others (with the tiles the other way round the 21504 x 5376 matrix was read
 // once per token tile: 945 MB of DRAM reads for 231 MB of weights, profiles/r02_ncu_gemm_bf16_gate27b.csv);

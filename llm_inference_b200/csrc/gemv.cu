@@ -931,7 +931,8 @@ constexpr uint32_t body_type() {
 
 // Every matrix of the batch: dequantize -> (activations packed once) -> tcgen05 bf16 GEMM.
 template <class B>
-cudaError_t launch_fast(const GemvArgs* args, int n, cudaStream_t s) {
+cudaError_t launch_fast(const GemvArgs* args, int n, cudaStream_t s, const float* geglu_gate = nullptr,
+                        const float* geglu_up = nullptr) {
   const uint32_t type = body_type<B>(), K = args[0].n_cols, n_tok = args[0].n_tok;
   const uint32_t nkb = K / fastmm::KB;
   const uint32_t tnf = n_tok > 128 ? 256u : 128u, n_tt = (n_tok + tnf - 1) / tnf;
@@ -963,8 +964,13 @@ cudaError_t launch_fast(const GemvArgs* args, int n, cudaStream_t s) {
   {
     const uint64_t items = uint64_t(n_tt) * nkb * tnf * 8;
     const unsigned blocks = unsigned(std::min<uint64_t>((items + 255) / 256, uint64_t(g_sm_count) * 16));
-    cudaError_t e = llmi_launch(fast_pack_act_kernel, dim3(blocks), dim3(256), 0, s, args[0].act, args[0].act_stride, kind, K,
-                                n_tok, tnf, n_tt, nkb, reinterpret_cast<uint4*>(g_fast_x));
+    cudaError_t e;
+    if (geglu_gate)  // the activation IS gelu(gate) * up of the two fp32 batches: no quantized detour
+      e = llmi_launch(fast_geglu_pack_kernel, dim3(blocks), dim3(256), 0, s, geglu_gate, geglu_up, K, n_tok, tnf, n_tt, nkb,
+                      reinterpret_cast<uint4*>(g_fast_x));
+    else
+      e = llmi_launch(fast_pack_act_kernel, dim3(blocks), dim3(256), 0, s, args[0].act, args[0].act_stride, kind, K, n_tok, tnf,
+                      n_tt, nkb, reinterpret_cast<uint4*>(g_fast_x));
     if (e != cudaSuccess) return e;
   }
   for (int i = 0; i < n; ++i) {
@@ -1373,6 +1379,27 @@ cudaError_t llmi_launch_gemv_tokens(const llmi_weight_s* const* ws, float* const
     case LLMI_Q6_K: return launch_tokens<Q6_K>(args, m, s);
     case LLMI_F16: return launch_tokens<F16>(args, m, s);
     case LLMI_BF16: return launch_tokens<BF16>(args, m, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// Throughput prefill only: out[token][row] = W . (gelu_tanh(gate[token]) * up[token]) for a token batch — ffn_down fed by
+// the fp32 gate / up batches ([n_tok][n_cols] each) without the quantized GEGLU stage in between (gemm_bf16.cuh).
+cudaError_t llmi_launch_fast_ffn_down(const llmi_weight_s& w, const float* gate, const float* up, float* out, uint32_t out_stride,
+                                      uint32_t n_tok, cudaStream_t s) {
+  if (!g_prefill_fast || w.n_cols % fastmm::KB || w.n_slabs == 0) return cudaErrorInvalidValue;
+  llmi_act_s none;
+  GemvArgs g = make_args(w, none, out);
+  g.n_tok = n_tok;
+  g.out_stride = out_stride;
+  switch (w.type) {
+    case LLMI_Q4_0: return launch_fast<Q4_0>(&g, 1, s, gate, up);
+    case LLMI_Q8_0: return launch_fast<Q8_0>(&g, 1, s, gate, up);
+    case LLMI_Q5_0: return launch_fast<Q5_0>(&g, 1, s, gate, up);
+    case LLMI_Q4_K: return launch_fast<Q4_K>(&g, 1, s, gate, up);
+    case LLMI_Q6_K: return launch_fast<Q6_K>(&g, 1, s, gate, up);
+    case LLMI_F16: return launch_fast<F16>(&g, 1, s, gate, up);
+    case LLMI_BF16: return launch_fast<BF16>(&g, 1, s, gate, up);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -181,6 +181,8 @@ void llmi_gemv_set_shape(int warps, int slabs_per_cta);  // 0 = heuristic
 void llmi_gemv_set_ring(int mode, int ctas_per_sm, int depth, int warps);
 // throughput prefill (gemm_bf16.cuh): token batches of >= 64 go through the dequantize-to-bf16 tcgen05 GEMM (not bit-exact)
 void llmi_gemv_set_prefill_fast(int on);
+cudaError_t llmi_launch_fast_ffn_down(const llmi_weight_s& w, const float* gate, const float* up, float* out, uint32_t out_stride,
+                                      uint32_t n_tok, cudaStream_t s);  // fast mode: ffn_down fed by gelu(gate) * up directly
 int llmi_gemv_prefill_fast();
 cudaError_t llmi_launch_gemv_argmax(const llmi_weight_s& w, const llmi_act_s& a, float* out, unsigned long long* key,
                                     float softcap, cudaStream_t s, const GemvLL* ll = nullptr);

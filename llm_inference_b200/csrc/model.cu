@@ -474,10 +474,15 @@ int run_batch(llmi_model_s* m, const int32_t* toks, uint32_t n_tok, bool want_lo
     }
     M_RC(gemv_tokens_group(m, {w.gate, w.up}, {m->gate, m->up}, {F, F}, m->bact_E, E, n_tok));
     const int kd = llmi_act_kind_for(w.down->type);
-    M_TRY(llmi_launch_geglu_act(m->gate, m->up, F, kd, get_bact(m, m->bact_F, kd, F), nullptr, s, n_tok,
-                                uint32_t(act_bytes(kd, F))));
-    m->prefill_launches++;
-    M_RC(gemv_tokens_group(m, {w.down}, {m->ffn_out}, {E}, m->bact_F, F, n_tok));
+    if (llmi_gemv_prefill_fast() && n_tok >= 64 && F % 64 == 0) {  // throughput mode: GEGLU straight into ffn_down's operand
+      M_TRY(llmi_launch_fast_ffn_down(*w.down, m->gate, m->up, m->ffn_out, E, n_tok, s));
+      m->prefill_launches += 3;
+    } else {
+      M_TRY(llmi_launch_geglu_act(m->gate, m->up, F, kd, get_bact(m, m->bact_F, kd, F), nullptr, s, n_tok,
+                                  uint32_t(act_bytes(kd, F))));
+      m->prefill_launches++;
+      M_RC(gemv_tokens_group(m, {w.down}, {m->ffn_out}, {E}, m->bact_F, F, n_tok));
+    }
     {
       NormArgs na;
       na.y = m->ffn_out; na.w_post = w.post_ffw_norm; na.h = m->h; na.n = E; na.eps = m->eps; na.xn_out = m->xn;
