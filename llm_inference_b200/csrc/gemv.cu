@@ -643,8 +643,9 @@ bool ring_wanted(const GemvArgs* args, int n) {
 
 template <class B>
 cudaError_t launch_ring(const GemvArgs* args, int n, cudaStream_t s, const GemvLL* ll, uint32_t ctas, int D, uint32_t total,
-                        size_t smem) {
+                        size_t smem, const RingNorm* norm = nullptr) {
   RingBatch b;
+  if (norm) b.norm = *norm;
   b.n = n;
   b.total = total;
   b.part_items = uint32_t((uint64_t(total) + ctas - 1) / ctas);
@@ -665,6 +666,12 @@ cudaError_t launch_ring(const GemvArgs* args, int n, cudaStream_t s, const GemvL
   cudaError_t e = ring_fix_for(s, &b.fix);
   if (e != cudaSuccess) return e;
   const dim3 grid(ctas), block(g_ring_w * 32);
+  if (norm) {  // the RMSNorm stage as the kernel's prologue: 16 warps, single GPU (gemv_ring.cuh ring_norm_prologue)
+    if (g_ring_w != 16 || ll) return cudaErrorNotSupported;
+    if (D == 2) return llmi_launch(gemv_ring_kernel<B, 16, 2, false, true>, grid, block, smem, s, b);
+    if (D == 3) return llmi_launch(gemv_ring_kernel<B, 16, 3, false, true>, grid, block, smem, s, b);
+    return cudaErrorNotSupported;
+  }
 #define LLMI_RING_CASE(WW, DD)                                                                               \
   if (g_ring_w == WW && D == DD)                                                                             \
     return ll ? llmi_launch(gemv_ring_kernel<B, WW, DD, true>, grid, block, smem, s, b)                      \
@@ -690,6 +697,12 @@ cudaError_t ring_optin() {
   LLMI_RING_OPT(16, 2, false); LLMI_RING_OPT(16, 3, false);
   LLMI_RING_OPT(16, 2, true); LLMI_RING_OPT(16, 3, true);
 #undef LLMI_RING_OPT
+  if (std::is_same<B, BodyQ4_0>::value || std::is_same<B, BodyQ8_0>::value) {  // the norm prologue emits Q8_0 activations
+    if ((e = cudaFuncSetAttribute(gemv_ring_kernel<B, 16, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  int(RING_MAX_SMEM))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(gemv_ring_kernel<B, 16, 3, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  int(RING_MAX_SMEM))) != cudaSuccess) return e;
+  }
   return cudaSuccess;
 }
 
@@ -1381,6 +1394,39 @@ cudaError_t llmi_launch_gemv_tokens(const llmi_weight_s* const* ws, float* const
     case LLMI_BF16: return launch_tokens<BF16>(args, m, s);
     default: return cudaErrorInvalidValue;
   }
+}
+
+// The RMSNorm stage that feeds a batch of mat-vecs, fused into their launch as the ring kernel's prologue
+// (gemv_ring.cuh): norm_act_kernel's stage — a 5 us hand-over + single-SM latency chain between two mat-vecs — becomes
+// ~1.5 us of redundant work on every SM inside the consumer.  Bit-identical to norm_act_kernel + llmi_launch_gemv_batch.
+// cudaErrorNotSupported: the fused form does not apply to this launch (the caller runs the two kernels instead).
+cudaError_t llmi_launch_gemv_batch_norm(const llmi_weight_s* const* ws, float* const* outs, int n, const float* y,
+                                        const float* w_post, const float* h_in, float* h_out, const float* w_norm, uint32_t n_cols,
+                                        double eps, cudaStream_t s) {
+  if (n < 1 || n > GEMV_MAX_BATCH || g_ring_mode == 1 || !y || h_in == h_out) return cudaErrorNotSupported;
+  const uint32_t type = ws[0]->type;
+  if (type != LLMI_Q4_0 && type != LLMI_Q8_0) return cudaErrorNotSupported;
+  const uint32_t T = n_cols >= 2048 ? 1024u : 512u;
+  if (n_cols % 32 || n_cols > T * RING_NORM_PER) return cudaErrorNotSupported;
+  llmi_act_s a;
+  a.kind = ACT_Q8_0;
+  a.n = n_cols;
+  GemvArgs args[GEMV_MAX_BATCH];
+  for (int i = 0; i < n; ++i) {
+    if (ws[i]->type != type || ws[i]->n_cols != n_cols || ws[i]->n_slabs == 0) return cudaErrorNotSupported;
+    args[i] = make_args(*ws[i], a, outs[i]);
+  }
+  RingNorm nm;
+  nm.y = y; nm.w_post = w_post; nm.h_in = h_in; nm.h_out = h_out; nm.w = w_norm; nm.n = n_cols; nm.T = T; nm.eps = eps;
+  uint32_t rc = 0, rt = 0;
+  int rd = 0;
+  size_t rs = 0;
+  if (type == LLMI_Q4_0) {
+    if (!(g_ring_mode == 2 || ring_wanted<Q4_0>(args, n)) || !ring_plan<Q4_0>(args, n, rc, rd, rt, rs)) return cudaErrorNotSupported;
+    return launch_ring<Q4_0>(args, n, s, nullptr, rc, rd, rt, rs, &nm);
+  }
+  if (!(g_ring_mode == 2 || ring_wanted<Q8_0>(args, n)) || !ring_plan<Q8_0>(args, n, rc, rd, rt, rs)) return cudaErrorNotSupported;
+  return launch_ring<Q8_0>(args, n, s, nullptr, rc, rd, rt, rs, &nm);
 }
 
 // Throughput prefill only: out[token][row] = W . (gelu_tanh(gate[token]) * up[token]) for a token batch — ffn_down fed by

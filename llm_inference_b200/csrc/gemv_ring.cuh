@@ -125,6 +125,18 @@ struct RingLds<BodyHalf<BF>> {
   }
 };
 
+// Optional prologue of the ring kernel: the RMSNorm stage that produces its activation (norm_act_kernel's arithmetic:
+// h' = h + (rms_scale(y) * y) * w_post; xn = (rms_scale(h') * h') * w; Q8_0(xn)), run by EVERY CTA on its own copy.
+struct RingNorm {
+  const float* y = nullptr;       // output of the previous mat-vec
+  const float* w_post = nullptr;  // its post-norm weight (nullptr: h' = h + y)
+  const float* h_in = nullptr;    // residual stream before the stage
+  float* h_out = nullptr;         // ... after it: ANOTHER buffer (CTA 0 writes it while the other CTAs still read h_in)
+  const float* w = nullptr;       // norm weight of the stage that feeds the mat-vec
+  uint32_t n = 0, T = 0;          // elements; logical threads of norm_act_kernel (512 / 1024)
+  double eps = 0.0;
+};
+
 struct RingBatch {
   GemvArgs a[GEMV_MAX_BATCH];          // same format, same activation => same K, nb, units, chunks
   uint32_t slab_end[GEMV_MAX_BATCH];   // exclusive prefix of slabs per matrix
@@ -132,6 +144,7 @@ struct RingBatch {
   uint32_t total;   // work items of the launch = (slabs of all matrices) x chunks
   uint32_t part_items;  // capacity of the chunk-partial array of a CTA (items)
   uint32_t late_fill;   // 1: do not touch HBM before griddepcontrol.wait (A/B knob)
+  RingNorm norm;        // PRO instantiations only
   uint2* fix;       // [gridDim.x][chunks][8] flagged chunk partials of slabs split across CTAs; all zero between launches
   LLPeers peers;
   LLTag tag;
@@ -265,12 +278,92 @@ struct RingCursor {
   }
 };
 
-template <class B, int W, int D, bool PUSH>
-__global__ void __launch_bounds__(W * 32) gemv_ring_kernel(const RingBatch batch) {
+constexpr int RING_NORM_PER = 6;  // elements per logical thread (norm_act_kernel's NORM_PER)
+// norm_act_kernel's arithmetic for the T = 512 / 1024 LOGICAL threads of that kernel, played by the W * 32 physical
+// threads of this CTA (thread t plays logical threads t, t + W * 32, ...): the same per-thread sums, the same
+// xor-shuffle tree per logical warp, the T/32 warp sums left to right, the same quantizer per 32-element block —
+// bit for bit the activation the separate kernel would have left in global memory, written to `act` (shared memory).
+template <int W>
+__device__ __forceinline__ void ring_norm_prologue(const RingNorm& nm, uint8_t* act, float* red1, float* red2) {
+  constexpr int PT = W * 32, MAXP = 1024 / PT;
+  const uint32_t n = nm.n, T = nm.T;
+  const int NP = int(T) / PT, NW = int(T) / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float yv[MAXP][RING_NORM_PER], hv[MAXP][RING_NORM_PER];
+#pragma unroll
+  for (int p = 0; p < MAXP; ++p)
+#pragma unroll
+    for (int k = 0; k < RING_NORM_PER; ++k) {
+      const uint32_t i = threadIdx.x + uint32_t(p) * PT + uint32_t(k) * T;
+      const bool ok = p < NP && i < n;
+      hv[p][k] = ok ? nm.h_in[i] : 0.0f;
+      yv[p][k] = ok ? nm.y[i] : 0.0f;
+    }
+#pragma unroll
+  for (int p = 0; p < MAXP; ++p) {
+    float ss = 0.0f;
+#pragma unroll
+    for (int k = 0; k < RING_NORM_PER; ++k) ss += __fmul_rn(yv[p][k], yv[p][k]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (lane == 0 && p < NP) red1[warp + p * W] = ss;
+  }
+  __syncthreads();
+  {
+    float tot = 0.0f;
+    for (int i = 0; i < NW; ++i) tot += red1[i];
+    const float sc = rms_scale(tot, n, nm.eps);
+#pragma unroll
+    for (int p = 0; p < MAXP; ++p)
+#pragma unroll
+      for (int k = 0; k < RING_NORM_PER; ++k) {
+        const uint32_t i = threadIdx.x + uint32_t(p) * PT + uint32_t(k) * T;
+        const bool ok = p < NP && i < n;
+        const float add = nm.w_post ? __fmul_rn(__fmul_rn(sc, yv[p][k]), ok ? nm.w_post[i] : 0.0f) : yv[p][k];
+        hv[p][k] = __fadd_rn(hv[p][k], add);
+        if (ok && blockIdx.x == 0) nm.h_out[i] = hv[p][k];
+      }
+  }
+#pragma unroll
+  for (int p = 0; p < MAXP; ++p) {
+    float ss = 0.0f;
+#pragma unroll
+    for (int k = 0; k < RING_NORM_PER; ++k) ss += __fmul_rn(hv[p][k], hv[p][k]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (lane == 0 && p < NP) red2[warp + p * W] = ss;
+  }
+  __syncthreads();
+  float tot = 0.0f;
+  for (int i = 0; i < NW; ++i) tot += red2[i];
+  const float sc = rms_scale(tot, n, nm.eps);
+#pragma unroll
+  for (int p = 0; p < MAXP; ++p) {
+    if (p >= NP) break;
+    float xv[RING_NORM_PER];
+    bool live[RING_NORM_PER];
+    uint32_t blk[RING_NORM_PER];
+    const uint32_t lw = uint32_t(warp + p * W);  // logical warp: pass k holds block k * NW + lw
+#pragma unroll
+    for (int k = 0; k < RING_NORM_PER; ++k) {
+      const uint32_t i = threadIdx.x + uint32_t(p) * PT + uint32_t(k) * T;
+      xv[k] = __fmul_rn(__fmul_rn(sc, hv[p][k]), i < n ? nm.w[i] : 0.0f);
+      live[k] = lw * 32u + uint32_t(k) * T < n;
+      blk[k] = uint32_t(k) * uint32_t(NW) + lw;
+    }
+    warp_quantize_q8_0_multi<RING_NORM_PER>(xv, live, blk, n, act, lane);
+  }
+  __syncthreads();
+}
+
+template <class B, int W, int D, bool PUSH, bool PRO = false>
+// (minimum CTAs per SM = 1024 threads' worth: caps the kernel at 64 registers so that two 16-warp or four 8-warp CTAs fit)
+__global__ void __launch_bounds__(W * 32, 1024 / (W * 32)) gemv_ring_kernel(const RingBatch batch) {
   using G = RingGeo<B>;
   using F = RingFmt<B>;
   extern __shared__ __align__(128) uint8_t smem[];  // [W*D slots][activation][chunk partials of this CTA]
   __shared__ __align__(8) uint64_t bars[1];         // activation staging
+  __shared__ float red1[PRO ? 32 : 1], red2[PRO ? 32 : 1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_trigger();
   TL_ENTER(2);
@@ -344,11 +437,15 @@ __global__ void __launch_bounds__(W * 32) gemv_ring_kernel(const RingBatch batch
   // the activation vector is the predecessor's output
   pdl_wait();
   TL_MARK(1);
-  if (threadIdx.x == 0) {
-    mbar_expect_tx(&bars[0], a0.act_bytes);
-    bulk_g2s(sm_act, a0.act, a0.act_bytes, &bars[0]);
+  if constexpr (PRO) {
+    ring_norm_prologue<W>(batch.norm, sm_act, red1, red2);
+  } else {
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(&bars[0], a0.act_bytes);
+      bulk_g2s(sm_act, a0.act, a0.act_bytes, &bars[0]);
+    }
+    mbar_wait(&bars[0], 0);
   }
-  mbar_wait(&bars[0], 0);
   TL_MARK(3);
   const uint32_t act_s = smem_s + act_off;
   int s = 0;

@@ -179,6 +179,11 @@ void llmi_gemv_set_shape(int warps, int slabs_per_cta);  // 0 = heuristic
 // persistent bulk-copy-fed kernel (gemv_ring.cuh): mode 0 heuristic / 1 never / 2 wherever it fits; CTAs per SM and
 // ring slots per warp (0 = default)
 void llmi_gemv_set_ring(int mode, int ctas_per_sm, int depth, int warps);
+// norm_act_kernel's stage as the prologue of the mat-vec launch it feeds (ring kernel only): cudaErrorNotSupported when
+// the fused form does not apply — the caller then launches llmi_launch_norm_act + llmi_launch_gemv_batch
+cudaError_t llmi_launch_gemv_batch_norm(const llmi_weight_s* const* ws, float* const* outs, int n, const float* y,
+                                        const float* w_post, const float* h_in, float* h_out, const float* w_norm, uint32_t n_cols,
+                                        double eps, cudaStream_t s);
 // throughput prefill (gemm_bf16.cuh): token batches of >= 64 go through the dequantize-to-bf16 tcgen05 GEMM (not bit-exact)
 void llmi_gemv_set_prefill_fast(int on);
 cudaError_t llmi_launch_fast_ffn_down(const llmi_weight_s& w, const float* gate, const float* up, float* out, uint32_t out_stride,

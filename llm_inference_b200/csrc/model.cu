@@ -72,6 +72,10 @@ struct llmi_model_s {
   bool pf_used = false;
   size_t pf_mb[4] = {48, 24, 24, 24};
   bool prefill_ok = true;
+  float* h2 = nullptr;     // second residual buffer: a norm stage fused into a mat-vec launch reads one and writes the other
+  bool fuse_norm = false;  // LLMI_FUSE_NORM=1: norm stages as prologues of the ring mat-vec launches they feed.  Bit-identical, two
+                           // launches fewer per layer, but measured SLOWER (27b: 4.39 -> 5.30 ms per token): every CTA redoes
+                           // the quantizer-heavy stage, 4x the single-CTA kernel's work per SM (profiles/r02_notes.md)
   bool fuse_geglu = false;  // LLMI_FUSE_GEGLU=1: gate, up and GEGLU as one launch (gemv_geglu_kernel).  Bit-identical, one
                             // launch fewer per layer, but measured SLOWER (1b 0.828 vs 0.765 ms/token, 27b 5.25 vs 5.02): a
                             // CTA that owns 32 rows of both matrices walks 3-11 items per warp one after the other,
@@ -229,6 +233,28 @@ int run_step(llmi_model_s* m, const int32_t* tok, bool want_logits, bool want_ar
   M_TRY(llmi_launch_embed(make_embed_args(*m->embd), tok, std::sqrt(float(E)), m->h, s, 1, sh ? &ll_embed : nullptr,
                           m->off_h));  // model.cpp:710-712
   m->launches_per_step++;
+  // the residual stream lives in h_cur; a norm stage that runs as the prologue of the mat-vec it feeds
+  // (llmi_launch_gemv_batch_norm) reads h_cur and leaves the updated stream in h_alt
+  float *h_cur = m->h, *h_alt = m->h2;
+  bool qkv_done = false;  // this layer's q/k/v launch already went out with the previous layer's last norm in front
+  auto try_fused = [&](std::initializer_list<llmi_weight_t> ws, std::initializer_list<float*> outs, const float* y,
+                       const float* w_post, const float* w_norm, bool* fused) -> int {
+    *fused = false;
+    if (sh || !m->fuse_norm || !h_alt) return LLMI_OK;
+    const llmi_weight_s* bw[3];
+    float* bo[3];
+    int n = 0;
+    for (llmi_weight_t w : ws) bw[n++] = w;
+    n = 0;
+    for (float* o : outs) bo[n++] = o;
+    const cudaError_t e = llmi_launch_gemv_batch_norm(bw, bo, n, y, w_post, h_cur, h_alt, w_norm, E, m->eps, s);
+    if (e == cudaErrorNotSupported) return LLMI_OK;
+    M_TRY(e);
+    std::swap(h_cur, h_alt);
+    m->launches_per_step++;
+    *fused = true;
+    return LLMI_OK;
+  };
   GemvLL gl;  // exchange context of the mat-vec launches of a sharded model
   if (sh) gl.peers = m->ll.peers;
   auto push = [&](uint32_t idx, std::initializer_list<uint32_t> offs) -> const GemvLL* {
@@ -258,14 +284,17 @@ int run_step(llmi_model_s* m, const int32_t* tok, bool want_logits, bool want_ar
     const int kq = llmi_act_kind_for(w.q->type);
     if (l == 0) {  // attn_norm of layer 0 (later layers: fused into the previous layer's last kernel)
       NormArgs na;
-      na.h = m->h; na.w = w.attn_norm; na.n = E; na.eps = m->eps; na.xn_out = m->xn;
+      na.h = h_cur; na.w = w.attn_norm; na.n = E; na.eps = m->eps; na.xn_out = m->xn;
       na.act_kind = kq; na.act_buf = get_act(m->act_E, kq, E)->buf;
       M_TRY(llmi_launch_norm_act(na, s));
       m->launches_per_step++;
     }
-    M_RC(extra_acts(m, m->act_E, m->xn, E, kq, {w.k, w.v}));
-    // model.cpp:754 (Q), 784 (K), 803 (V): one grid per format group
-    M_RC(gemv_group(m, {w.q, w.k, w.v}, {m->q, m->k, m->v}, m->act_E, push(1 + 4 * l, {m->off_q, m->off_k, m->off_v})));
+    if (!qkv_done) {
+      M_RC(extra_acts(m, m->act_E, m->xn, E, kq, {w.k, w.v}));
+      // model.cpp:754 (Q), 784 (K), 803 (V): one grid per format group
+      M_RC(gemv_group(m, {w.q, w.k, w.v}, {m->q, m->k, m->v}, m->act_E, push(1 + 4 * l, {m->off_q, m->off_k, m->off_v})));
+    }
+    qkv_done = false;
     AttnArgs aa;  // q/k norm, RoPE, KV append and attention in one kernel
     if (sh) {
       aa.ll_q = m->comm + m->off_q; aa.ll_k = m->comm + m->off_k; aa.ll_v = m->comm + m->off_v;
@@ -295,10 +324,13 @@ int run_step(llmi_model_s* m, const int32_t* tok, bool want_logits, bool want_ar
       m->launches_per_step++;
     }
     M_RC(gemv_group(m, {w.o}, {m->attn_out}, m->act_HD, push(2 + 4 * l, {m->off_ao})));  // model.cpp:557
-    {
+    bool gate_up_done = false;  // post-attention norm + residual + ffn_norm as the prologue of the gate / up launch
+    if (!m->fuse_geglu && w.gate->type == w.up->type)
+      M_RC(try_fused({w.gate, w.up}, {m->gate, m->up}, m->attn_out, w.post_attn_norm, w.ffn_norm, &gate_up_done));
+    if (!gate_up_done) {
       const int kg = llmi_act_kind_for(w.gate->type);
       NormArgs na;  // post-attention norm + residual, then ffn_norm (model.cpp:843-858)
-      na.y = m->attn_out; na.w_post = w.post_attn_norm; na.h = m->h; na.w = w.ffn_norm; na.n = E; na.eps = m->eps;
+      na.y = m->attn_out; na.w_post = w.post_attn_norm; na.h = h_cur; na.w = w.ffn_norm; na.n = E; na.eps = m->eps;
       if (sh) { na.y = nullptr; na.ll_y = m->comm + m->off_ao; na.ll_tag = m->tag(2 + 4 * l); }
       na.xn_out = m->xn; na.act_kind = kg; na.act_buf = get_act(m->act_E, kg, E)->buf;
       {  // while the single-CTA norm runs: gate/up, continuing behind what the attention gap asked for
@@ -325,8 +357,9 @@ int run_step(llmi_model_s* m, const int32_t* tok, bool want_logits, bool want_ar
         m->launches_per_step++;
       }
     } else {
-      M_RC(gemv_group(m, {w.gate, w.up}, {m->gate, m->up}, m->act_E,
-                      push(3 + 4 * l, {m->off_gate, m->off_up})));  // model.cpp:875, 877
+      if (!gate_up_done)
+        M_RC(gemv_group(m, {w.gate, w.up}, {m->gate, m->up}, m->act_E,
+                        push(3 + 4 * l, {m->off_gate, m->off_up})));  // model.cpp:875, 877
       const LLTag tg = m->tag(3 + 4 * l);
       M_RC(prefetch({w.down}, 0, m->pf_mb[2]));  // while GEGLU runs
       M_TRY(llmi_launch_geglu_act(m->gate, m->up, F, kd, get_act(m->act_F, kd, F)->buf, nullptr, s, 1, 0,
@@ -335,9 +368,14 @@ int run_step(llmi_model_s* m, const int32_t* tok, bool want_logits, bool want_ar
       m->launches_per_step++;
     }
     M_RC(gemv_group(m, {w.down}, {m->ffn_out}, m->act_F, push(4 + 4 * l, {m->off_fo})));  // model.cpp:909
-    {
+    if (l + 1 < m->L) {  // post-ffw norm + residual + the next layer's attn_norm as the prologue of its q / k / v launch
+      LayerW& nx = m->layers[l + 1];
+      if (nx.q->type == nx.k->type && nx.q->type == nx.v->type)
+        M_RC(try_fused({nx.q, nx.k, nx.v}, {m->q, m->k, m->v}, m->ffn_out, w.post_ffw_norm, nx.attn_norm, &qkv_done));
+    }
+    if (!qkv_done) {
       NormArgs na;  // post-ffw norm + residual (model.cpp:915-924), then the next norm
-      na.y = m->ffn_out; na.w_post = w.post_ffw_norm; na.h = m->h; na.n = E; na.eps = m->eps; na.xn_out = m->xn;
+      na.y = m->ffn_out; na.w_post = w.post_ffw_norm; na.h = h_cur; na.n = E; na.eps = m->eps; na.xn_out = m->xn;
       if (sh) { na.y = nullptr; na.ll_y = m->comm + m->off_fo; na.ll_tag = m->tag(4 + 4 * l); }
       if (l + 1 < m->L) {
         const int kn = llmi_act_kind_for(m->layers[l + 1].q->type);
@@ -890,6 +928,7 @@ int load_impl(llmi_model_s* m, const uint8_t* image, uint64_t size, uint32_t t_m
   if (m->batch > t_max) m->batch = t_max;
   const size_t B = m->batch;
   M_RC(dev_alloc(m, (void**)&m->h, B * E * 4));
+  M_RC(dev_alloc(m, (void**)&m->h2, E * 4));
   M_RC(dev_alloc(m, (void**)&m->xn, B * mx * 4));
   M_RC(dev_alloc(m, (void**)&m->q, B * HD * 4));
   M_RC(dev_alloc(m, (void**)&m->k, B * KD * 4));
@@ -912,6 +951,7 @@ int load_impl(llmi_model_s* m, const uint8_t* image, uint64_t size, uint32_t t_m
   if (m->batch < 2) m->prefill_ok = false;
   if (const char* e = getenv("LLMI_NO_PREFILL")) m->prefill_ok = m->prefill_ok && !(e[0] == '1');
   if (const char* e = getenv("LLMI_FUSE_GEGLU")) m->fuse_geglu = e[0] == '1';
+  if (const char* e = getenv("LLMI_FUSE_NORM")) m->fuse_norm = e[0] == '1';
   {
     // one exchange buffer, same layout on every rank (element = {value bits, tag}): the region of the per-launch
     // path (sharded models only), then the region of the persistent decode kernel

@@ -154,6 +154,41 @@ def test_batched_prefill_is_bitwise_the_token_by_token_path(gpu_ops, monkeypatch
     assert outs["batched"][1] < outs["single"][1] / 4  # 3 batches of launches instead of 37 tokens' worth
 
 
+@pytest.mark.parametrize("dims", [synth.GemmaDims("small", 3, 512, 1024, 4, 2, 128, 640),
+                                  synth.GemmaDims("wide", 2, 2560, 1024, 4, 2, 256, 640)], ids=lambda d: d.name)
+def test_norm_stage_fused_into_the_ring_kernel_is_bitwise_the_two_kernels(gpu_ops, monkeypatch, dims):
+    """llmi_launch_gemv_batch_norm: the RMSNorm (+ residual + next norm + Q8_0 quantizer) stage as the prologue of the
+    persistent mat-vec launch it feeds, every CTA computing its own copy of the activation in shared memory, the
+    residual stream alternating between two buffers.  Forced onto every launch of a small model (ring mode 2; the ring
+    kernel is by default only taken by >= 10 MB Q4_0 launches, and the fusion is opt-in: LLMI_FUSE_NORM=1, measured slower)
+    and compared BITWISE with the separate kernels (ring mode 1, and
+    LLMI_FUSE_NORM=0 with the ring on): logits token by token and the greedy decode after them; 512 logical norm threads
+    (E = 512) and 1024 (E = 2560: two logical threads per physical thread)."""
+    from llm_inference_b200.model import Model
+    img = synth.build_gemma3_gguf(dims, synth.Q4_0, synth.F16, seed=41)
+    prompt = (np.arange(9, dtype=np.int32) * 13 + 1) % dims.vocab
+    outs = {}
+    monkeypatch.setenv("LLMI_NO_PREFILL", "1")  # the prompt goes token by token through run_step
+    for mode, ring, fuse in (("fused", 2, "1"), ("ring_unfused", 2, "0"), ("slab", 1, "1")):
+        monkeypatch.setenv("LLMI_FUSE_NORM", fuse)
+        gpu_ops.set_gemv_ring(ring, 0, 0, 0)
+        m = Model(img, max_positions=48)
+        lg = [m.forward(prompt, 0)]
+        pos = len(prompt)
+        for _ in range(3):
+            lg.append(m.forward([int(lg[-1].argmax())], pos))
+            pos += 1
+        toks, _ = m.decode_greedy(int(lg[-1].argmax()), pos, 6)
+        outs[mode] = (np.stack(lg), toks, m.launches_per_step)
+        m.close()
+    gpu_ops.set_gemv_ring(0, 0, 0, 0)
+    monkeypatch.delenv("LLMI_FUSE_NORM", raising=False)
+    for other in ("ring_unfused", "slab"):
+        assert np.array_equal(outs["fused"][0].view(np.uint32), outs[other][0].view(np.uint32)), other
+        assert np.array_equal(outs["fused"][1], outs[other][1]), other
+    assert outs["fused"][2] < outs["slab"][2]  # two launches fewer per layer
+
+
 @pytest.mark.parametrize("wt,et", [(synth.Q4_0, synth.F16), ("q4_k_m", synth.Q6_K)])
 def test_cluster_norm_is_bitwise_the_single_cta_norm(gpu_ops, monkeypatch, wt, et):
     """norm_act_cluster_kernel (8 CTAs, distributed shared memory; used from E = 2048 on) spreads the single-CTA kernel's
