@@ -779,6 +779,95 @@ __global__ void softcap_kernel(float* logits, uint32_t n, float softcap) {
   if (i < n) logits[i] = __fmul_rn(softcap, tanhf(__fdiv_rn(logits[i], softcap)));
 }
 
+// ---- token batches of a row-sharded model (prefill): the all-gather of [token][row] tiles -----------
+// Every rank computes its own columns (= matrix rows) of a [n_tok][stride] fp32 batch in place; the batch buffers sit
+// at the same byte offset of every rank's exchange allocation.  bx_exchange_kernel copies this rank's columns into
+// every peer's buffer (plain 16-byte stores over NVLink peer memory) and ends in a barrier: the last CTA to finish
+// (fence + ticket) raises this rank's flag on every peer and waits for every peer's flag, so when the kernel
+// completes all columns of all ranks are in place.  Consecutive exchanges use different buffers and a rank can be at
+// most one exchange ahead of its slowest peer (it needs that peer's flag), so a buffer is never overwritten while a
+// peer still reads it.  n_seg == 0: the barrier alone.
+__global__ void __launch_bounds__(256) bx_exchange_kernel(BxArgs a) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ uint32_t s_last;
+  const uint32_t world = a.peers.n, tid = threadIdx.x;
+  for (uint32_t g = 0; g < a.n_seg; ++g) {
+    const BxSeg sg = a.seg[g];
+    if (sg.cols == 0) continue;
+    const bool vec = ((sg.col0 | sg.cols | sg.stride) & 3u) == 0;
+    const uint32_t per = vec ? sg.cols / 4 : sg.cols;
+    const uint64_t items = uint64_t(a.n_tok) * per;
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + tid; i < items; i += uint64_t(gridDim.x) * blockDim.x) {
+      const uint32_t t = uint32_t(i / per), c = uint32_t(i % per);
+      const uint64_t elem = uint64_t(t) * sg.stride + sg.col0 + (vec ? c * 4 : c);
+      const uint64_t byte = sg.byte_off + elem * 4;
+      const char* mine = reinterpret_cast<const char*>(a.peers.base[a.rank]) + byte;
+      if (vec) {
+        const float4 v = *reinterpret_cast<const float4*>(mine);
+        for (uint32_t p = 0; p < world; ++p)
+          if (p != a.rank) *reinterpret_cast<float4*>(reinterpret_cast<char*>(a.peers.base[p]) + byte) = v;
+      } else {
+        const float v = *reinterpret_cast<const float*>(mine);
+        for (uint32_t p = 0; p < world; ++p)
+          if (p != a.rank) *reinterpret_cast<float*>(reinterpret_cast<char*>(a.peers.base[p]) + byte) = v;
+      }
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(a.counter, 1u) == gridDim.x - 1 ? 1u : 0u;
+  __syncthreads();
+  if (!s_last) return;
+  if (tid == 0) *a.counter = 0;
+  __threadfence_system();  // (acquire side of the ticket: every CTA's stores are ordered before the flags below)
+  if (tid < world && tid != a.rank) {
+    uint32_t* theirs = reinterpret_cast<uint32_t*>(a.peers.base[tid] + a.flag_off + a.rank);
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(a.seq) : "memory");
+    const uint32_t* mine = reinterpret_cast<const uint32_t*>(a.peers.base[a.rank] + a.flag_off + tid);
+    unsigned long long limit_ns = 4000000000ull, t0;
+    bool dead = false;
+    if (a.err) {
+      uint32_t d, ms;
+      asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(d) : "l"(a.err) : "memory");
+      asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(ms) : "l"(a.err + 1) : "memory");
+      dead = d != 0;
+      if (ms) limit_ns = (unsigned long long)ms * 1000000ull;
+    }
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (uint32_t spins = 1; !dead; ++spins) {
+      uint32_t f;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(f) : "l"(mine) : "memory");
+      if (int32_t(f - a.seq) >= 0) break;  // a peer may already have raised the next exchange's flag
+      if ((spins & 255u) == 0) {
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > limit_ns) {
+          if (a.err) *a.err = 1;
+          break;
+        }
+      }
+      __nanosleep(64);
+    }
+  }
+  __threadfence_system();
+}
+
+// embed_tokens + scale_embeddings for a token batch of a row-sharded model: the rank that holds a token's row writes
+// it into the residual batch of every rank (a bx_exchange barrier follows).
+__global__ void embed_shard_batch_kernel(EmbedArgs a, const int32_t* __restrict__ token, float scale, LLPeers peers,
+                                         uint64_t h_byte_off) {
+  pdl_trigger();
+  pdl_wait();
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x, m = blockIdx.y;
+  if (e >= a.n_cols) return;
+  const uint32_t row = uint32_t(token[m]);
+  if (row < a.row_begin || row >= a.row_end) return;
+  const float v = dequant_elem(a, row - a.row_begin, e) * scale;
+  for (uint32_t p = 0; p < peers.n; ++p)
+    reinterpret_cast<float*>(reinterpret_cast<char*>(peers.base[p]) + h_byte_off)[size_t(m) * a.n_cols + e] = v;
+}
+
 }  // namespace
 
 TL_EXPORT(llmi_debug_timeline_glue)
@@ -983,4 +1072,18 @@ cudaError_t llmi_launch_finish_token(unsigned long long* key, int32_t* cur_tok, 
 
 cudaError_t llmi_launch_softcap(float* logits, uint32_t n, float softcap, cudaStream_t s) {
   return llmi_launch(softcap_kernel, dim3((n + 255) / 256), dim3(256), 0, s, logits, n, softcap);
+}
+
+cudaError_t llmi_launch_bx_exchange(const BxArgs& a, cudaStream_t s) {
+  if (a.peers.n < 2 || a.n_seg > 3 || !a.counter) return cudaErrorInvalidValue;
+  uint64_t items = 0;
+  for (uint32_t g = 0; g < a.n_seg; ++g) items += uint64_t(a.n_tok) * (a.seg[g].cols / 4 + 1);
+  const unsigned blocks = unsigned(std::max<uint64_t>(1, std::min<uint64_t>((items + 255) / 256, 148ull * 8)));
+  return llmi_launch(bx_exchange_kernel, dim3(blocks), dim3(256), 0, s, a);
+}
+
+cudaError_t llmi_launch_embed_shard_batch(const EmbedArgs& a, const int32_t* token, float scale, const LLPeers& peers,
+                                          uint64_t h_byte_off, uint32_t n_tok, cudaStream_t s) {
+  return llmi_launch(embed_shard_batch_kernel, dim3((a.n_cols + 255) / 256, n_tok), dim3(256), 0, s, a, token, scale, peers,
+                     h_byte_off);
 }

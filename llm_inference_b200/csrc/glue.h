@@ -89,4 +89,22 @@ cudaError_t llmi_launch_finish_token(unsigned long long* key, int32_t* cur_tok, 
 // exchanged vector -> plain floats (+ optional soft-cap): the host-facing logits of a row-sharded model
 cudaError_t llmi_launch_ll_unpack(const uint2* ll, const LLTag& tag, float* out, uint32_t n, float softcap,
                                   cudaStream_t s);
+// Token batches of a row-sharded model (glue.cu bx_exchange_kernel): this rank's columns of up to three
+// [n_tok][stride] fp32 batches go to every peer, then a barrier over the ranks.
+struct BxSeg {
+  uint64_t byte_off = 0;                 // of the batch buffer inside every rank's exchange allocation
+  uint32_t stride = 0, col0 = 0, cols = 0;  // floats per token; this rank's columns [col0, col0 + cols)
+};
+struct BxArgs {
+  LLPeers peers;
+  uint32_t rank = 0, n_seg = 0, n_tok = 0;
+  BxSeg seg[3];
+  uint32_t flag_off = 0;        // element offset of the barrier flags (one per rank) in the exchange buffer
+  uint32_t seq = 0;             // number of this exchange (the same on every rank)
+  uint32_t* counter = nullptr;  // CTA ticket (device word, zero between launches)
+  uint32_t* err = nullptr;      // as LLTag::err
+};
+cudaError_t llmi_launch_bx_exchange(const BxArgs& a, cudaStream_t s);
+cudaError_t llmi_launch_embed_shard_batch(const EmbedArgs& a, const int32_t* token, float scale, const LLPeers& peers,
+                                          uint64_t h_byte_off, uint32_t n_tok, cudaStream_t s);
 cudaError_t llmi_launch_softcap(float* logits, uint32_t n, float softcap, cudaStream_t s);

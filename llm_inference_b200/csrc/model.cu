@@ -92,6 +92,12 @@ struct llmi_model_s {
   uint32_t off_h = 0, off_q = 0, off_k = 0, off_v = 0, off_ao = 0, off_gate = 0, off_up = 0, off_fo = 0, off_key = 0,
            off_logits = 0;
   std::vector<void*> ipc_opened;  // peer mappings to close
+  // token batches of a sharded model (run_batch): the fp32 batch buffers h, q, k, v, attn_out, gate, up, ffn_out and the
+  // logits live INSIDE the exchange allocation (same byte offset on every rank), so a rank's columns can be copied
+  // straight into its peers' buffers (glue.cu bx_exchange_kernel); off_bar: the barrier flags, bx_seq: exchanges so far
+  uint32_t off_bar = 0, bx_seq = 0;
+  uint32_t* d_bx_counter = nullptr;
+  uint64_t bx_off(const void* p) const { return uint64_t(static_cast<const char*>(p) - reinterpret_cast<const char*>(comm)); }
   // persistent decode kernel (mega.cu): one cooperative launch per decode call.  Its exchange
   // region follows the per-launch path's inside `comm` (one allocation, one IPC handle).
   bool use_mega = false;
@@ -464,6 +470,34 @@ int gemv_tokens_group(llmi_model_s* m, std::initializer_list<llmi_weight_t> ws, 
   return LLMI_OK;
 }
 
+// Row-sharded token batch: this rank's columns of the given [n_tok][stride] fp32 batches (the rows of the matrices
+// that produced them) go to every peer, then a barrier (glue.cu bx_exchange_kernel).  No buffers: the barrier alone.
+struct BxBuf {
+  const float* buf;
+  uint32_t stride;
+  llmi_weight_t w;
+};
+int bx_exchange(llmi_model_s* m, std::initializer_list<BxBuf> bufs, uint32_t n_tok) {
+  BxArgs a;
+  a.peers = m->ll.peers;
+  a.rank = uint32_t(m->rank);
+  a.n_tok = n_tok;
+  a.flag_off = m->off_bar;
+  a.seq = ++m->bx_seq;
+  a.counter = m->d_bx_counter;
+  a.err = m->d_llerr;
+  for (const BxBuf& b : bufs) {
+    BxSeg& sg = a.seg[a.n_seg++];
+    sg.byte_off = m->bx_off(b.buf);
+    sg.stride = b.stride;
+    sg.col0 = uint32_t(b.w->row_begin);
+    sg.cols = uint32_t(b.w->row_end - b.w->row_begin);
+  }
+  M_TRY(llmi_launch_bx_exchange(a, m->stream));
+  m->prefill_launches++;
+  return LLMI_OK;
+}
+
 // n_tok <= batch prompt tokens through all layers together (the loop nest of the reference's forward is
 // layer-major with the tokens inside, model.cpp:714-960).  Per token the arithmetic is the one run_step
 // does — same kernels with a token index — so the KV cache and the logits are bit-identical to feeding the
@@ -473,8 +507,25 @@ int gemv_tokens_group(llmi_model_s* m, std::initializer_list<llmi_weight_t> ws, 
 int run_batch(llmi_model_s* m, const int32_t* toks, uint32_t n_tok, bool want_logits) {
   cudaStream_t s = m->stream;
   const uint32_t E = m->E, F = m->F, HD = m->H * m->D, KD = m->HK * m->D;
-  M_TRY(llmi_launch_embed(make_embed_args(*m->embd), toks, std::sqrt(float(E)), m->h, s, n_tok));
-  m->prefill_launches++;
+  // Row-sharded model: every token-batched mat-vec computes this rank's rows of every token (the columns
+  // [row_begin, row_end) of the [n_tok][rows] batch) and bx_exchange all-gathers them over NVLink peer memory; norms,
+  // attention, GEGLU and the KV cache are replicated as in run_step.  A row is still computed start to finish on one
+  // device, so the batch is bit-identical to the single-GPU batch of the same mode.
+  const bool sh = m->sharded();
+  if (sh && m->ll.peers.n != uint32_t(m->world))
+    return llmi_fail(LLMI_ERR_STATE, "row-sharded model: llmi_model_comm_connect has not been called");
+  if (sh) {
+    // every rank has left its previous call (nobody still reads the residual batch), then the owners of the tokens'
+    // embedding rows write them into every rank's batch
+    M_RC(bx_exchange(m, {}, n_tok));
+    M_TRY(llmi_launch_embed_shard_batch(make_embed_args(*m->embd), toks, std::sqrt(float(E)), m->ll.peers, m->bx_off(m->h),
+                                        n_tok, s));
+    m->prefill_launches++;
+    M_RC(bx_exchange(m, {}, n_tok));
+  } else {
+    M_TRY(llmi_launch_embed(make_embed_args(*m->embd), toks, std::sqrt(float(E)), m->h, s, n_tok));
+    m->prefill_launches++;
+  }
   for (uint32_t l = 0; l < m->L; ++l) {
     LayerW& w = m->layers[l];
     const int kq = llmi_act_kind_for(w.q->type);
@@ -487,6 +538,7 @@ int run_batch(llmi_model_s* m, const int32_t* toks, uint32_t n_tok, bool want_lo
       m->prefill_launches++;
     }
     M_RC(gemv_tokens_group(m, {w.q, w.k, w.v}, {m->q, m->k, m->v}, {HD, KD, KD}, m->bact_E, E, n_tok));
+    if (sh) M_RC(bx_exchange(m, {{m->q, HD, w.q}, {m->k, KD, w.k}, {m->v, KD, w.v}}, n_tok));
     AttnArgs aa;
     aa.q = m->q; aa.k = m->k; aa.v = m->v; aa.wq_norm = w.q_norm; aa.wk_norm = w.k_norm;
     aa.kcache = m->kcache + size_t(l) * m->t_max * m->HK * m->D;
@@ -501,6 +553,7 @@ int run_batch(llmi_model_s* m, const int32_t* toks, uint32_t n_tok, bool want_lo
     M_TRY(llmi_launch_attention(aa, s, n_tok));
     m->prefill_launches += 2;
     M_RC(gemv_tokens_group(m, {w.o}, {m->attn_out}, {E}, m->bact_HD, HD, n_tok));
+    if (sh) M_RC(bx_exchange(m, {{m->attn_out, E, w.o}}, n_tok));
     {
       const int kg = llmi_act_kind_for(w.gate->type);
       NormArgs na;
@@ -511,6 +564,7 @@ int run_batch(llmi_model_s* m, const int32_t* toks, uint32_t n_tok, bool want_lo
       m->prefill_launches++;
     }
     M_RC(gemv_tokens_group(m, {w.gate, w.up}, {m->gate, m->up}, {F, F}, m->bact_E, E, n_tok));
+    if (sh) M_RC(bx_exchange(m, {{m->gate, F, w.gate}, {m->up, F, w.up}}, n_tok));
     const int kd = llmi_act_kind_for(w.down->type);
     if (llmi_gemv_prefill_fast() && n_tok >= 64 && F % 64 == 0) {  // throughput mode: GEGLU straight into ffn_down's operand
       M_TRY(llmi_launch_fast_ffn_down(*w.down, m->gate, m->up, m->ffn_out, E, n_tok, s));
@@ -521,6 +575,7 @@ int run_batch(llmi_model_s* m, const int32_t* toks, uint32_t n_tok, bool want_lo
       m->prefill_launches++;
       M_RC(gemv_tokens_group(m, {w.down}, {m->ffn_out}, {E}, m->bact_F, F, n_tok));
     }
+    if (sh) M_RC(bx_exchange(m, {{m->ffn_out, E, w.down}}, n_tok));
     {
       NormArgs na;
       na.y = m->ffn_out; na.w_post = w.post_ffw_norm; na.h = m->h; na.n = E; na.eps = m->eps; na.xn_out = m->xn;
@@ -549,6 +604,7 @@ int run_batch(llmi_model_s* m, const int32_t* toks, uint32_t n_tok, bool want_lo
     la.buf = m->bact_E[kl] + size_t(n_tok - 1) * act_bytes(kl, E);
     M_TRY(llmi_launch_gemv(*m->embd, la, m->logits, s));
     m->prefill_launches++;
+    if (sh) M_RC(bx_exchange(m, {{m->logits, m->V, m->embd}}, 1));
     if (m->final_softcap > 0.0f) {
       M_TRY(llmi_launch_softcap(m->logits, m->V, m->final_softcap, s));
       m->prefill_launches++;
@@ -927,18 +983,21 @@ int load_impl(llmi_model_s* m, const uint8_t* image, uint64_t size, uint32_t t_m
   if (const char* e = getenv("LLMI_PREFILL_BATCH")) m->batch = uint32_t(std::max(1, atoi(e)));
   if (m->batch > t_max) m->batch = t_max;
   const size_t B = m->batch;
-  M_RC(dev_alloc(m, (void**)&m->h, B * E * 4));
+  if (!m->sharded()) {  // (sharded: these are regions of the exchange allocation, below)
+    M_RC(dev_alloc(m, (void**)&m->h, B * E * 4));
+    M_RC(dev_alloc(m, (void**)&m->q, B * HD * 4));
+    M_RC(dev_alloc(m, (void**)&m->k, B * KD * 4));
+    M_RC(dev_alloc(m, (void**)&m->v, B * KD * 4));
+    M_RC(dev_alloc(m, (void**)&m->attn_out, B * E * 4));
+    M_RC(dev_alloc(m, (void**)&m->gate, B * F * 4));
+    M_RC(dev_alloc(m, (void**)&m->up, B * F * 4));
+    M_RC(dev_alloc(m, (void**)&m->ffn_out, B * E * 4));
+    M_RC(dev_alloc(m, (void**)&m->logits, size_t(m->V) * 4));
+  }
   M_RC(dev_alloc(m, (void**)&m->h2, E * 4));
   M_RC(dev_alloc(m, (void**)&m->xn, B * mx * 4));
-  M_RC(dev_alloc(m, (void**)&m->q, B * HD * 4));
-  M_RC(dev_alloc(m, (void**)&m->k, B * KD * 4));
-  M_RC(dev_alloc(m, (void**)&m->v, B * KD * 4));
   M_RC(dev_alloc(m, (void**)&m->q_rot, HD * 4));
   M_RC(dev_alloc(m, (void**)&m->attn, B * HD * 4));
-  M_RC(dev_alloc(m, (void**)&m->attn_out, B * E * 4));
-  M_RC(dev_alloc(m, (void**)&m->gate, B * F * 4));
-  M_RC(dev_alloc(m, (void**)&m->up, B * F * 4));
-  M_RC(dev_alloc(m, (void**)&m->ffn_out, B * E * 4));
   M_RC(dev_alloc(m, (void**)&m->qbuf, B * HD * 4));
   // a batch needs every consumer of a vector to take the same activation kind (true for the uniform and the
   // Q4_K_M layouts; otherwise prompts go token by token) and attention's fused quantizer to apply
@@ -958,15 +1017,36 @@ int load_impl(llmi_model_s* m, const uint8_t* image, uint64_t size, uint32_t t_m
     uint32_t off = 0;
     auto take = [&](uint32_t n) { const uint32_t o = off; off += (n + 1u) & ~1u; return o; };
     if (m->sharded()) {
-      m->prefill_ok = false;  // prompts of a sharded model go token by token through the exchange path
       m->off_h = take(E); m->off_q = take(HD); m->off_k = take(KD); m->off_v = take(KD); m->off_ao = take(E);
       m->off_gate = take(F); m->off_up = take(F); m->off_fo = take(E); m->off_key = take(2 * LLMI_MAX_WORLD);
       m->off_logits = take(m->V);
+      m->off_bar = take(LLMI_MAX_WORLD);
+      if (const char* e = getenv("LLMI_NO_SHARD_PREFILL")) m->prefill_ok = m->prefill_ok && !(e[0] == '1');
     }
     M_RC(mega_plan(m, off));
+    // the fp32 batch buffers of a sharded model: regions of the same allocation, 256-byte aligned
+    uint64_t reg[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (m->sharded()) {
+      const size_t bytes[9] = {B * E * 4, B * HD * 4, B * KD * 4, B * KD * 4, B * E * 4, B * F * 4, B * F * 4, B * E * 4,
+                               size_t(m->V) * 4};
+      uint64_t o64 = off;
+      for (int i = 0; i < 9; ++i) {
+        o64 = (o64 + 31) / 32 * 32;
+        reg[i] = o64;
+        o64 += (bytes[i] + 7) / 8;
+      }
+      if (o64 > 0xffffffffull) return llmi_fail(LLMI_ERR_SIZE, "llmi_model_load_shard: exchange allocation too large");
+      off = uint32_t(o64);
+    }
     m->comm_elems = off;
     M_TRY(cudaMalloc((void**)&m->comm, size_t(off) * sizeof(uint2)));  // not in `owned`: exported through CUDA IPC
     M_TRY(cudaMemset(m->comm, 0, size_t(off) * sizeof(uint2)));
+    if (m->sharded()) {
+      float** dst[9] = {&m->h, &m->q, &m->k, &m->v, &m->attn_out, &m->gate, &m->up, &m->ffn_out, &m->logits};
+      for (int i = 0; i < 9; ++i) *dst[i] = reinterpret_cast<float*>(m->comm + reg[i]);
+      M_RC(dev_alloc(m, (void**)&m->d_bx_counter, 16));
+      M_TRY(cudaMemset(m->d_bx_counter, 0, 16));
+    }
     M_RC(dev_alloc(m, (void**)&m->d_epoch, 16));
     M_RC(dev_alloc(m, (void**)&m->d_llerr, 16));
     M_RC(dev_alloc(m, (void**)&m->d_done, 16));
@@ -989,7 +1069,6 @@ int load_impl(llmi_model_s* m, const uint8_t* image, uint64_t size, uint32_t t_m
     }
     M_TRY(cudaDeviceSynchronize());
   }
-  M_RC(dev_alloc(m, (void**)&m->logits, size_t(m->V) * 4));
   const size_t kv_elems = size_t(m->L) * t_max * KD;
   M_RC(dev_alloc(m, (void**)&m->kcache, kv_elems * 4));
   M_RC(dev_alloc(m, (void**)&m->vcache, kv_elems * 2));

@@ -25,10 +25,12 @@ def main() -> int:
     ap.add_argument("--weights", default="q4_0")
     ap.add_argument("--steps", type=int, default=32)
     ap.add_argument("--prompt", type=int, default=8)
+    ap.add_argument("--prefill", default="exact", choices=["exact", "fast"],
+                    help="fast: the bf16 tensor-core prompt mode (both the sharded and the single-GPU model)")
     a = ap.parse_args()
     import torch.distributed as dist
 
-    from llm_inference_b200 import synth
+    from llm_inference_b200 import ops, synth
     from llm_inference_b200.model import Model
 
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
@@ -42,11 +44,14 @@ def main() -> int:
     et = {"q4_0": synth.F16, "q8_0": synth.Q8_0, "q4_k_m": synth.Q6_K}[a.weights]
     img = synth.build_gemma3_gguf(dims, wt, et, seed=7, embd_std=0.004)
     t_max = a.prompt + a.steps + 8
+    ops.init_ops(1, local)
+    ops.set_prefill_mode(a.prefill == "fast")  # read when a model is loaded (it sizes the token batches)
     m = Model(img, max_positions=t_max, device=local, world=world, rank=rank)
     m.connect()
     prompt = (np.arange(a.prompt, dtype=np.int32) * 37 + 11) % dims.vocab
     t0 = time.time()
     lg = m.forward(prompt, 0)
+    prompt_ms, prompt_launches = m.last_forward_stats()
     first = int(lg.argmax())
     toks, ms = m.decode_greedy(first, a.prompt, a.steps)
     lg_after = m.forward([int(toks[-1])], a.prompt + a.steps)  # full logits through the exchange once more
@@ -56,6 +61,7 @@ def main() -> int:
     if rank == 0:
         ref = Model(img, max_positions=t_max, device=local)
         rl = ref.forward(prompt, 0)
+        ref_prompt_ms = ref.last_forward_stats()[0]
         rtoks, rms = ref.decode_greedy(int(rl.argmax()), a.prompt, a.steps)
         rl_after = ref.forward([int(rtoks[-1])], a.prompt + a.steps)
         ok = (not err and np.array_equal(rl.view(np.uint32), lg.view(np.uint32)) and np.array_equal(rtoks, toks)
@@ -63,6 +69,8 @@ def main() -> int:
         detail = {"prompt_logits_bitwise": bool(np.array_equal(rl.view(np.uint32), lg.view(np.uint32))),
                   "tokens_equal": bool(np.array_equal(rtoks, toks)),
                   "final_logits_bitwise": bool(np.array_equal(rl_after.view(np.uint32), lg_after.view(np.uint32))),
+                  "prefill": a.prefill, "prompt_tokens": a.prompt, "prompt_ms_sharded": prompt_ms,
+                  "prompt_launches_sharded": prompt_launches, "prompt_ms_single": ref_prompt_ms,
                   "ms_per_token_sharded": ms / a.steps, "ms_per_token_single": rms / a.steps,
                   "launches_per_step": m.launches_per_step, "tokens_head": [int(t) for t in toks[:8]]}
         ref.close()
