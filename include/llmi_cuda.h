@@ -193,7 +193,11 @@ int llmi_model_load(const void* gguf_image, uint64_t size, uint32_t max_position
  * start to finish on one device in the canonical order, so logits and tokens are bit-identical to world = 1.
  * Wiring: every rank calls llmi_model_comm_handle, the host all-gathers the 64-byte handles (torch.distributed,
  * MPI, ...), every rank calls llmi_model_comm_connect with the world x 64 bytes in rank order.  All ranks must
- * then make the same forward / decode calls.  world = 1 is llmi_model_load. */
+ * then make the same forward / decode calls.  world = 1 is llmi_model_load.
+ * Prompts (n_tokens > 1) of a sharded model go through the token-batched kernels like the single-GPU model's: every
+ * rank computes its rows of every token of a batch and copies that column block of the [token][row] batch into every
+ * peer's buffer (plain stores over peer memory + a flag barrier, four exchanges per layer); bit-identical to the
+ * single-GPU batch in both prefill modes.  LLMI_NO_SHARD_PREFILL=1 at load: token by token through the tagged exchange. */
 int llmi_model_load_shard(const void* gguf_image, uint64_t size, uint32_t max_positions, int world, int rank,
                           llmi_model_t* out);
 /* The row range [*row_begin, *row_end) of an n_rows matrix that rank `rank` of `world` holds: contiguous,
@@ -209,6 +213,10 @@ int llmi_model_comm_error(llmi_model_t m);
 /* Clears the flag (and the argmax scratch) after the host has dealt with the failure; every rank calls it, with all
  * ranks' streams drained, before the next step. */
 int llmi_model_comm_reset(llmi_model_t m);
+/* Unmaps the peers' exchange buffers (drains this rank's stream first).  Tear-down order of a sharded model: every
+ * rank disconnects, the host synchronizes the ranks (barrier), then every rank calls llmi_model_free — a rank must not
+ * free a buffer a peer still has mapped.  The model cannot run again afterwards. */
+int llmi_model_comm_disconnect(llmi_model_t m);
 int llmi_model_free(llmi_model_t m);
 /* dims[8] = {n_layer, n_embd, n_ff, n_head, n_head_kv, head_dim, vocab, max_positions} */
 int llmi_model_info(llmi_model_t m, uint32_t* dims, uint64_t* weight_bytes);

@@ -56,6 +56,7 @@ SIGNATURES = {
     "llmi_model_comm_connect": (_int, [_vp, _vp]),
     "llmi_model_comm_error": (_int, [_vp]),
     "llmi_model_comm_reset": (_int, [_vp]),
+    "llmi_model_comm_disconnect": (_int, [_vp]),
     "llmi_model_free": (_int, [_vp]),
     "llmi_model_info": (_int, [_vp, C.POINTER(_u32), C.POINTER(_u64)]),
     "llmi_model_forward": (_int, [_vp, _vp, _int, _int, _vp]),

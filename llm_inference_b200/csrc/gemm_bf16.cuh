@@ -159,6 +159,16 @@ __global__ void fast_pack_act_kernel(const uint8_t* __restrict__ act, uint32_t a
   }
 }
 
+// The throughput mode's GEGLU (model.cpp:887-901 with a fast tanh).  Every operation rounds on its own (no contraction),
+// so the value does not depend on the kernel it is inlined into: a row-sharded model computes it on the rank that
+// owns the column (geglu_cols_kernel) and must get the bits of the fused pack below.
+__device__ __forceinline__ float fast_geglu(float x, float u) {
+  const float x3 = __fmul_rn(__fmul_rn(__fmul_rn(0.044715f, x), x), x);
+  const float inner = __fmul_rn(0.7978845608028654f, __fadd_rn(x, x3));
+  const float th = __fsub_rn(1.0f, __fdiv_rn(2.0f, __fadd_rn(__expf(__fmul_rn(2.0f, inner)), 1.0f)));  // tanh; exp overflow -> 1, underflow -> -1
+  return __fmul_rn(__fmul_rn(__fmul_rn(0.5f, x), __fadd_rn(1.0f, th)), u);
+}
+
 // hidden = gelu_tanh(gate) * up of a token batch, straight into the down-projection's bf16 operand order — in this mode
 // the GEGLU stage neither quantizes (geglu_act_kernel: 11 % of a fast prompt, most of it the Q8_0 quantizer's shuffles
 // and IEEE divisions) nor takes the detour through fast_pack_act_kernel.  The reference's formula (model.cpp:887-901).
@@ -181,14 +191,25 @@ __global__ void fast_geglu_pack_kernel(const float* __restrict__ gate, const flo
       const float4 ga = g4[0], gb = g4[1], ua = u4[0], ub = u4[1];
       const float gs[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w}, us[8] = {ua.x, ua.y, ua.z, ua.w, ub.x, ub.y, ub.z, ub.w};
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float x = gs[i];
-        const float inner = 0.7978845608028654f * (x + 0.044715f * x * x * x);
-        const float th = 1.0f - 2.0f / (__expf(2.0f * inner) + 1.0f);  // tanh; exp overflow -> 1, underflow -> -1
-        v[i] = 0.5f * x * (1.0f + th) * us[i];
-      }
+      for (int i = 0; i < 8; ++i) v[i] = fast_geglu(gs[i], us[i]);
     }
     out[o] = fastmm::pack8(v);
+  }
+}
+
+// Row-sharded token batch: gate[token][c] = GEGLU(gate[token][c], up[token][c]) in place for this rank's columns
+// [col0, col0 + cols) — the rank that computed a gate / up column pair combines it, so only the hidden column travels
+// (half the exchange) and the GEGLU arithmetic is split over the ranks.  FAST: the throughput mode's formula, else the
+// reference's operation order (glue_device.cuh geglu()).
+template <bool FAST>
+__global__ void geglu_cols_kernel(float* __restrict__ gate, const float* __restrict__ up, uint32_t stride, uint32_t col0,
+                                  uint32_t cols, uint32_t n_tok) {
+  pdl_trigger();
+  pdl_wait();
+  const uint64_t total = uint64_t(n_tok) * cols;
+  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < total; i += uint64_t(gridDim.x) * blockDim.x) {
+    const size_t e = size_t(i / cols) * stride + col0 + uint32_t(i % cols);
+    gate[e] = FAST ? fast_geglu(gate[e], up[e]) : geglu(gate[e], up[e]);
   }
 }
 

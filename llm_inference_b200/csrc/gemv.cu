@@ -978,7 +978,10 @@ cudaError_t launch_fast(const GemvArgs* args, int n, cudaStream_t s, const float
     const uint64_t items = uint64_t(n_tt) * nkb * tnf * 8;
     const unsigned blocks = unsigned(std::min<uint64_t>((items + 255) / 256, uint64_t(g_sm_count) * 16));
     cudaError_t e;
-    if (geglu_gate)  // the activation IS gelu(gate) * up of the two fp32 batches: no quantized detour
+    if (geglu_gate && !geglu_up)  // `gate` already holds the hidden batch (row-sharded model: combined by the columns' owners)
+      e = llmi_launch(fast_pack_act_kernel, dim3(blocks), dim3(256), 0, s, reinterpret_cast<const uint8_t*>(geglu_gate), K * 4u,
+                      int(ACT_F32), K, n_tok, tnf, n_tt, nkb, reinterpret_cast<uint4*>(g_fast_x));
+    else if (geglu_gate)  // the activation IS gelu(gate) * up of the two fp32 batches: no quantized detour
       e = llmi_launch(fast_geglu_pack_kernel, dim3(blocks), dim3(256), 0, s, geglu_gate, geglu_up, K, n_tok, tnf, n_tt, nkb,
                       reinterpret_cast<uint4*>(g_fast_x));
     else
@@ -1448,6 +1451,16 @@ cudaError_t llmi_launch_fast_ffn_down(const llmi_weight_s& w, const float* gate,
     case LLMI_BF16: return launch_fast<BF16>(&g, 1, s, gate, up);
     default: return cudaErrorInvalidValue;
   }
+}
+
+// Row-sharded token batch: GEGLU in place on this rank's columns of the gate batch (gemm_bf16.cuh geglu_cols_kernel).
+cudaError_t llmi_launch_geglu_cols(float* gate, const float* up, uint32_t stride, uint32_t col0, uint32_t cols, uint32_t n_tok,
+                                   bool fast, cudaStream_t s) {
+  if (cols == 0 || n_tok == 0) return cudaSuccess;
+  const uint64_t total = uint64_t(n_tok) * cols;
+  const unsigned blocks = unsigned(std::min<uint64_t>((total + 255) / 256, uint64_t(g_sm_count) * 16));
+  return fast ? llmi_launch(geglu_cols_kernel<true>, dim3(blocks), dim3(256), 0, s, gate, up, stride, col0, cols, n_tok)
+              : llmi_launch(geglu_cols_kernel<false>, dim3(blocks), dim3(256), 0, s, gate, up, stride, col0, cols, n_tok);
 }
 
 cudaError_t llmi_launch_gemv(const llmi_weight_s& w, const llmi_act_s& a, float* out, cudaStream_t s) {

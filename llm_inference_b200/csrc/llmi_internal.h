@@ -186,6 +186,9 @@ cudaError_t llmi_launch_gemv_batch_norm(const llmi_weight_s* const* ws, float* c
                                         double eps, cudaStream_t s);
 // throughput prefill (gemm_bf16.cuh): token batches of >= 64 go through the dequantize-to-bf16 tcgen05 GEMM (not bit-exact)
 void llmi_gemv_set_prefill_fast(int on);
+cudaError_t llmi_launch_geglu_cols(float* gate, const float* up, uint32_t stride, uint32_t col0, uint32_t cols, uint32_t n_tok,
+                                   bool fast, cudaStream_t s);
+// (up == nullptr: `gate` already holds the hidden batch)
 cudaError_t llmi_launch_fast_ffn_down(const llmi_weight_s& w, const float* gate, const float* up, float* out, uint32_t out_stride,
                                       uint32_t n_tok, cudaStream_t s);  // fast mode: ffn_down fed by gelu(gate) * up directly
 int llmi_gemv_prefill_fast();

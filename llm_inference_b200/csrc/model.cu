@@ -564,14 +564,29 @@ int run_batch(llmi_model_s* m, const int32_t* toks, uint32_t n_tok, bool want_lo
       m->prefill_launches++;
     }
     M_RC(gemv_tokens_group(m, {w.gate, w.up}, {m->gate, m->up}, {F, F}, m->bact_E, E, n_tok));
-    if (sh) M_RC(bx_exchange(m, {{m->gate, F, w.gate}, {m->up, F, w.up}}, n_tok));
     const int kd = llmi_act_kind_for(w.down->type);
-    if (llmi_gemv_prefill_fast() && n_tok >= 64 && F % 64 == 0) {  // throughput mode: GEGLU straight into ffn_down's operand
-      M_TRY(llmi_launch_fast_ffn_down(*w.down, m->gate, m->up, m->ffn_out, E, n_tok, s));
+    const bool fast_down = llmi_gemv_prefill_fast() && n_tok >= 64 && F % 64 == 0;
+    // sharded: gate and up hold the same columns on a rank (same shape, same partition), so the rank combines them
+    // and only the hidden columns travel — half the exchange, and the GEGLU arithmetic is split over the ranks
+    const bool own_geglu = sh && w.gate->row_begin == w.up->row_begin && w.gate->row_end == w.up->row_end;
+    if (own_geglu) {
+      M_TRY(llmi_launch_geglu_cols(m->gate, m->up, F, uint32_t(w.gate->row_begin), uint32_t(w.gate->row_end - w.gate->row_begin),
+                                   n_tok, fast_down, s));
+      m->prefill_launches++;
+      M_RC(bx_exchange(m, {{m->gate, F, w.gate}}, n_tok));
+    } else if (sh) {
+      M_RC(bx_exchange(m, {{m->gate, F, w.gate}, {m->up, F, w.up}}, n_tok));
+    }
+    if (fast_down) {  // throughput mode: GEGLU straight into ffn_down's operand
+      M_TRY(llmi_launch_fast_ffn_down(*w.down, m->gate, own_geglu ? nullptr : m->up, m->ffn_out, E, n_tok, s));
       m->prefill_launches += 3;
     } else {
-      M_TRY(llmi_launch_geglu_act(m->gate, m->up, F, kd, get_bact(m, m->bact_F, kd, F), nullptr, s, n_tok,
-                                  uint32_t(act_bytes(kd, F))));
+      if (own_geglu) {  // the hidden batch is complete: the quantizer alone
+        M_TRY(llmi_launch_act(m->gate, F, kd, get_bact(m, m->bact_F, kd, F), s, n_tok, uint32_t(act_bytes(kd, F))));
+      } else {
+        M_TRY(llmi_launch_geglu_act(m->gate, m->up, F, kd, get_bact(m, m->bact_F, kd, F), nullptr, s, n_tok,
+                                    uint32_t(act_bytes(kd, F))));
+      }
       m->prefill_launches++;
       M_RC(gemv_tokens_group(m, {w.down}, {m->ffn_out}, {E}, m->bact_F, F, n_tok));
     }
@@ -1259,6 +1274,22 @@ int llmi_model_comm_reset(llmi_model_t m) {
     m->mega_epoch = 1;
     m->mega_tok_uses = 0;
   }
+  return LLMI_OK;
+}
+
+// Unmaps the peers' buffers: every rank disconnects, the host barriers, then the ranks free their models (a buffer
+// must not be freed while a peer still has it mapped).
+int llmi_model_comm_disconnect(llmi_model_t m) {
+  if (!m) return llmi_fail(LLMI_ERR_ARG, "llmi_model_comm_disconnect: null model");
+  if (m->stream) M_TRY(cudaStreamSynchronize(m->stream));
+  if (m->decode_graph) {  // the captured kernels hold the peers' addresses
+    cudaGraphExecDestroy(m->decode_graph);
+    m->decode_graph = nullptr;
+  }
+  for (void* p : m->ipc_opened) cudaIpcCloseMemHandle(p);
+  m->ipc_opened.clear();
+  m->ll.peers.n = 0;
+  m->mega.peers.n = 0;
   return LLMI_OK;
 }
 

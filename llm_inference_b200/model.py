@@ -91,6 +91,16 @@ class Model:
         """True when this model decodes with the persistent kernel (LLMI_DECODE=mega at load time)."""
         return bool(_lib.load().llmi_model_decode_path(self.h))
 
+    def disconnect(self, group=None) -> None:
+        """Tear-down of a sharded model, first half: unmap the peers' buffers, then wait for every rank to have done
+        so (a rank must not free a buffer a peer still has mapped).  :meth:`close` afterwards."""
+        if self.world == 1 or not self.h:
+            return
+        import torch.distributed as dist
+
+        _lib.check(_lib.load().llmi_model_comm_disconnect(self.h))
+        dist.barrier(group=group)
+
     def close(self) -> None:
         if self.h:
             _lib.load().llmi_model_free(self.h)

@@ -39,7 +39,7 @@ def main() -> int:
     if a.model == "small":
         dims = synth.GemmaDims("small", 3, 512, 1024, 4, 2, 128, 520)  # vocab 520: 65 slabs, ragged over the ranks
     else:
-        dims = synth.GEMMA3[a.model]
+        dims = synth.GEMMA3[a.model if a.model in synth.GEMMA3 else "gemma-3-" + a.model]
     wt = {"q4_0": synth.Q4_0, "q8_0": synth.Q8_0, "q4_k_m": "q4_k_m"}[a.weights]
     et = {"q4_0": synth.F16, "q8_0": synth.Q8_0, "q4_k_m": synth.Q6_K}[a.weights]
     img = synth.build_gemma3_gguf(dims, wt, et, seed=7, embd_std=0.004)
@@ -77,6 +77,7 @@ def main() -> int:
     flags = [None] * world
     dist.all_gather_object(flags, bool(ok and not err))
     dist.barrier()
+    m.disconnect()
     m.close()
     if rank == 0:
         print(json.dumps({"check": "sharded model == single-GPU model (bitwise)", "world": world, "model": a.model,
