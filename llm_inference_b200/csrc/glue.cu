@@ -532,7 +532,7 @@ __global__ void __launch_bounds__(128) fast_attention_tc_kernel(AttnArgs a, uint
   __half* Ps = reinterpret_cast<__half*>(Ss + 4 * 16 * SLD);  // [4 warps][16][PLD]
   pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t hkv = blockIdx.x, G = a.H / a.HK, TPB = 64 / G;
+  const uint32_t hkv = blockIdx.x + a.hk_begin, G = a.H / a.HK, TPB = 64 / G;
   const uint32_t tokb = blockIdx.y * TPB;
   pdl_wait();
   const int pos0 = *a.pos;
@@ -966,6 +966,10 @@ cudaError_t llmi_attention_init(uint32_t t_max, uint32_t D) {
   }
 }
 
+bool llmi_attention_batch_tc(uint32_t H, uint32_t HK, uint32_t D) {
+  return llmi_gemv_prefill_fast() && D >= 64 && D <= 256 && HK && H % HK == 0 && 64 % (H / HK) == 0 && !getenv("LLMI_FAST_ATTN_NO_TC");
+}
+
 template <int D>
 static cudaError_t attention_launch(const AttnArgs& a, uint32_t n_tok, cudaStream_t s) {
   const size_t smem = llmi_attention_smem(a.t_max, a.D);
@@ -981,7 +985,7 @@ static cudaError_t attention_launch(const AttnArgs& a, uint32_t n_tok, cudaStrea
   }
   if (e != cudaSuccess) return e;
   if constexpr (D <= 256)
-  if (llmi_gemv_prefill_fast() && D >= 64 && 64 % (a.H / a.HK) == 0 && !getenv("LLMI_FAST_ATTN_NO_TC")) {
+  if (llmi_attention_batch_tc(a.H, a.HK, D)) {
     // throughput prefill, tensor-core form (grow-only f16 scratch for q and K)
     static __half *qh = nullptr, *kh = nullptr;
     static size_t qh_n = 0, kh_n = 0;
@@ -1014,7 +1018,7 @@ static cudaError_t attention_launch(const AttnArgs& a, uint32_t n_tok, cudaStrea
       optin = true;
     }
     const uint32_t tpb = 64 / (a.H / a.HK);
-    if ((e = llmi_launch(fast_attention_tc_kernel<D>, dim3(a.HK, (n_tok + tpb - 1) / tpb), dim3(128), fsm, s, a, n_tok,
+    if ((e = llmi_launch(fast_attention_tc_kernel<D>, dim3(a.hk_count ? a.hk_count : a.HK, (n_tok + tpb - 1) / tpb), dim3(128), fsm, s, a, n_tok,
                          (const __half*)qh, (const __half*)kh)) != cudaSuccess)
       return e;
     if (a.act_kind == ACT_NONE) return cudaSuccess;

@@ -66,6 +66,10 @@ struct AttnArgs {
   // row-sharded model: q/k/v arrive through the flagged exchange buffer instead
   const uint2 *ll_q = nullptr, *ll_k = nullptr, *ll_v = nullptr;
   LLTag ll_tag;
+  // token batch of a row-sharded model in the throughput mode (llmi_attention_batch_tc): the main kernel runs the KV
+  // heads [hk_begin, hk_begin + hk_count) only and writes their query heads' columns of `out`; the prologue (norms,
+  // RoPE, KV append for every head) stays replicated.  hk_count == 0: every head.
+  uint32_t hk_begin = 0, hk_count = 0;
 };
 
 cudaError_t llmi_launch_embed(const EmbedArgs& a, const int32_t* token, float scale, float* h, cudaStream_t s,
@@ -78,6 +82,7 @@ cudaError_t llmi_launch_rope_table(float2* table, uint32_t t_max, uint32_t D, fl
 size_t llmi_attention_smem(uint32_t t_max, uint32_t D);
 cudaError_t llmi_attention_init(uint32_t t_max, uint32_t D);
 cudaError_t llmi_launch_attention(const AttnArgs& a, cudaStream_t s, uint32_t n_tok = 1);
+bool llmi_attention_batch_tc(uint32_t H, uint32_t HK, uint32_t D);  // a token batch runs the tensor-core attention kernel
 cudaError_t llmi_launch_geglu_act(const float* gate, const float* up, uint32_t n, int kind, uint8_t* buf,
                                   float* hidden_out, cudaStream_t s, uint32_t n_tok = 1, uint32_t act_stride = 0,
                                   const uint2* ll_gate = nullptr, const uint2* ll_up = nullptr,

@@ -475,7 +475,8 @@ int gemv_tokens_group(llmi_model_s* m, std::initializer_list<llmi_weight_t> ws, 
 struct BxBuf {
   const float* buf;
   uint32_t stride;
-  llmi_weight_t w;
+  llmi_weight_t w;      // this rank's columns = the rows of w it holds, or (w == nullptr) [col0, col0 + cols)
+  uint32_t col0 = 0, cols = 0;
 };
 int bx_exchange(llmi_model_s* m, std::initializer_list<BxBuf> bufs, uint32_t n_tok) {
   BxArgs a;
@@ -490,8 +491,8 @@ int bx_exchange(llmi_model_s* m, std::initializer_list<BxBuf> bufs, uint32_t n_t
     BxSeg& sg = a.seg[a.n_seg++];
     sg.byte_off = m->bx_off(b.buf);
     sg.stride = b.stride;
-    sg.col0 = uint32_t(b.w->row_begin);
-    sg.cols = uint32_t(b.w->row_end - b.w->row_begin);
+    sg.col0 = b.w ? uint32_t(b.w->row_begin) : b.col0;
+    sg.cols = b.w ? uint32_t(b.w->row_end - b.w->row_begin) : b.cols;
   }
   M_TRY(llmi_launch_bx_exchange(a, m->stream));
   m->prefill_launches++;
@@ -550,8 +551,22 @@ int run_batch(llmi_model_s* m, const int32_t* toks, uint32_t n_tok, bool want_lo
     const int ko = llmi_act_kind_for(w.o->type);
     aa.act_kind = ko; aa.act_buf = get_bact(m, m->bact_HD, ko, HD); aa.act_stride = uint32_t(act_bytes(ko, HD));
     aa.qbuf = m->qbuf;
+    // sharded, throughput mode: the tensor-core kernel runs this rank's KV heads only (1 / world of the attention
+    // arithmetic), the heads' output columns travel, the quantizer runs on the complete batch
+    const bool own_heads = sh && m->HK % uint32_t(m->world) == 0 && llmi_attention_batch_tc(m->H, m->HK, m->D);
+    if (own_heads) {
+      aa.hk_count = m->HK / uint32_t(m->world);
+      aa.hk_begin = aa.hk_count * uint32_t(m->rank);
+      aa.act_kind = ACT_NONE;
+    }
     M_TRY(llmi_launch_attention(aa, s, n_tok));
     m->prefill_launches += 2;
+    if (own_heads) {
+      const uint32_t per = aa.hk_count * (m->H / m->HK) * m->D;
+      M_RC(bx_exchange(m, {{m->attn, HD, nullptr, per * uint32_t(m->rank), per}}, n_tok));
+      M_TRY(llmi_launch_act(m->attn, HD, ko, aa.act_buf, s, n_tok, aa.act_stride));
+      m->prefill_launches++;
+    }
     M_RC(gemv_tokens_group(m, {w.o}, {m->attn_out}, {E}, m->bact_HD, HD, n_tok));
     if (sh) M_RC(bx_exchange(m, {{m->attn_out, E, w.o}}, n_tok));
     {
@@ -1008,11 +1023,11 @@ int load_impl(llmi_model_s* m, const uint8_t* image, uint64_t size, uint32_t t_m
     M_RC(dev_alloc(m, (void**)&m->up, B * F * 4));
     M_RC(dev_alloc(m, (void**)&m->ffn_out, B * E * 4));
     M_RC(dev_alloc(m, (void**)&m->logits, size_t(m->V) * 4));
+    M_RC(dev_alloc(m, (void**)&m->attn, B * HD * 4));
   }
   M_RC(dev_alloc(m, (void**)&m->h2, E * 4));
   M_RC(dev_alloc(m, (void**)&m->xn, B * mx * 4));
   M_RC(dev_alloc(m, (void**)&m->q_rot, HD * 4));
-  M_RC(dev_alloc(m, (void**)&m->attn, B * HD * 4));
   M_RC(dev_alloc(m, (void**)&m->qbuf, B * HD * 4));
   // a batch needs every consumer of a vector to take the same activation kind (true for the uniform and the
   // Q4_K_M layouts; otherwise prompts go token by token) and attention's fused quantizer to apply
@@ -1040,12 +1055,12 @@ int load_impl(llmi_model_s* m, const uint8_t* image, uint64_t size, uint32_t t_m
     }
     M_RC(mega_plan(m, off));
     // the fp32 batch buffers of a sharded model: regions of the same allocation, 256-byte aligned
-    uint64_t reg[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    uint64_t reg[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     if (m->sharded()) {
-      const size_t bytes[9] = {B * E * 4, B * HD * 4, B * KD * 4, B * KD * 4, B * E * 4, B * F * 4, B * F * 4, B * E * 4,
-                               size_t(m->V) * 4};
+      const size_t bytes[10] = {B * E * 4, B * HD * 4, B * KD * 4, B * KD * 4, B * E * 4, B * F * 4, B * F * 4, B * E * 4,
+                                size_t(m->V) * 4, B * HD * 4};
       uint64_t o64 = off;
-      for (int i = 0; i < 9; ++i) {
+      for (int i = 0; i < 10; ++i) {
         o64 = (o64 + 31) / 32 * 32;
         reg[i] = o64;
         o64 += (bytes[i] + 7) / 8;
@@ -1057,8 +1072,8 @@ int load_impl(llmi_model_s* m, const uint8_t* image, uint64_t size, uint32_t t_m
     M_TRY(cudaMalloc((void**)&m->comm, size_t(off) * sizeof(uint2)));  // not in `owned`: exported through CUDA IPC
     M_TRY(cudaMemset(m->comm, 0, size_t(off) * sizeof(uint2)));
     if (m->sharded()) {
-      float** dst[9] = {&m->h, &m->q, &m->k, &m->v, &m->attn_out, &m->gate, &m->up, &m->ffn_out, &m->logits};
-      for (int i = 0; i < 9; ++i) *dst[i] = reinterpret_cast<float*>(m->comm + reg[i]);
+      float** dst[10] = {&m->h, &m->q, &m->k, &m->v, &m->attn_out, &m->gate, &m->up, &m->ffn_out, &m->logits, &m->attn};
+      for (int i = 0; i < 10; ++i) *dst[i] = reinterpret_cast<float*>(m->comm + reg[i]);
       M_RC(dev_alloc(m, (void**)&m->d_bx_counter, 16));
       M_TRY(cudaMemset(m->d_bx_counter, 0, 16));
     }
