@@ -150,6 +150,9 @@ __global__ void fast_pack_act_kernel(const uint8_t* __restrict__ act, uint32_t a
         const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = h2f(uint16_t(ws[i >> 1] >> (16 * (i & 1))));
+      } else if (kind == ACT_BF16_RAW) {  // already bf16 (a sharded model's hidden batch): re-ordered, not re-rounded
+        out[o] = *reinterpret_cast<const uint4*>(p + size_t(k0) * 2);
+        continue;
       } else {
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = reinterpret_cast<const float*>(p)[k0 + i];
@@ -203,13 +206,51 @@ __global__ void fast_geglu_pack_kernel(const float* __restrict__ gate, const flo
 // reference's operation order (glue_device.cuh geglu()).
 template <bool FAST>
 __global__ void geglu_cols_kernel(float* __restrict__ gate, const float* __restrict__ up, uint32_t stride, uint32_t col0,
-                                  uint32_t cols, uint32_t n_tok) {
+                                  uint32_t cols, uint32_t n_tok, PeerOut po) {
   pdl_trigger();
   pdl_wait();
   const uint64_t total = uint64_t(n_tok) * cols;
   for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < total; i += uint64_t(gridDim.x) * blockDim.x) {
     const size_t e = size_t(i / cols) * stride + col0 + uint32_t(i % cols);
-    gate[e] = FAST ? fast_geglu(gate[e], up[e]) : geglu(gate[e], up[e]);
+    const float hv = FAST ? fast_geglu(gate[e], up[e]) : geglu(gate[e], up[e]);
+    gate[e] = hv;
+    for (uint32_t j = 0; j < po.n; ++j) po.p[j][e] = hv;  // (po.n > 0: the hidden columns go to every peer right here)
+  }
+}
+// The same, eight columns per thread (col0, cols and stride multiples of 8: 16-byte stores over NVLink).  H16: the
+// hidden values leave as bf16 into `hid16` ([token][stride] halves, local and peers) instead — the throughput mode's
+// ffn_down rounds its activation to bf16 anyway (fast_pack_act_kernel), so rounding before the exchange gives the same
+// operand bits and halves the bytes again.
+template <bool FAST, bool H16>
+__global__ void geglu_cols8_kernel(float* __restrict__ gate, const float* __restrict__ up, uint32_t stride, uint32_t col0,
+                                   uint32_t cols, uint32_t n_tok, PeerOut po, __nv_bfloat16* __restrict__ hid16,
+                                   ptrdiff_t hid16_delta /* bytes from the gate batch to the hid16 batch, same on every rank */) {
+  pdl_trigger();
+  pdl_wait();
+  const uint32_t per = cols / 8;
+  const uint64_t total = uint64_t(n_tok) * per;
+  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < total; i += uint64_t(gridDim.x) * blockDim.x) {
+    const size_t e = size_t(i / per) * stride + col0 + uint32_t(i % per) * 8;
+    const float4 ga = *reinterpret_cast<const float4*>(gate + e), gb = *reinterpret_cast<const float4*>(gate + e + 4);
+    const float4 ua = *reinterpret_cast<const float4*>(up + e), ub = *reinterpret_cast<const float4*>(up + e + 4);
+    const float gs[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w}, us[8] = {ua.x, ua.y, ua.z, ua.w, ub.x, ub.y, ub.z, ub.w};
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = FAST ? fast_geglu(gs[k], us[k]) : geglu(gs[k], us[k]);
+    if (H16) {
+      const uint4 w = fastmm::pack8(v);
+      *reinterpret_cast<uint4*>(hid16 + e) = w;
+      for (uint32_t j = 0; j < po.n; ++j)
+        *reinterpret_cast<uint4*>(reinterpret_cast<char*>(po.p[j]) + hid16_delta + e * 2) = w;
+    } else {
+      const float4 va = make_float4(v[0], v[1], v[2], v[3]), vb = make_float4(v[4], v[5], v[6], v[7]);
+      *reinterpret_cast<float4*>(gate + e) = va;
+      *reinterpret_cast<float4*>(gate + e + 4) = vb;
+      for (uint32_t j = 0; j < po.n; ++j) {
+        *reinterpret_cast<float4*>(po.p[j] + e) = va;
+        *reinterpret_cast<float4*>(po.p[j] + e + 4) = vb;
+      }
+    }
   }
 }
 
@@ -220,7 +261,7 @@ __global__ void geglu_cols_kernel(float* __restrict__ gate, const float* __restr
 template <int TNF>
 __global__ void __launch_bounds__(192, 1)
 gemm_bf16_kernel(const uint8_t* __restrict__ A, const uint8_t* __restrict__ Bt, float* __restrict__ out, uint32_t out_stride,
-                 uint32_t n_rows, uint32_t n_tok, uint32_t nkb) {
+                 uint32_t n_rows, uint32_t n_tok, uint32_t nkb, PeerOut po) {
   using namespace fastmm;
   using C = Cfg<TNF>;
   extern __shared__ __align__(1024) uint8_t fsm_raw[];
@@ -296,6 +337,14 @@ gemm_bf16_kernel(const uint8_t* __restrict__ A, const uint8_t* __restrict__ Bt, 
 #pragma unroll
         for (int k = 0; k < 16; ++k)
           if (tok0 + k < n_tok) out[size_t(tok0 + k) * out_stride + row] = __int_as_float(v[k]);
+        // row-sharded model: the same 128-byte row segments into every peer's batch over NVLink (posted stores: the
+        // all-gather rides under the other CTAs' MMAs; a barrier kernel follows the launch)
+        for (uint32_t j = 0; j < po.n; ++j) {
+          float* dst = po.p[j];
+#pragma unroll
+          for (int k = 0; k < 16; ++k)
+            if (tok0 + k < n_tok) dst[size_t(tok0 + k) * out_stride + row] = __int_as_float(v[k]);
+        }
       }
     }
   }

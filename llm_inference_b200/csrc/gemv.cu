@@ -945,7 +945,7 @@ constexpr uint32_t body_type() {
 // Every matrix of the batch: dequantize -> (activations packed once) -> tcgen05 bf16 GEMM.
 template <class B>
 cudaError_t launch_fast(const GemvArgs* args, int n, cudaStream_t s, const float* geglu_gate = nullptr,
-                        const float* geglu_up = nullptr) {
+                        const float* geglu_up = nullptr, GemmPush* push = nullptr, const void* hid16 = nullptr) {
   const uint32_t type = body_type<B>(), K = args[0].n_cols, n_tok = args[0].n_tok;
   const uint32_t nkb = K / fastmm::KB;
   const uint32_t tnf = n_tok > 128 ? 256u : 128u, n_tt = (n_tok + tnf - 1) / tnf;
@@ -978,7 +978,10 @@ cudaError_t launch_fast(const GemvArgs* args, int n, cudaStream_t s, const float
     const uint64_t items = uint64_t(n_tt) * nkb * tnf * 8;
     const unsigned blocks = unsigned(std::min<uint64_t>((items + 255) / 256, uint64_t(g_sm_count) * 16));
     cudaError_t e;
-    if (geglu_gate && !geglu_up)  // `gate` already holds the hidden batch (row-sharded model: combined by the columns' owners)
+    if (hid16)  // the hidden batch as bf16 (row-sharded model: combined and rounded by the columns' owners)
+      e = llmi_launch(fast_pack_act_kernel, dim3(blocks), dim3(256), 0, s, reinterpret_cast<const uint8_t*>(hid16), K * 2u,
+                      int(ACT_BF16_RAW), K, n_tok, tnf, n_tt, nkb, reinterpret_cast<uint4*>(g_fast_x));
+    else if (geglu_gate && !geglu_up)  // `gate` already holds the hidden batch (row-sharded model: combined by the columns' owners)
       e = llmi_launch(fast_pack_act_kernel, dim3(blocks), dim3(256), 0, s, reinterpret_cast<const uint8_t*>(geglu_gate), K * 4u,
                       int(ACT_F32), K, n_tok, tnf, n_tt, nkb, reinterpret_cast<uint4*>(g_fast_x));
     else if (geglu_gate)  // the activation IS gelu(gate) * up of the two fp32 batches: no quantized detour
@@ -999,21 +1002,25 @@ cudaError_t launch_fast(const GemvArgs* args, int n, cudaStream_t s, const float
     if (e != cudaSuccess) return e;
     if (tnf == 256)
       e = llmi_launch(gemm_bf16_kernel<256>, dim3(n_tt, tiles), dim3(192), fastmm::Cfg<256>::SMEM, s, (const uint8_t*)g_fast_w,
-                      (const uint8_t*)g_fast_x, args[i].out, args[i].out_stride, args[i].n_local, n_tok, nkb);
+                      (const uint8_t*)g_fast_x, args[i].out, args[i].out_stride, args[i].n_local, n_tok, nkb,
+                      llmi_peer_out(push, args[i].out));
     else
       e = llmi_launch(gemm_bf16_kernel<128>, dim3(n_tt, tiles), dim3(192), fastmm::Cfg<128>::SMEM, s, (const uint8_t*)g_fast_w,
-                      (const uint8_t*)g_fast_x, args[i].out, args[i].out_stride, args[i].n_local, n_tok, nkb);
+                      (const uint8_t*)g_fast_x, args[i].out, args[i].out_stride, args[i].n_local, n_tok, nkb,
+                      llmi_peer_out(push, args[i].out));
     if (e != cudaSuccess) return e;
   }
+  if (push) push->done = true;
   return cudaSuccess;
 }
 
 template <class B>
-cudaError_t launch_tokens(const GemvArgs* args, int n, cudaStream_t s) {
+cudaError_t launch_tokens(const GemvArgs* args, int n, cudaStream_t s, GemmPush* push = nullptr) {
+  if (push) push->done = false;  // only the tensor-core GEMM stores into the peers itself
   if (g_prefill_fast && args[0].n_tok >= 64 && args[0].n_cols % fastmm::KB == 0) {
     bool same = true;  // one activation, one K
     for (int i = 1; i < n; ++i) same = same && args[i].act == args[0].act && args[i].n_cols == args[0].n_cols;
-    if (same) return launch_fast<B>(args, n, s);
+    if (same) return launch_fast<B>(args, n, s, nullptr, nullptr, push);
   }
   if (g_umma && args[0].n_tok >= g_umma_min_tokens && args[0].nb >= uint32_t(umma::SB)) {  // K >= one stage (256)
     if (std::is_same<B, BodyQ4_0>::value) return launch_umma<false>(args, n, s);
@@ -1370,7 +1377,8 @@ cudaError_t llmi_launch_gemv_geglu(const llmi_weight_s& gate, const llmi_weight_
 // starting at act_base; matrix i writes token m's rows to outs[i] + m * out_strides[i].
 cudaError_t llmi_launch_gemv_tokens(const llmi_weight_s* const* ws, float* const* outs, const uint32_t* out_strides,
                                     int n, int act_kind, uint64_t act_n, const uint8_t* act_base, uint32_t n_tok,
-                                    cudaStream_t s) {
+                                    cudaStream_t s, GemmPush* push) {
+  if (push) push->done = false;
   if (n < 1 || n > GEMV_MAX_BATCH || n_tok == 0) return cudaErrorInvalidValue;
   llmi_act_s a;
   a.kind = act_kind;
@@ -1388,13 +1396,13 @@ cudaError_t llmi_launch_gemv_tokens(const llmi_weight_s* const* ws, float* const
   }
   if (m == 0) return cudaSuccess;
   switch (ws[0]->type) {
-    case LLMI_Q4_0: return launch_tokens<Q4_0>(args, m, s);
-    case LLMI_Q8_0: return launch_tokens<Q8_0>(args, m, s);
-    case LLMI_Q5_0: return launch_tokens<Q5_0>(args, m, s);
-    case LLMI_Q4_K: return launch_tokens<Q4_K>(args, m, s);
-    case LLMI_Q6_K: return launch_tokens<Q6_K>(args, m, s);
-    case LLMI_F16: return launch_tokens<F16>(args, m, s);
-    case LLMI_BF16: return launch_tokens<BF16>(args, m, s);
+    case LLMI_Q4_0: return launch_tokens<Q4_0>(args, m, s, push);
+    case LLMI_Q8_0: return launch_tokens<Q8_0>(args, m, s, push);
+    case LLMI_Q5_0: return launch_tokens<Q5_0>(args, m, s, push);
+    case LLMI_Q4_K: return launch_tokens<Q4_K>(args, m, s, push);
+    case LLMI_Q6_K: return launch_tokens<Q6_K>(args, m, s, push);
+    case LLMI_F16: return launch_tokens<F16>(args, m, s, push);
+    case LLMI_BF16: return launch_tokens<BF16>(args, m, s, push);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -1435,32 +1443,46 @@ cudaError_t llmi_launch_gemv_batch_norm(const llmi_weight_s* const* ws, float* c
 // Throughput prefill only: out[token][row] = W . (gelu_tanh(gate[token]) * up[token]) for a token batch — ffn_down fed by
 // the fp32 gate / up batches ([n_tok][n_cols] each) without the quantized GEGLU stage in between (gemm_bf16.cuh).
 cudaError_t llmi_launch_fast_ffn_down(const llmi_weight_s& w, const float* gate, const float* up, float* out, uint32_t out_stride,
-                                      uint32_t n_tok, cudaStream_t s) {
+                                      uint32_t n_tok, cudaStream_t s, GemmPush* push, const void* hid16) {
+  if (push) push->done = false;
   if (!g_prefill_fast || w.n_cols % fastmm::KB || w.n_slabs == 0) return cudaErrorInvalidValue;
   llmi_act_s none;
   GemvArgs g = make_args(w, none, out);
   g.n_tok = n_tok;
   g.out_stride = out_stride;
   switch (w.type) {
-    case LLMI_Q4_0: return launch_fast<Q4_0>(&g, 1, s, gate, up);
-    case LLMI_Q8_0: return launch_fast<Q8_0>(&g, 1, s, gate, up);
-    case LLMI_Q5_0: return launch_fast<Q5_0>(&g, 1, s, gate, up);
-    case LLMI_Q4_K: return launch_fast<Q4_K>(&g, 1, s, gate, up);
-    case LLMI_Q6_K: return launch_fast<Q6_K>(&g, 1, s, gate, up);
-    case LLMI_F16: return launch_fast<F16>(&g, 1, s, gate, up);
-    case LLMI_BF16: return launch_fast<BF16>(&g, 1, s, gate, up);
+    case LLMI_Q4_0: return launch_fast<Q4_0>(&g, 1, s, gate, up, push, hid16);
+    case LLMI_Q8_0: return launch_fast<Q8_0>(&g, 1, s, gate, up, push, hid16);
+    case LLMI_Q5_0: return launch_fast<Q5_0>(&g, 1, s, gate, up, push, hid16);
+    case LLMI_Q4_K: return launch_fast<Q4_K>(&g, 1, s, gate, up, push, hid16);
+    case LLMI_Q6_K: return launch_fast<Q6_K>(&g, 1, s, gate, up, push, hid16);
+    case LLMI_F16: return launch_fast<F16>(&g, 1, s, gate, up, push, hid16);
+    case LLMI_BF16: return launch_fast<BF16>(&g, 1, s, gate, up, push, hid16);
     default: return cudaErrorInvalidValue;
   }
 }
 
 // Row-sharded token batch: GEGLU in place on this rank's columns of the gate batch (gemm_bf16.cuh geglu_cols_kernel).
 cudaError_t llmi_launch_geglu_cols(float* gate, const float* up, uint32_t stride, uint32_t col0, uint32_t cols, uint32_t n_tok,
-                                   bool fast, cudaStream_t s) {
+                                   bool fast, cudaStream_t s, const GemmPush* push, void* hid16) {
   if (cols == 0 || n_tok == 0) return cudaSuccess;
+  const PeerOut po = llmi_peer_out(push, gate);
+  if (((stride | col0 | cols) & 7u) == 0) {
+    const uint64_t total = uint64_t(n_tok) * (cols / 8);
+    const unsigned blocks = unsigned(std::min<uint64_t>((total + 255) / 256, uint64_t(g_sm_count) * 16));
+    __nv_bfloat16* h16 = static_cast<__nv_bfloat16*>(hid16);
+    const ptrdiff_t delta = hid16 ? reinterpret_cast<const char*>(hid16) - reinterpret_cast<const char*>(gate) : 0;
+    if (fast && hid16)
+      return llmi_launch(geglu_cols8_kernel<true, true>, dim3(blocks), dim3(256), 0, s, gate, up, stride, col0, cols, n_tok, po, h16, delta);
+    if (hid16) return cudaErrorInvalidValue;  // bf16 hidden values exist in the throughput mode only
+    return fast ? llmi_launch(geglu_cols8_kernel<true, false>, dim3(blocks), dim3(256), 0, s, gate, up, stride, col0, cols, n_tok, po, h16, delta)
+                : llmi_launch(geglu_cols8_kernel<false, false>, dim3(blocks), dim3(256), 0, s, gate, up, stride, col0, cols, n_tok, po, h16, delta);
+  }
+  if (hid16) return cudaErrorInvalidValue;
   const uint64_t total = uint64_t(n_tok) * cols;
   const unsigned blocks = unsigned(std::min<uint64_t>((total + 255) / 256, uint64_t(g_sm_count) * 16));
-  return fast ? llmi_launch(geglu_cols_kernel<true>, dim3(blocks), dim3(256), 0, s, gate, up, stride, col0, cols, n_tok)
-              : llmi_launch(geglu_cols_kernel<false>, dim3(blocks), dim3(256), 0, s, gate, up, stride, col0, cols, n_tok);
+  return fast ? llmi_launch(geglu_cols_kernel<true>, dim3(blocks), dim3(256), 0, s, gate, up, stride, col0, cols, n_tok, po)
+              : llmi_launch(geglu_cols_kernel<false>, dim3(blocks), dim3(256), 0, s, gate, up, stride, col0, cols, n_tok, po);
 }
 
 cudaError_t llmi_launch_gemv(const llmi_weight_s& w, const llmi_act_s& a, float* out, cudaStream_t s) {

@@ -453,6 +453,10 @@ __global__ void __launch_bounds__(256) fast_attn_prologue_kernel(AttnArgs a, uin
   const int pos = *a.pos + int(tok);
   const bool is_q = slot < a.H;
   const uint32_t head = is_q ? slot : slot - a.H;
+  if (is_q && a.hk_count) {  // row-sharded batch: only this rank's query heads are attended to (and only their q rows exist here)
+    const uint32_t hk = head / (a.H / a.HK);
+    if (hk < a.hk_begin || hk >= a.hk_begin + a.hk_count) return;
+  }
   const float* x = is_q ? a.q + (size_t(tok) * a.H + head) * D : a.k + (size_t(tok) * a.HK + head) * D;
   const float* wn = is_q ? a.wq_norm : a.wk_norm;
   float x0[NC], x1[NC];

@@ -33,6 +33,7 @@ struct llmi_weight_s {
 
 // kinds of prepared activation
 enum : int { ACT_NONE = 0, ACT_Q8_0 = 1, ACT_Q8_K = 2, ACT_F16 = 3, ACT_F32 = 4 };
+constexpr int ACT_BF16_RAW = 5;  // throughput prefill only: a [token][K] bf16 batch handed to fast_pack_act_kernel as it is
 
 // One bit per supported weight format / per activation kind: kernels that are compiled for a subset of the formats
 // (mega_impl.cuh) carry a mask of these as a template parameter.
@@ -94,6 +95,28 @@ struct LLPeers {
   uint2* base[LLMI_MAX_WORLD] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   uint32_t n = 0;  // 0: not sharded
 };
+
+// Token batches of a row-sharded model (throughput mode): a GEMM whose output batch lives in the exchange allocation
+// stores every element into the same place of every peer's allocation from its own epilogue (the all-gather overlaps
+// the math tile by tile); `done` reports whether the launch that ran could do so (else the caller copies afterwards).
+struct GemmPush {
+  LLPeers peers;
+  uint32_t rank = 0;
+  bool done = false;
+  const float *skip_begin = nullptr, *skip_end = nullptr;  // an output batch inside this range stays local
+};
+struct PeerOut {  // the peers' images of an output pointer
+  float* p[LLMI_MAX_WORLD - 1] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  uint32_t n = 0;
+};
+inline PeerOut llmi_peer_out(const GemmPush* g, const float* mine) {
+  PeerOut po;
+  if (!g || (mine >= g->skip_begin && mine < g->skip_end)) return po;
+  const ptrdiff_t off = reinterpret_cast<const char*>(mine) - reinterpret_cast<const char*>(g->peers.base[g->rank]);
+  for (uint32_t r = 0; r < g->peers.n; ++r)
+    if (r != g->rank) po.p[po.n++] = reinterpret_cast<float*>(reinterpret_cast<char*>(g->peers.base[r]) + off);
+  return po;
+}
 
 // What a mat-vec launch needs to push its rows to every rank: the ranks' exchange buffers, the tag of this
 // exchange, and per matrix of the batch the element offset of its output vector inside the buffer.
@@ -165,7 +188,7 @@ cudaError_t llmi_launch_gemv(const llmi_weight_s& w, const llmi_act_s& a, float*
 // token-batched mat-vec (prefill): n_tok activations act_bytes(kind, n) apart, outputs out_strides[i] floats apart
 cudaError_t llmi_launch_gemv_tokens(const llmi_weight_s* const* ws, float* const* outs, const uint32_t* out_strides,
                                     int n, int act_kind, uint64_t act_n, const uint8_t* act_base, uint32_t n_tok,
-                                    cudaStream_t s);
+                                    cudaStream_t s, GemmPush* push = nullptr);
 cudaError_t llmi_launch_gemv_batch(const llmi_weight_s* const* ws, float* const* outs, int n, const llmi_act_s& a,
                                    cudaStream_t s, const GemvLL* ll = nullptr);  // same format, same activation, n <= 3
 // front of the weights of up to two matrices into L2 (side stream, during a glue kernel): gemv.cu l2_prefetch_kernel
@@ -187,10 +210,12 @@ cudaError_t llmi_launch_gemv_batch_norm(const llmi_weight_s* const* ws, float* c
 // throughput prefill (gemm_bf16.cuh): token batches of >= 64 go through the dequantize-to-bf16 tcgen05 GEMM (not bit-exact)
 void llmi_gemv_set_prefill_fast(int on);
 cudaError_t llmi_launch_geglu_cols(float* gate, const float* up, uint32_t stride, uint32_t col0, uint32_t cols, uint32_t n_tok,
-                                   bool fast, cudaStream_t s);
+                                   bool fast, cudaStream_t s, const GemmPush* push = nullptr,
+                                   void* hid16 = nullptr);
 // (up == nullptr: `gate` already holds the hidden batch)
 cudaError_t llmi_launch_fast_ffn_down(const llmi_weight_s& w, const float* gate, const float* up, float* out, uint32_t out_stride,
-                                      uint32_t n_tok, cudaStream_t s);  // fast mode: ffn_down fed by gelu(gate) * up directly
+                                      uint32_t n_tok, cudaStream_t s, GemmPush* push = nullptr,
+                                      const void* hid16 = nullptr);  // fast mode: ffn_down fed by gelu(gate) * up directly
 int llmi_gemv_prefill_fast();
 cudaError_t llmi_launch_gemv_argmax(const llmi_weight_s& w, const llmi_act_s& a, float* out, unsigned long long* key,
                                     float softcap, cudaStream_t s, const GemvLL* ll = nullptr);

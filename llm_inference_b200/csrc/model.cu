@@ -96,6 +96,7 @@ struct llmi_model_s {
   // logits live INSIDE the exchange allocation (same byte offset on every rank), so a rank's columns can be copied
   // straight into its peers' buffers (glue.cu bx_exchange_kernel); off_bar: the barrier flags, bx_seq: exchanges so far
   uint32_t off_bar = 0, bx_seq = 0;
+  void* hid16 = nullptr;  // [batch][F] bf16: the hidden batch of the throughput mode, rounded by the columns' owners
   uint32_t* d_bx_counter = nullptr;
   uint64_t bx_off(const void* p) const { return uint64_t(static_cast<const char*>(p) - reinterpret_cast<const char*>(comm)); }
   // persistent decode kernel (mega.cu): one cooperative launch per decode call.  Its exchange
@@ -444,7 +445,9 @@ uint8_t* get_bact(llmi_model_s* m, uint8_t** set, int kind, uint64_t n) {
 
 // Mat-vecs of a batch that consume the same activations: one grid per format group.
 int gemv_tokens_group(llmi_model_s* m, std::initializer_list<llmi_weight_t> ws, std::initializer_list<float*> outs,
-                      std::initializer_list<uint32_t> strides, uint8_t** set, uint64_t n, uint32_t n_tok) {
+                      std::initializer_list<uint32_t> strides, uint8_t** set, uint64_t n, uint32_t n_tok,
+                      GemmPush* push = nullptr) {
+  bool all_pushed = push != nullptr;
   std::vector<llmi_weight_t> w(ws);
   std::vector<float*> o(outs);
   std::vector<uint32_t> st(strides);
@@ -464,9 +467,11 @@ int gemv_tokens_group(llmi_model_s* m, std::initializer_list<llmi_weight_t> ws, 
         ++k;
       }
     const int kind = llmi_act_kind_for(w[i]->type);
-    M_TRY(llmi_launch_gemv_tokens(bw, bo, bs, k, kind, n, set[kind], n_tok, m->stream));
+    M_TRY(llmi_launch_gemv_tokens(bw, bo, bs, k, kind, n, set[kind], n_tok, m->stream, push));
+    if (push) all_pushed = all_pushed && push->done;
     m->prefill_launches++;
   }
+  if (push) push->done = all_pushed;
   return LLMI_OK;
 }
 
@@ -515,6 +520,27 @@ int run_batch(llmi_model_s* m, const int32_t* toks, uint32_t n_tok, bool want_lo
   const bool sh = m->sharded();
   if (sh && m->ll.peers.n != uint32_t(m->world))
     return llmi_fail(LLMI_ERR_STATE, "row-sharded model: llmi_model_comm_connect has not been called");
+  // throughput mode: the GEMM epilogues (and the GEGLU kernel) store into every peer's batch themselves, so an
+  // exchange shrinks to its barrier; the exact kernels leave the copy to bx_exchange_kernel
+  GemmPush gp;
+  gp.peers = m->ll.peers;
+  gp.rank = uint32_t(m->rank);
+  GemmPush* push = sh ? &gp : nullptr;
+  if (const char* e = getenv("LLMI_NO_GEMM_PUSH")) if (e[0] == '1') push = nullptr;
+  auto pushed = [&]() { return push && push->done; };
+  // sharded, throughput mode: the tensor-core attention kernel runs this rank's KV heads only (1 / world of the
+  // attention arithmetic): q never leaves its rank, the heads' output columns travel, the quantizer runs on the
+  // complete batch
+  bool own_heads = sh && m->HK % uint32_t(m->world) == 0 && llmi_attention_batch_tc(m->H, m->HK, m->D);
+  if (own_heads) {  // (the q rows this rank computes must be exactly its heads')
+    const uint64_t per = uint64_t(HD) / uint32_t(m->world);
+    for (const LayerW& lw : m->layers)
+      own_heads = own_heads && lw.q->row_begin == per * uint32_t(m->rank) && lw.q->row_end == per * (uint32_t(m->rank) + 1);
+  }
+  if (own_heads) {
+    gp.skip_begin = m->q;
+    gp.skip_end = m->q + size_t(m->batch) * HD;
+  }
   if (sh) {
     // every rank has left its previous call (nobody still reads the residual batch), then the owners of the tokens'
     // embedding rows write them into every rank's batch
@@ -538,8 +564,10 @@ int run_batch(llmi_model_s* m, const int32_t* toks, uint32_t n_tok, bool want_lo
       M_TRY(llmi_launch_norm_act(na, s));
       m->prefill_launches++;
     }
-    M_RC(gemv_tokens_group(m, {w.q, w.k, w.v}, {m->q, m->k, m->v}, {HD, KD, KD}, m->bact_E, E, n_tok));
-    if (sh) M_RC(bx_exchange(m, {{m->q, HD, w.q}, {m->k, KD, w.k}, {m->v, KD, w.v}}, n_tok));
+    M_RC(gemv_tokens_group(m, {w.q, w.k, w.v}, {m->q, m->k, m->v}, {HD, KD, KD}, m->bact_E, E, n_tok, push));
+    if (sh && pushed()) M_RC(bx_exchange(m, {}, n_tok));
+    else if (sh && own_heads) M_RC(bx_exchange(m, {{m->k, KD, w.k}, {m->v, KD, w.v}}, n_tok));
+    else if (sh) M_RC(bx_exchange(m, {{m->q, HD, w.q}, {m->k, KD, w.k}, {m->v, KD, w.v}}, n_tok));
     AttnArgs aa;
     aa.q = m->q; aa.k = m->k; aa.v = m->v; aa.wq_norm = w.q_norm; aa.wk_norm = w.k_norm;
     aa.kcache = m->kcache + size_t(l) * m->t_max * m->HK * m->D;
@@ -551,9 +579,6 @@ int run_batch(llmi_model_s* m, const int32_t* toks, uint32_t n_tok, bool want_lo
     const int ko = llmi_act_kind_for(w.o->type);
     aa.act_kind = ko; aa.act_buf = get_bact(m, m->bact_HD, ko, HD); aa.act_stride = uint32_t(act_bytes(ko, HD));
     aa.qbuf = m->qbuf;
-    // sharded, throughput mode: the tensor-core kernel runs this rank's KV heads only (1 / world of the attention
-    // arithmetic), the heads' output columns travel, the quantizer runs on the complete batch
-    const bool own_heads = sh && m->HK % uint32_t(m->world) == 0 && llmi_attention_batch_tc(m->H, m->HK, m->D);
     if (own_heads) {
       aa.hk_count = m->HK / uint32_t(m->world);
       aa.hk_begin = aa.hk_count * uint32_t(m->rank);
@@ -567,8 +592,9 @@ int run_batch(llmi_model_s* m, const int32_t* toks, uint32_t n_tok, bool want_lo
       M_TRY(llmi_launch_act(m->attn, HD, ko, aa.act_buf, s, n_tok, aa.act_stride));
       m->prefill_launches++;
     }
-    M_RC(gemv_tokens_group(m, {w.o}, {m->attn_out}, {E}, m->bact_HD, HD, n_tok));
-    if (sh) M_RC(bx_exchange(m, {{m->attn_out, E, w.o}}, n_tok));
+    M_RC(gemv_tokens_group(m, {w.o}, {m->attn_out}, {E}, m->bact_HD, HD, n_tok, push));
+    if (sh && pushed()) M_RC(bx_exchange(m, {}, n_tok));
+    else if (sh) M_RC(bx_exchange(m, {{m->attn_out, E, w.o}}, n_tok));
     {
       const int kg = llmi_act_kind_for(w.gate->type);
       NormArgs na;
@@ -584,16 +610,20 @@ int run_batch(llmi_model_s* m, const int32_t* toks, uint32_t n_tok, bool want_lo
     // sharded: gate and up hold the same columns on a rank (same shape, same partition), so the rank combines them
     // and only the hidden columns travel — half the exchange, and the GEGLU arithmetic is split over the ranks
     const bool own_geglu = sh && w.gate->row_begin == w.up->row_begin && w.gate->row_end == w.up->row_end;
+    // (throughput mode, stores into the peers enabled: the hidden values travel as the bf16 operand they become)
+    void* hid16 = own_geglu && fast_down && push ? m->hid16 : nullptr;
     if (own_geglu) {
       M_TRY(llmi_launch_geglu_cols(m->gate, m->up, F, uint32_t(w.gate->row_begin), uint32_t(w.gate->row_end - w.gate->row_begin),
-                                   n_tok, fast_down, s));
+                                   n_tok, fast_down, s, push, hid16));
       m->prefill_launches++;
-      M_RC(bx_exchange(m, {{m->gate, F, w.gate}}, n_tok));
+      if (push) M_RC(bx_exchange(m, {}, n_tok));
+      else M_RC(bx_exchange(m, {{m->gate, F, w.gate}}, n_tok));
     } else if (sh) {
       M_RC(bx_exchange(m, {{m->gate, F, w.gate}, {m->up, F, w.up}}, n_tok));
     }
+    if (push) push->done = false;
     if (fast_down) {  // throughput mode: GEGLU straight into ffn_down's operand
-      M_TRY(llmi_launch_fast_ffn_down(*w.down, m->gate, own_geglu ? nullptr : m->up, m->ffn_out, E, n_tok, s));
+      M_TRY(llmi_launch_fast_ffn_down(*w.down, m->gate, own_geglu ? nullptr : m->up, m->ffn_out, E, n_tok, s, push, hid16));
       m->prefill_launches += 3;
     } else {
       if (own_geglu) {  // the hidden batch is complete: the quantizer alone
@@ -603,9 +633,10 @@ int run_batch(llmi_model_s* m, const int32_t* toks, uint32_t n_tok, bool want_lo
                                     uint32_t(act_bytes(kd, F))));
       }
       m->prefill_launches++;
-      M_RC(gemv_tokens_group(m, {w.down}, {m->ffn_out}, {E}, m->bact_F, F, n_tok));
+      M_RC(gemv_tokens_group(m, {w.down}, {m->ffn_out}, {E}, m->bact_F, F, n_tok, push));
     }
-    if (sh) M_RC(bx_exchange(m, {{m->ffn_out, E, w.down}}, n_tok));
+    if (sh && pushed()) M_RC(bx_exchange(m, {}, n_tok));
+    else if (sh) M_RC(bx_exchange(m, {{m->ffn_out, E, w.down}}, n_tok));
     {
       NormArgs na;
       na.y = m->ffn_out; na.w_post = w.post_ffw_norm; na.h = m->h; na.n = E; na.eps = m->eps; na.xn_out = m->xn;
@@ -1055,12 +1086,12 @@ int load_impl(llmi_model_s* m, const uint8_t* image, uint64_t size, uint32_t t_m
     }
     M_RC(mega_plan(m, off));
     // the fp32 batch buffers of a sharded model: regions of the same allocation, 256-byte aligned
-    uint64_t reg[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    uint64_t reg[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     if (m->sharded()) {
-      const size_t bytes[10] = {B * E * 4, B * HD * 4, B * KD * 4, B * KD * 4, B * E * 4, B * F * 4, B * F * 4, B * E * 4,
-                                size_t(m->V) * 4, B * HD * 4};
+      const size_t bytes[11] = {B * E * 4, B * HD * 4, B * KD * 4, B * KD * 4, B * E * 4, B * F * 4, B * F * 4, B * E * 4,
+                                size_t(m->V) * 4, B * HD * 4, B * F * 2};
       uint64_t o64 = off;
-      for (int i = 0; i < 10; ++i) {
+      for (int i = 0; i < 11; ++i) {
         o64 = (o64 + 31) / 32 * 32;
         reg[i] = o64;
         o64 += (bytes[i] + 7) / 8;
@@ -1074,6 +1105,7 @@ int load_impl(llmi_model_s* m, const uint8_t* image, uint64_t size, uint32_t t_m
     if (m->sharded()) {
       float** dst[10] = {&m->h, &m->q, &m->k, &m->v, &m->attn_out, &m->gate, &m->up, &m->ffn_out, &m->logits, &m->attn};
       for (int i = 0; i < 10; ++i) *dst[i] = reinterpret_cast<float*>(m->comm + reg[i]);
+      m->hid16 = m->comm + reg[10];
       M_RC(dev_alloc(m, (void**)&m->d_bx_counter, 16));
       M_TRY(cudaMemset(m->d_bx_counter, 0, 16));
     }
