@@ -314,7 +314,8 @@ __global__ void __launch_bounds__(1024) attention_kernel(AttnArgs a, uint32_t nb
 #ifdef LLMI_TIMELINE
   if (tl_slot >= 0) g_tl_attn_slot = tl_slot;
 #endif
-  attention_body<D, MODE, false>(a, nbuf, blockIdx.x, blockIdx.y, att_smem, nullptr);
+  // (MODE 2 of a row-sharded batch: this rank's heads only, AttnArgs::hk_begin)
+  attention_body<D, MODE, false>(a, nbuf, blockIdx.x + (MODE == 2 ? a.hk_begin * (a.H / a.HK) : 0u), blockIdx.y, att_smem, nullptr);
   TL_MARK(2);
 }
 
@@ -1043,7 +1044,7 @@ static cudaError_t attention_launch(const AttnArgs& a, uint32_t n_tok, cudaStrea
     if (a.act_kind == ACT_NONE) return cudaSuccess;
     return llmi_launch_act(a.out, a.H * a.D, a.act_kind, a.act_buf, s, n_tok, a.act_stride);
   }
-  return llmi_launch(attention_kernel<D, 2>, dim3(a.H, n_tok), dim3(1024), smem, s, a, nbuf);
+  return llmi_launch(attention_kernel<D, 2>, dim3(a.hk_count ? a.hk_count * (a.H / a.HK) : a.H, n_tok), dim3(1024), smem, s, a, nbuf);
 }
 
 // n_tok > 1 (prefill batch): two launches, a.qbuf required (n_tok * H * D words).

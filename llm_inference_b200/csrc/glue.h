@@ -66,9 +66,9 @@ struct AttnArgs {
   // row-sharded model: q/k/v arrive through the flagged exchange buffer instead
   const uint2 *ll_q = nullptr, *ll_k = nullptr, *ll_v = nullptr;
   LLTag ll_tag;
-  // token batch of a row-sharded model in the throughput mode (llmi_attention_batch_tc): the main kernel runs the KV
-  // heads [hk_begin, hk_begin + hk_count) only and writes their query heads' columns of `out`; the prologue (norms,
-  // RoPE, KV append for every head) stays replicated.  hk_count == 0: every head.
+  // token batch of a row-sharded model: the main kernel (the tensor-core kernel of the throughput mode, MODE 2 of the
+  // exact one) runs the KV heads [hk_begin, hk_begin + hk_count) only and writes their query heads' columns of `out`;
+  // the K/V part of the prologue (norm, RoPE, append for every KV head) stays replicated.  hk_count == 0: every head.
   uint32_t hk_begin = 0, hk_count = 0;
 };
 

@@ -528,16 +528,20 @@ int run_batch(llmi_model_s* m, const int32_t* toks, uint32_t n_tok, bool want_lo
   GemmPush* push = sh ? &gp : nullptr;
   if (const char* e = getenv("LLMI_NO_GEMM_PUSH")) if (e[0] == '1') push = nullptr;
   auto pushed = [&]() { return push && push->done; };
-  // sharded, throughput mode: the tensor-core attention kernel runs this rank's KV heads only (1 / world of the
-  // attention arithmetic): q never leaves its rank, the heads' output columns travel, the quantizer runs on the
-  // complete batch
-  bool own_heads = sh && m->HK % uint32_t(m->world) == 0 && llmi_attention_batch_tc(m->H, m->HK, m->D);
+  // sharded: the main attention kernel runs this rank's KV heads only (1 / world of the attention arithmetic), the
+  // heads' output columns travel and the quantizer runs on the complete batch.  Throughput mode (q_local): the
+  // prologue skips the other ranks' query heads too, so q never leaves the rank that computed it.
+  bool own_heads = sh && m->HK % uint32_t(m->world) == 0;
   if (own_heads) {  // (the q rows this rank computes must be exactly its heads')
     const uint64_t per = uint64_t(HD) / uint32_t(m->world);
     for (const LayerW& lw : m->layers)
       own_heads = own_heads && lw.q->row_begin == per * uint32_t(m->rank) && lw.q->row_end == per * (uint32_t(m->rank) + 1);
   }
-  if (own_heads) {
+  if (const char* e = getenv("LLMI_NO_HEAD_SHARD")) own_heads = own_heads && !(e[0] == '1');
+  // (throughput mode: only the tensor-core attention kernel takes a head range, its CUDA-core fallback does not)
+  if (llmi_gemv_prefill_fast() && !llmi_attention_batch_tc(m->H, m->HK, m->D)) own_heads = false;
+  const bool q_local = own_heads && llmi_attention_batch_tc(m->H, m->HK, m->D);
+  if (q_local) {
     gp.skip_begin = m->q;
     gp.skip_end = m->q + size_t(m->batch) * HD;
   }
@@ -566,7 +570,7 @@ int run_batch(llmi_model_s* m, const int32_t* toks, uint32_t n_tok, bool want_lo
     }
     M_RC(gemv_tokens_group(m, {w.q, w.k, w.v}, {m->q, m->k, m->v}, {HD, KD, KD}, m->bact_E, E, n_tok, push));
     if (sh && pushed()) M_RC(bx_exchange(m, {}, n_tok));
-    else if (sh && own_heads) M_RC(bx_exchange(m, {{m->k, KD, w.k}, {m->v, KD, w.v}}, n_tok));
+    else if (sh && q_local) M_RC(bx_exchange(m, {{m->k, KD, w.k}, {m->v, KD, w.v}}, n_tok));
     else if (sh) M_RC(bx_exchange(m, {{m->q, HD, w.q}, {m->k, KD, w.k}, {m->v, KD, w.v}}, n_tok));
     AttnArgs aa;
     aa.q = m->q; aa.k = m->k; aa.v = m->v; aa.wq_norm = w.q_norm; aa.wk_norm = w.k_norm;
