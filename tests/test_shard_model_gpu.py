@@ -29,20 +29,24 @@ def test_sharded_model_is_bitwise_the_single_gpu_model(gpu_ops, world, weights, 
     assert res["prompt_logits_bitwise"] and res["tokens_equal"] and res["final_logits_bitwise"], res
 
 
-@pytest.mark.parametrize("world,weights,prompt,prefill,batch,port", [
-    (2, "q4_0", 40, "exact", None, 29544),   # token-lane kernel, one batch
-    (3, "q8_0", 37, "exact", "16", 29545),  # three batches, the last one ragged; ragged row ranges
-    (2, "q4_0", 100, "fast", None, 29546),   # bf16 tensor-core mode
-    (3, "q8_0", 150, "fast", "64", 29547),
+@pytest.mark.parametrize("world,model,weights,prompt,prefill,batch,port", [
+    (2, "small", "q4_0", 40, "exact", None, 29544),   # token-lane kernel, one batch; each rank attends with its own heads
+    (3, "small", "q8_0", 37, "exact", "16", 29545),  # three batches, the last one ragged; ragged row ranges; attention replicated
+    (2, "small", "q4_0", 100, "fast", None, 29546),   # bf16 tensor-core mode: GEMM epilogues store into the peer, q stays local
+    (3, "small", "q8_0", 150, "fast", "64", 29547),
+    (8, "wide", "q4_0", 100, "fast", None, 29548),    # a world of 8, one KV head per rank
+    (8, "wide", "q4_0", 70, "exact", "32", 29549),
 ])
-def test_sharded_prompt_batches_are_bitwise_the_single_gpu_batches(gpu_ops, world, weights, prompt, prefill, batch, port):
+def test_sharded_prompt_batches_are_bitwise_the_single_gpu_batches(gpu_ops, world, model, weights, prompt, prefill, batch,
+                                                                   port):
     """Prompts of a sharded model go through the token-batched kernels (run_batch): every rank computes its rows of
     every token and bx_exchange_kernel all-gathers the [token][row] tiles over peer memory.  Logits after the prompt,
     the greedy tokens that continue from its KV cache and the final logits must equal the single-GPU model's in the
     same mode bit for bit."""
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(port), str(REPO / "tools" / "sharded_model_check.py"),
-           "--same-device", "--steps", "4", "--prompt", str(prompt), "--weights", weights, "--prefill", prefill]
+           "--same-device", "--steps", "4", "--prompt", str(prompt), "--weights", weights, "--prefill", prefill,
+           "--model", model]
     env = dict(os.environ, OMP_NUM_THREADS="1")
     env.pop("LLMI_PREFILL", None)
     if batch:

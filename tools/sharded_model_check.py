@@ -38,6 +38,8 @@ def main() -> int:
     dist.init_process_group("gloo")
     if a.model == "small":
         dims = synth.GemmaDims("small", 3, 512, 1024, 4, 2, 128, 520)  # vocab 520: 65 slabs, ragged over the ranks
+    elif a.model == "wide":  # 8 KV heads: every rank of a world of 8 owns one (head-sharded attention of a prompt batch)
+        dims = synth.GemmaDims("wide", 2, 512, 1024, 16, 8, 64, 520)
     else:
         dims = synth.GEMMA3[a.model if a.model in synth.GEMMA3 else "gemma-3-" + a.model]
     wt = {"q4_0": synth.Q4_0, "q8_0": synth.Q8_0, "q4_k_m": "q4_k_m"}[a.weights]
