@@ -584,6 +584,12 @@ constexpr size_t RING_MAX_SMEM = 112 * 1024;
 // captured path is warmed up first.
 std::mutex g_fix_mu;
 std::map<cudaStream_t, uint2*> g_fix;
+struct StreamScratch {
+  void* p[SCR_COUNT] = {};
+  size_t bytes[SCR_COUNT] = {};
+};
+std::mutex g_scr_mu;
+std::map<cudaStream_t, StreamScratch> g_scr;
 cudaError_t ring_fix_for(cudaStream_t s, uint2** out) {
   std::lock_guard<std::mutex> lk(g_fix_mu);
   auto it = g_fix.find(s);
@@ -765,9 +771,6 @@ constexpr int TOK_MAX_TILE = 8;
 
 constexpr size_t tl_smem(int W) { return 32 * TL_ACT_ROW + 32 * TL_SC_ROW * 4 + size_t(W) * (16 * 8 * 32 + 16 * 8 * 4); }
 
-// grow-only scratch for the chunk partials of one token-per-lane launch
-static float* g_part = nullptr;
-static size_t g_part_floats = 0;
 
 template <bool IS_Q8>
 cudaError_t launch_toklane(const GemvArgs* args, int n, cudaStream_t s) {
@@ -781,15 +784,8 @@ cudaError_t launch_toklane(const GemvArgs* args, int n, cudaStream_t s) {
     if (J > jmax) jmax = J;
     need += size_t(J) * args[i].n_tok * args[i].n_slabs * LLMI_SLAB;
   }
-  if (need > g_part_floats) {
-    cudaError_t e = cudaStreamSynchronize(s);
-    if (e != cudaSuccess) return e;
-    if (g_part) cudaFree(g_part);
-    g_part = nullptr;
-    g_part_floats = 0;
-    if ((e = cudaMalloc(&g_part, need * sizeof(float))) != cudaSuccess) return e;
-    g_part_floats = need;
-  }
+  float* g_part = nullptr;  // chunk partials of this launch (per-stream scratch)
+  if (cudaError_t e = llmi_stream_scratch(s, SCR_PART, need * sizeof(float), (void**)&g_part)) return e;
   size_t off = 0;
   uint64_t outs = 0;
   for (int i = 0; i < n; ++i) {
@@ -815,9 +811,6 @@ cudaError_t launch_toklane(const GemvArgs* args, int n, cudaStream_t s) {
 }
 
 // grow-only scratch of one tensor-core prefill launch: activations in UMMA operand order + fp32 scales
-static uint4* g_bq = nullptr;
-static float* g_bd = nullptr;
-static size_t g_bq_items = 0, g_bd_floats = 0;
 bool g_umma = true;  // LLMI_NO_UMMA=1: token batches stay on the dp4a token-per-lane kernel (A/B)
 // Below this many tokens the dp4a token-per-lane kernel is at least as fast (measured, profiles/r01_notes.md: a CTA
 // of the tensor-core kernel has ~3 us of fixed cost); LLMI_UMMA_MIN_TOKENS overrides (>= 32: one token tile).
@@ -861,31 +854,13 @@ cudaError_t launch_umma(const GemvArgs* args, int n, cudaStream_t s) {
   size_t need = 0;
   for (int i = 0; i < n; ++i) need += size_t(J) * n_tok * args[i].n_slabs * LLMI_SLAB;
   const size_t bq_items = size_t(tiles_n) * nb0 * 64, bd_floats = size_t(tiles_n) * nb0 * umma::TN;
-  if (need > g_part_floats || bq_items > g_bq_items || bd_floats > g_bd_floats) {
-    cudaError_t e = cudaStreamSynchronize(s);
-    if (e != cudaSuccess) return e;
-    if (need > g_part_floats) {
-      if (g_part) cudaFree(g_part);
-      g_part = nullptr;
-      g_part_floats = 0;
-      if ((e = cudaMalloc(&g_part, need * sizeof(float))) != cudaSuccess) return e;
-      g_part_floats = need;
-    }
-    if (bq_items > g_bq_items) {
-      if (g_bq) cudaFree(g_bq);
-      g_bq = nullptr;
-      g_bq_items = 0;
-      if ((e = cudaMalloc(&g_bq, bq_items * sizeof(uint4))) != cudaSuccess) return e;
-      g_bq_items = bq_items;
-    }
-    if (bd_floats > g_bd_floats) {
-      if (g_bd) cudaFree(g_bd);
-      g_bd = nullptr;
-      g_bd_floats = 0;
-      if ((e = cudaMalloc(&g_bd, bd_floats * sizeof(float))) != cudaSuccess) return e;
-      g_bd_floats = bd_floats;
-    }
-  }
+  float* g_part = nullptr;  // per-stream scratch: chunk partials, the batch's quants and scales in operand order
+  uint4* g_bq = nullptr;
+  float* g_bd = nullptr;
+  cudaError_t se;
+  if ((se = llmi_stream_scratch(s, SCR_PART, need * sizeof(float), (void**)&g_part)) != cudaSuccess) return se;
+  if ((se = llmi_stream_scratch(s, SCR_BQ, bq_items * sizeof(uint4), (void**)&g_bq)) != cudaSuccess) return se;
+  if ((se = llmi_stream_scratch(s, SCR_BD, bd_floats * sizeof(float), (void**)&g_bd)) != cudaSuccess) return se;
   size_t off = 0;
   uint32_t ctas = 0;
   uint64_t outs = 0;
@@ -928,9 +903,6 @@ cudaError_t launch_umma(const GemvArgs* args, int n, cudaStream_t s) {
 
 // ---- throughput prefill (gemm_bf16.cuh): opt-in, not the parity path ---------------------------------------------
 bool g_prefill_fast = false;  // LLMI_PREFILL=fast / llmi_set_prefill_mode(1)
-static uint8_t* g_fast_w = nullptr;  // grow-only scratch: dequantized weights / packed activations of one launch
-static uint8_t* g_fast_x = nullptr;
-static size_t g_fast_w_bytes = 0, g_fast_x_bytes = 0;
 
 template <class B>
 constexpr uint32_t body_type() {
@@ -955,23 +927,11 @@ cudaError_t launch_fast(const GemvArgs* args, int n, cudaStream_t s, const float
     w_need = std::max(w_need, tiles * nkb * fastmm::A_BYTES);
   }
   const size_t x_need = size_t(n_tt) * nkb * tnf * fastmm::KB * 2;
-  if (w_need > g_fast_w_bytes || x_need > g_fast_x_bytes) {
-    cudaError_t e = cudaStreamSynchronize(s);
-    if (e != cudaSuccess) return e;
-    if (w_need > g_fast_w_bytes) {
-      if (g_fast_w) cudaFree(g_fast_w);
-      g_fast_w = nullptr;
-      g_fast_w_bytes = 0;
-      if ((e = cudaMalloc(&g_fast_w, w_need)) != cudaSuccess) return e;
-      g_fast_w_bytes = w_need;
-    }
-    if (x_need > g_fast_x_bytes) {
-      if (g_fast_x) cudaFree(g_fast_x);
-      g_fast_x = nullptr;
-      g_fast_x_bytes = 0;
-      if ((e = cudaMalloc(&g_fast_x, x_need)) != cudaSuccess) return e;
-      g_fast_x_bytes = x_need;
-    }
+  uint8_t *g_fast_w = nullptr, *g_fast_x = nullptr;  // per-stream scratch: dequantized weights / packed activations of one launch
+  {
+    cudaError_t e;
+    if ((e = llmi_stream_scratch(s, SCR_FAST_W, w_need, (void**)&g_fast_w)) != cudaSuccess) return e;
+    if ((e = llmi_stream_scratch(s, SCR_FAST_X, x_need, (void**)&g_fast_x)) != cudaSuccess) return e;
   }
   const int kind = llmi_act_kind_for(type);
   {
@@ -1145,6 +1105,33 @@ void llmi_gemv_set_shape(int warps, int slabs_per_cta) {
   g_slabs_per_cta = slabs_per_cta;
 }
 
+cudaError_t llmi_stream_scratch(cudaStream_t s, int slot, size_t bytes, void** out) {
+  if (slot < 0 || slot >= SCR_COUNT || !out) return cudaErrorInvalidValue;
+  std::lock_guard<std::mutex> lk(g_scr_mu);
+  StreamScratch& sc = g_scr[s];
+  if (bytes > sc.bytes[slot] || !sc.p[slot]) {
+    cudaError_t e = cudaStreamSynchronize(s);  // launches in flight may still use the old buffer
+    if (e != cudaSuccess) return e;
+    if (sc.p[slot]) cudaFree(sc.p[slot]);
+    sc.p[slot] = nullptr;
+    sc.bytes[slot] = 0;
+    const size_t want = bytes ? bytes : 16;
+    if ((e = cudaMalloc(&sc.p[slot], want)) != cudaSuccess) return e;
+    sc.bytes[slot] = want;
+  }
+  *out = sc.p[slot];
+  return cudaSuccess;
+}
+
+void llmi_stream_scratch_release(cudaStream_t s) {  // the stream is about to be destroyed (llmi_model_free)
+  std::lock_guard<std::mutex> lk(g_scr_mu);
+  auto it = g_scr.find(s);
+  if (it == g_scr.end()) return;
+  for (void* p : it->second.p)
+    if (p) cudaFree(p);
+  g_scr.erase(it);
+}
+
 // llmi_shutdown: the grow-only scratch of the token-batched launches (chunk partials, packed activations).
 void llmi_gemv_shutdown() {
   {
@@ -1152,17 +1139,11 @@ void llmi_gemv_shutdown() {
     for (auto& kv : g_fix) cudaFree(kv.second);
     g_fix.clear();
   }
-  if (g_fast_w) cudaFree(g_fast_w);
-  if (g_fast_x) cudaFree(g_fast_x);
-  g_fast_w = g_fast_x = nullptr;
-  g_fast_w_bytes = g_fast_x_bytes = 0;
-  if (g_part) cudaFree(g_part);
-  if (g_bq) cudaFree(g_bq);
-  if (g_bd) cudaFree(g_bd);
-  g_part = nullptr;
-  g_bq = nullptr;
-  g_bd = nullptr;
-  g_part_floats = g_bq_items = g_bd_floats = 0;
+  std::lock_guard<std::mutex> lk(g_scr_mu);
+  for (auto& kv : g_scr)
+    for (void* p : kv.second.p)
+      if (p) cudaFree(p);
+  g_scr.clear();
 }
 
 // Bench / test knobs of the token-batched path, re-read by every llmi_model_load.

@@ -992,26 +992,10 @@ static cudaError_t attention_launch(const AttnArgs& a, uint32_t n_tok, cudaStrea
   if constexpr (D <= 256)
   if (llmi_attention_batch_tc(a.H, a.HK, D)) {
     // throughput prefill, tensor-core form (grow-only f16 scratch for q and K)
-    static __half *qh = nullptr, *kh = nullptr;
-    static size_t qh_n = 0, kh_n = 0;
+    __half *qh = nullptr, *kh = nullptr;
     const size_t nq = size_t(n_tok) * a.H * D, nk = size_t(a.HK) * a.t_max * D;
-    if (nq > qh_n || nk > kh_n) {
-      if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
-      if (nq > qh_n) {
-        if (qh) cudaFree(qh);
-        qh = nullptr;
-        qh_n = 0;
-        if ((e = cudaMalloc(&qh, nq * 2)) != cudaSuccess) return e;
-        qh_n = nq;
-      }
-      if (nk > kh_n) {
-        if (kh) cudaFree(kh);
-        kh = nullptr;
-        kh_n = 0;
-        if ((e = cudaMalloc(&kh, nk * 2)) != cudaSuccess) return e;
-        kh_n = nk;
-      }
-    }
+    if ((e = llmi_stream_scratch(s, SCR_ATT_Q, nq * 2, (void**)&qh)) != cudaSuccess) return e;
+    if ((e = llmi_stream_scratch(s, SCR_ATT_K, nk * 2, (void**)&kh)) != cudaSuccess) return e;
     const unsigned pb = unsigned(std::min<size_t>((nq + nk + 255) / 256, 148 * 16));
     if ((e = llmi_launch(fast_attn_prep_kernel, dim3(pb), dim3(256), 0, s, a, n_tok, qh, kh)) != cudaSuccess) return e;
     constexpr int LD = D + 8;

@@ -96,6 +96,13 @@ struct LLPeers {
   uint32_t n = 0;  // 0: not sharded
 };
 
+// Grow-only device scratch of the token-batched launches, one set PER STREAM: two models prefilling on different
+// streams never share a partials / operand buffer.  Returns a buffer of at least `bytes` (a larger request drains the
+// stream, frees and reallocates).  Everything is freed by llmi_shutdown.
+enum : int { SCR_PART = 0, SCR_BQ, SCR_BD, SCR_FAST_W, SCR_FAST_X, SCR_ATT_Q, SCR_ATT_K, SCR_COUNT };
+cudaError_t llmi_stream_scratch(cudaStream_t s, int slot, size_t bytes, void** out);
+void llmi_stream_scratch_release(cudaStream_t s);
+
 // Token batches of a row-sharded model (throughput mode): a GEMM whose output batch lives in the exchange allocation
 // stores every element into the same place of every peer's allocation from its own epilogue (the all-gather overlaps
 // the math tile by tile); `done` reports whether the launch that ran could do so (else the caller copies afterwards).

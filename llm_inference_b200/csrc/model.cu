@@ -1272,7 +1272,10 @@ int llmi_model_free(llmi_model_t m) {
   if (m->pf_stream) cudaStreamDestroy(m->pf_stream);
   if (m->ev0) cudaEventDestroy(m->ev0);
   if (m->ev1) cudaEventDestroy(m->ev1);
-  if (m->stream) cudaStreamDestroy(m->stream);
+  if (m->stream) {
+    llmi_stream_scratch_release(m->stream);
+    cudaStreamDestroy(m->stream);
+  }
   delete m;
   return LLMI_OK;
 }
