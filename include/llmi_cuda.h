@@ -184,7 +184,8 @@ typedef struct llmi_model_s* llmi_model_t;
  * Architecture "gemma3" only; anything else returns LLMI_ERR_TYPE (use the
  * ops.h drop-in with the reference's model.cpp for those). */
 int llmi_model_load(const void* gguf_image, uint64_t size, uint32_t max_positions, llmi_model_t* out);
-/* Row-sharded model over `world` GPUs of one node, one process (or host thread) per GPU: rank
+/* Row-sharded model over `world` GPUs of one node, one PROCESS per GPU (llmi_init binds a process to one device and a CUDA IPC handle
+ * cannot be opened by the process that created it): rank
  * `rank` uploads a contiguous, slab-aligned range of the output rows of EVERY matrix — the thread partition of
  * ops.cpp:439-448 lifted to devices — and keeps activations, norms, attention and the KV cache replicated.  The
  * vectors the mat-vecs produce are exchanged by the mat-vec kernels themselves: each output row is written,

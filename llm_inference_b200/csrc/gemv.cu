@@ -815,6 +815,7 @@ bool g_umma = true;  // LLMI_NO_UMMA=1: token batches stay on the dp4a token-per
 // Below this many tokens the dp4a token-per-lane kernel is at least as fast (measured, profiles/r01_notes.md: a CTA
 // of the tensor-core kernel has ~3 us of fixed cost); LLMI_UMMA_MIN_TOKENS overrides (>= 32: one token tile).
 uint32_t g_umma_min_tokens = 128;
+uint32_t g_fast_tnf = 0;  // LLMI_FAST_TNF = 128 | 256 pins the token tile of the bf16 GEMM (0: by grid fill)
 
 // The quant plane of a matrix as a 2-D tensor for TMA: [slab][the slab's K run] in 8-byte elements; box = 16 slabs x
 // one stage (8 blocks).  The encoder lives in the driver library: fetched once through the runtime, no -lcuda.
@@ -920,7 +921,23 @@ cudaError_t launch_fast(const GemvArgs* args, int n, cudaStream_t s, const float
                         const float* geglu_up = nullptr, GemmPush* push = nullptr, const void* hid16 = nullptr) {
   const uint32_t type = body_type<B>(), K = args[0].n_cols, n_tok = args[0].n_tok;
   const uint32_t nkb = K / fastmm::KB;
-  const uint32_t tnf = n_tok > 128 ? 256u : 128u, n_tt = (n_tok + tnf - 1) / tnf;
+  // token tile: 256 when the grid fills the GPU; 128 when the launch is short of CTAs (row shards of a sharded model:
+  // 5376 / 8 rows x 2048 tokens is 48 CTAs of 256 tokens) and halving the tile shortens the last wave.  Estimated
+  // time = waves x tile width; a 128-token CTA takes ~0.66 of a 256-token CTA's time, not half (measured: all-128 makes
+  // the 27b prompt's GEMMs 25 % slower where the wave count says 5 % faster, profiles/r02_fast_tnf_ab.txt), so the
+  // narrow tile must win by 30 %.  The result does not depend on the tile (bitwise, same file).
+  uint32_t tnf = n_tok > 128 ? 256u : 128u;
+  if (tnf == 256 && g_fast_tnf != 256) {
+    uint64_t t256 = 0, t128 = 0;
+    for (int i = 0; i < n; ++i) {
+      const uint64_t tiles = (uint64_t(args[i].n_slabs) * LLMI_SLAB + fastmm::TM - 1) / fastmm::TM;
+      const uint64_t c256 = tiles * ((n_tok + 255) / 256), c128 = tiles * ((n_tok + 127) / 128);
+      t256 += (c256 + g_sm_count - 1) / g_sm_count * 256;
+      t128 += (c128 + g_sm_count - 1) / g_sm_count * 128;
+    }
+    if (g_fast_tnf == 128 || t128 * 13 < t256 * 10) tnf = 128;
+  }
+  const uint32_t n_tt = (n_tok + tnf - 1) / tnf;
   size_t w_need = 0;
   for (int i = 0; i < n; ++i) {
     const size_t tiles = (size_t(args[i].n_slabs) * LLMI_SLAB + fastmm::TM - 1) / fastmm::TM;
@@ -1152,6 +1169,9 @@ void llmi_gemv_read_env() {
   g_umma = !(e && e[0] == '1');
   e = getenv("LLMI_UMMA_MIN_TOKENS");
   g_umma_min_tokens = e ? uint32_t(std::max(32, atoi(e))) : 128u;
+  e = getenv("LLMI_FAST_TNF");
+  g_fast_tnf = e ? uint32_t(atoi(e)) : 0u;
+  if (g_fast_tnf != 128 && g_fast_tnf != 256) g_fast_tnf = 0;
   e = getenv("LLMI_PREFILL");  // "fast" / anything else = exact; unset: whatever llmi_set_prefill_mode last said
   if (e) g_prefill_fast = std::string(e) == "fast";
 }
