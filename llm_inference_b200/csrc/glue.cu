@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(1024) norm_act_kernel(NormArgs a) {
     if (a.ll_y) yv[k] = ok ? ll_waitf(a.ll_y + i, tag, a.ll_tag.err) : 0.0f;  // one decode token, grid = 1
     else yv[k] = (ok && a.y) ? a.y[i] : 0.0f;
   }
-  if (a.pos_inc && threadIdx.x == 0 && blockIdx.x == 0) *a.pos_inc += int32_t(gridDim.x);
+  if (a.pos_inc && threadIdx.x == 0 && blockIdx.x == 0) *a.pos_inc += int32_t(a.pos_inc_by ? a.pos_inc_by : gridDim.x);
   if (a.y || a.ll_y) {
     float ss = 0.0f;
 #pragma unroll
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(T / NORM_CL) norm_act_cluster_kernel(NormArgs 
     if (a.ll_y) yv[k] = ok ? ll_waitf(a.ll_y + i, tag, a.ll_tag.err) : 0.0f;
     else yv[k] = (ok && a.y) ? a.y[i] : 0.0f;
   }
-  if (a.pos_inc && lt == 0 && tok == 0) *a.pos_inc += int32_t(gridDim.x / NORM_CL);
+  if (a.pos_inc && lt == 0 && tok == 0) *a.pos_inc += int32_t(a.pos_inc_by ? a.pos_inc_by : gridDim.x / NORM_CL);
   cluster_wait();
   TL_MARK(3);
   if (a.y || a.ll_y) {

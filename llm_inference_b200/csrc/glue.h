@@ -36,6 +36,7 @@ struct NormArgs {
   int act_kind = ACT_NONE;
   uint8_t* act_buf = nullptr;
   int32_t* pos_inc = nullptr;     // optional device counter to bump (end of a token step) by the number of tokens
+  uint32_t pos_inc_by = 0;        // 0: the number of tokens of this launch (a launch over a token slice passes the batch size)
   uint32_t n_tok = 1;             // prefill batch: one CTA per token, vectors n apart, activations act_stride apart
   uint32_t act_stride = 0;
   // row-sharded model: y arrives through the flagged exchange buffer instead (tag = ll_tag); the last norm of a

@@ -545,6 +545,38 @@ int run_batch(llmi_model_s* m, const int32_t* toks, uint32_t n_tok, bool want_lo
     gp.skip_begin = m->q;
     gp.skip_end = m->q + size_t(m->batch) * HD;
   }
+  // sharded: the norm stages (post-norm + residual + next norm + quantizer: one CTA or cluster per token) run on a
+  // contiguous token slice per rank — the residual batch stays token-sliced, nobody else reads it — and the slices of
+  // the quantized activation (about one byte per element) are all-gathered for the mat-vecs that follow
+  const uint32_t tok_per = sh ? (n_tok + uint32_t(m->world) - 1) / uint32_t(m->world) : n_tok;
+  const uint32_t t0 = sh ? std::min(n_tok, tok_per * uint32_t(m->rank)) : 0, t1 = std::min(n_tok, t0 + tok_per);
+  bool seq_par = sh && n_tok >= 8u * uint32_t(m->world) && tok_per * uint32_t(m->world - 1) < n_tok;
+  if (const char* e = getenv("LLMI_NO_SEQ_NORM")) seq_par = seq_par && !(e[0] == '1');
+  auto in_comm = [&](const void* p) {
+    const char* c = static_cast<const char*>(p);
+    return c >= reinterpret_cast<const char*>(m->comm) && c < reinterpret_cast<const char*>(m->comm + m->comm_elems);
+  };
+  auto norm_stage = [&](NormArgs na) -> int {
+    if (na.act_kind != ACT_Q8_K) na.xn_out = nullptr;  // nobody reads the fp32 copy of a batch (Q8_K: the cluster kernel's staging)
+    const bool has_act = na.act_buf && na.act_kind != ACT_NONE;
+    if (!seq_par || (has_act && !in_comm(na.act_buf))) {
+      M_TRY(llmi_launch_norm_act(na, s));
+      m->prefill_launches++;
+      return LLMI_OK;
+    }
+    NormArgs sl = na;
+    if (sl.y) sl.y += size_t(t0) * E;
+    sl.h += size_t(t0) * E;
+    if (sl.xn_out) sl.xn_out += size_t(t0) * E;
+    if (sl.act_buf) sl.act_buf += size_t(t0) * sl.act_stride;
+    sl.n_tok = t1 - t0;
+    sl.pos_inc_by = n_tok;
+    M_TRY(llmi_launch_norm_act(sl, s));
+    m->prefill_launches++;
+    if (has_act)  // the slice is one contiguous byte range of the activation batch
+      M_RC(bx_exchange(m, {{reinterpret_cast<const float*>(na.act_buf), 0, nullptr, t0 * (na.act_stride / 4), (t1 - t0) * (na.act_stride / 4)}}, 1));
+    return LLMI_OK;
+  };
   if (sh) {
     // every rank has left its previous call (nobody still reads the residual batch), then the owners of the tokens'
     // embedding rows write them into every rank's batch
@@ -565,8 +597,7 @@ int run_batch(llmi_model_s* m, const int32_t* toks, uint32_t n_tok, bool want_lo
       na.h = m->h; na.w = w.attn_norm; na.n = E; na.eps = m->eps; na.xn_out = m->xn;
       na.act_kind = kq; na.act_buf = get_bact(m, m->bact_E, kq, E); na.n_tok = n_tok;
       na.act_stride = uint32_t(act_bytes(kq, E));
-      M_TRY(llmi_launch_norm_act(na, s));
-      m->prefill_launches++;
+      M_RC(norm_stage(na));
     }
     M_RC(gemv_tokens_group(m, {w.q, w.k, w.v}, {m->q, m->k, m->v}, {HD, KD, KD}, m->bact_E, E, n_tok, push));
     if (sh && pushed()) M_RC(bx_exchange(m, {}, n_tok));
@@ -605,8 +636,7 @@ int run_batch(llmi_model_s* m, const int32_t* toks, uint32_t n_tok, bool want_lo
       na.y = m->attn_out; na.w_post = w.post_attn_norm; na.h = m->h; na.w = w.ffn_norm; na.n = E; na.eps = m->eps;
       na.xn_out = m->xn; na.act_kind = kg; na.act_buf = get_bact(m, m->bact_E, kg, E); na.n_tok = n_tok;
       na.act_stride = uint32_t(act_bytes(kg, E));
-      M_TRY(llmi_launch_norm_act(na, s));
-      m->prefill_launches++;
+      M_RC(norm_stage(na));
     }
     M_RC(gemv_tokens_group(m, {w.gate, w.up}, {m->gate, m->up}, {F, F}, m->bact_E, E, n_tok));
     const int kd = llmi_act_kind_for(w.down->type);
@@ -657,8 +687,7 @@ int run_batch(llmi_model_s* m, const int32_t* toks, uint32_t n_tok, bool want_lo
           na.act_stride = uint32_t(act_bytes(kl, E));
         }
       }
-      M_TRY(llmi_launch_norm_act(na, s));
-      m->prefill_launches++;
+      M_RC(norm_stage(na));
     }
   }
   if (want_logits) {  // logits of the last token of the batch: the ordinary one-token mat-vec
@@ -1090,7 +1119,7 @@ int load_impl(llmi_model_s* m, const uint8_t* image, uint64_t size, uint32_t t_m
     }
     M_RC(mega_plan(m, off));
     // the fp32 batch buffers of a sharded model: regions of the same allocation, 256-byte aligned
-    uint64_t reg[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    uint64_t reg[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, bact_reg[5] = {0, 0, 0, 0, 0};
     if (m->sharded()) {
       const size_t bytes[11] = {B * E * 4, B * HD * 4, B * KD * 4, B * KD * 4, B * E * 4, B * F * 4, B * F * 4, B * E * 4,
                                 size_t(m->V) * 4, B * HD * 4, B * F * 2};
@@ -1100,6 +1129,20 @@ int load_impl(llmi_model_s* m, const uint8_t* image, uint64_t size, uint32_t t_m
         reg[i] = o64;
         o64 += (bytes[i] + 7) / 8;
       }
+      // quantized activations of the residual width: the norm stages of a batch run on a token slice per rank and
+      // the slices are all-gathered (run_batch), so these batches live in the exchange allocation too
+      bool used[5] = {false, false, false, false, false};
+      used[llmi_act_kind_for(m->embd->type)] = true;
+      for (const LayerW& w : m->layers) {
+        used[llmi_act_kind_for(w.q->type)] = true;
+        used[llmi_act_kind_for(w.gate->type)] = true;
+      }
+      for (int k = 1; k < 5; ++k)
+        if (used[k]) {
+          o64 = (o64 + 31) / 32 * 32;
+          bact_reg[k] = o64;
+          o64 += (B * act_bytes(k, E) + 7) / 8;
+        }
       if (o64 > 0xffffffffull) return llmi_fail(LLMI_ERR_SIZE, "llmi_model_load_shard: exchange allocation too large");
       off = uint32_t(o64);
     }
@@ -1110,6 +1153,8 @@ int load_impl(llmi_model_s* m, const uint8_t* image, uint64_t size, uint32_t t_m
       float** dst[10] = {&m->h, &m->q, &m->k, &m->v, &m->attn_out, &m->gate, &m->up, &m->ffn_out, &m->logits, &m->attn};
       for (int i = 0; i < 10; ++i) *dst[i] = reinterpret_cast<float*>(m->comm + reg[i]);
       m->hid16 = m->comm + reg[10];
+      for (int k = 1; k < 5; ++k)
+        if (bact_reg[k]) m->bact_E[k] = reinterpret_cast<uint8_t*>(m->comm + bact_reg[k]);
       M_RC(dev_alloc(m, (void**)&m->d_bx_counter, 16));
       M_TRY(cudaMemset(m->d_bx_counter, 0, 16));
     }
