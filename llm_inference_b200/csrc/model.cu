@@ -551,7 +551,14 @@ int run_batch(llmi_model_s* m, const int32_t* toks, uint32_t n_tok, bool want_lo
   const uint32_t tok_per = sh ? (n_tok + uint32_t(m->world) - 1) / uint32_t(m->world) : n_tok;
   const uint32_t t0 = sh ? std::min(n_tok, tok_per * uint32_t(m->rank)) : 0, t1 = std::min(n_tok, t0 + tok_per);
   bool seq_par = sh && n_tok >= 8u * uint32_t(m->world) && tok_per * uint32_t(m->world - 1) < n_tok;
-  if (const char* e = getenv("LLMI_NO_SEQ_NORM")) seq_par = seq_par && !(e[0] == '1');
+  {
+    // a norm stage costs ~48 ns per token, the extra exchange (copy of the slice + flag barrier) ~12 us: the slice pays
+    // from ~250 tokens taken off a rank (measured at N = 2: 2048-token batches 118.2 -> 116.3 ms, 256-token batches of
+    // the exact mode 1410 -> 1425 ms).  LLMI_SEQ_NORM_MIN_TOKENS overrides the threshold (tests: 1; 0 = never).
+    uint32_t min_off = 512;
+    if (const char* e = getenv("LLMI_SEQ_NORM_MIN_TOKENS")) min_off = uint32_t(std::max(0, atoi(e)));
+    seq_par = seq_par && min_off > 0 && n_tok - tok_per >= min_off;  // (the same decision on every rank)
+  }
   auto in_comm = [&](const void* p) {
     const char* c = static_cast<const char*>(p);
     return c >= reinterpret_cast<const char*>(m->comm) && c < reinterpret_cast<const char*>(m->comm + m->comm_elems);

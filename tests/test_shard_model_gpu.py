@@ -49,6 +49,7 @@ def test_sharded_prompt_batches_are_bitwise_the_single_gpu_batches(gpu_ops, worl
            "--model", model]
     env = dict(os.environ, OMP_NUM_THREADS="1")
     env.pop("LLMI_PREFILL", None)
+    env["LLMI_SEQ_NORM_MIN_TOKENS"] = "1"  # norm stages on a token slice per rank even for these short prompts
     if batch:
         env["LLMI_PREFILL_BATCH"] = batch
     r = subprocess.run(cmd, cwd=REPO, env=env, capture_output=True, text=True, timeout=300)
