@@ -39,6 +39,37 @@ def equal_ranges(n_rows: int, world: int, align: int = SLAB) -> list[tuple[int, 
     return [(r * per, (r + 1) * per) for r in range(world)]
 
 
+def token_slices(n_tok: int, world: int) -> list[tuple[int, int]]:
+    """Contiguous token slices of a prompt batch, ceil(n_tok / world) each (the last ranks' may be short or empty):
+    where the norm stages of a sharded batch run (model.cu run_batch)."""
+    per = -(-n_tok // world)
+    return [(min(n_tok, r * per), min(n_tok, (r + 1) * per)) for r in range(world)]
+
+
+def kv_head_ranges(n_head_kv: int, world: int) -> list[tuple[int, int]] | None:
+    """KV heads per rank for the attention of a sharded prompt batch, or None when the heads do not divide (then every
+    rank attends with every head)."""
+    if n_head_kv % world:
+        return None
+    per = n_head_kv // world
+    return [(r * per, (r + 1) * per) for r in range(world)]
+
+
+def allgather_columns(batch, ranges, rank: int, group=None):
+    """In-place all-gather of a [tokens][rows] batch whose columns ``ranges[rank]`` this rank has filled: the host-side
+    statement of what bx_exchange_kernel / the GEMM epilogue's peer stores do on the device (every rank ends up with every
+    rank's column block; no arithmetic on the way)."""
+    import torch.distributed as dist
+
+    for src, (b, e) in enumerate(ranges):
+        if e > b:
+            blk = batch[:, b:e].contiguous()
+            dist.broadcast(blk, src=src, group=group)
+            if src != rank:
+                batch[:, b:e] = blk
+    return batch
+
+
 def allgather_rows(full, ranges, rank: int, group=None):
     """In-place all-gather of a full-length vector whose ``ranges[rank]`` slice
     this rank has filled.  ``full`` is a torch tensor (cuda with NCCL, cpu with

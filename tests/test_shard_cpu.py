@@ -78,6 +78,69 @@ def test_sharded_matvec_allgather_equals_unsharded(world):
     assert q.get(timeout=5) == 1
 
 
+def _batch_worker(rank: int, world: int, port: int, cases, out_q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle.binding import Port
+    P = Port()
+    ok = True
+    for t, k, n, n_tok in cases:
+        w = synth.random_blocks(t, n, k, seed=t + k + n)
+        xs = np.random.default_rng(k + n_tok).standard_normal((n_tok, k)).astype(np.float32)
+        ranges = shard.row_ranges(n, world)
+        rb = synth.row_bytes(t, k)
+        b, e = ranges[rank]
+        batch = torch.full((n_tok, n), float("nan"))
+        if e > b:  # this rank's rows of EVERY token: the column block [b, e) of the [token][row] batch
+            mine = shard.shard_blocks(w, rb, (b, e))
+            for m in range(n_tok):
+                batch[m, b:e] = torch.from_numpy(P.mat_vec_mul(t, mine, xs[m], e - b, k))
+        shard.allgather_columns(batch, ranges, rank)
+        ref = np.stack([P.mat_vec_mul(t, w, xs[m], n, k) for m in range(n_tok)])
+        ok &= bool(np.array_equal(batch.numpy().view(np.uint32), ref.view(np.uint32)))
+    res = torch.tensor([1 if ok else 0])
+    dist.all_reduce(res, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        out_q.put(int(res.item()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_token_batch_allgather_equals_unsharded(world):
+    """The prompt path of a sharded model on CPU: every rank computes its rows of every token, the column
+    blocks are all-gathered (gloo), and the [token][row] batch equals the unsharded one bit for bit."""
+    cases = [(synth.Q4_0, 256, 136, 5), (synth.Q8_0, 128, 40, 3), (synth.Q4_K, 512, 72, 4), (synth.F16, 64, 20, 2)]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_batch_worker, args=(r, world, port, cases, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=180)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) == 1
+
+
+def test_token_slices_and_head_ranges():
+    """The partitions run_batch uses for the norm stages (token slices) and the attention (KV heads per rank)."""
+    for n, w in [(2048, 8), (2048, 3), (100, 8), (37, 3), (8, 8), (5, 8)]:
+        sl = shard.token_slices(n, w)
+        assert len(sl) == w and sl[0][0] == 0 and max(e for _, e in sl) == n
+        assert all(b0 <= e0 and e0 == b1 for (b0, e0), (b1, _) in zip(sl, sl[1:]) if e0 < n)
+        assert sum(e - b for b, e in sl) == n
+    assert shard.token_slices(2048, 8)[3] == (768, 1024)
+    assert shard.token_slices(100, 8)[7] == (91, 100)
+    assert shard.kv_head_ranges(16, 8) == [(2 * r, 2 * r + 2) for r in range(8)]
+    assert shard.kv_head_ranges(16, 3) is None and shard.kv_head_ranges(1, 2) is None
+    # the q rows a rank computes are exactly its heads' when the KV heads divide (gemma-3-27b: H 32, HK 16, D 128)
+    for w in (2, 4, 8):
+        rows = shard.row_ranges(32 * 128, w)
+        heads = shard.kv_head_ranges(16, w)
+        assert [(b * 2 * 128, e * 2 * 128) for b, e in heads] == rows
+
+
 def test_c_abi_shard_range_is_the_python_partition():
     """llmi_shard_range (what llmi_model_load_shard applies to every matrix) == shard.row_ranges: contiguous,
     slab-aligned, covering, as even as possible — for ragged row counts and more ranks than slabs."""
