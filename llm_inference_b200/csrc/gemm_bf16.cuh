@@ -216,6 +216,7 @@ __global__ void geglu_cols_kernel(float* __restrict__ gate, const float* __restr
     gate[e] = hv;
     for (uint32_t j = 0; j < po.n; ++j) po.p[j][e] = hv;  // (po.n > 0: the hidden columns go to every peer right here)
   }
+  if (po.n) __threadfence_system();
 }
 // The same, eight columns per thread (col0, cols and stride multiples of 8: 16-byte stores over NVLink).  H16: the
 // hidden values leave as bf16 into `hid16` ([token][stride] halves, local and peers) instead — the throughput mode's
@@ -252,6 +253,7 @@ __global__ void geglu_cols8_kernel(float* __restrict__ gate, const float* __rest
       }
     }
   }
+  if (po.n) __threadfence_system();  // (as in the GEMM epilogue: visible on the peers before the barrier kernel's flags)
 }
 
 // grid = (token tiles, row tiles) — the token tiles of one row tile run side by side, so its dequantized weights are
@@ -347,6 +349,9 @@ gemm_bf16_kernel(const uint8_t* __restrict__ A, const uint8_t* __restrict__ Bt, 
         }
       }
     }
+    // the peers' copies are system-scope visible before this grid can be seen as complete: the barrier kernel that
+    // follows raises the flags the peers' consumers wait for
+    if (po.n) __threadfence_system();
   }
   umma::tc_fence_before();
   __syncthreads();

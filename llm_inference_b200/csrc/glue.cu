@@ -871,6 +871,7 @@ __global__ void embed_shard_batch_kernel(EmbedArgs a, const int32_t* __restrict_
   const float v = dequant_elem(a, row - a.row_begin, e) * scale;
   for (uint32_t p = 0; p < peers.n; ++p)
     reinterpret_cast<float*>(reinterpret_cast<char*>(peers.base[p]) + h_byte_off)[size_t(m) * a.n_cols + e] = v;
+  __threadfence_system();
 }
 
 }  // namespace
