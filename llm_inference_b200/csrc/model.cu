@@ -513,10 +513,12 @@ int bx_exchange(llmi_model_s* m, std::initializer_list<BxBuf> bufs, uint32_t n_t
 int run_batch(llmi_model_s* m, const int32_t* toks, uint32_t n_tok, bool want_logits) {
   cudaStream_t s = m->stream;
   const uint32_t E = m->E, F = m->F, HD = m->H * m->D, KD = m->HK * m->D;
-  // Row-sharded model: every token-batched mat-vec computes this rank's rows of every token (the columns
-  // [row_begin, row_end) of the [n_tok][rows] batch) and bx_exchange all-gathers them over NVLink peer memory; norms,
-  // attention, GEGLU and the KV cache are replicated as in run_step.  A row is still computed start to finish on one
-  // device, so the batch is bit-identical to the single-GPU batch of the same mode.
+  // Row-sharded model: every token-batched mat-vec computes this rank's rows of every token (the
+  // columns [row_begin, row_end) of the [n_tok][rows] batch) and the column blocks are all-gathered over NVLink peer
+  // memory — by bx_exchange_kernel, or by the producer's own stores followed by the bare barrier.  GEGLU runs on the
+  // columns' owner, the main attention kernel with the rank's own heads, long batches' norm stages on a token slice
+  // per rank; the K/V prologue, the KV cache and the quantizers are replicated as in run_step.  Every value is still
+  // computed start to finish on one device, so the batch is bit-identical to the single-GPU batch of the same mode.
   const bool sh = m->sharded();
   if (sh && m->ll.peers.n != uint32_t(m->world))
     return llmi_fail(LLMI_ERR_STATE, "row-sharded model: llmi_model_comm_connect has not been called");
